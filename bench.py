@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — field gates evaluated / second on BASELINE.json's headline config (C3):
+a synthetic 2^24-gate Add/Mul/AssertZero circuit over the BLS12-381 scalar field (255-bit),
+a batch of 4096 independent witnesses sharded across N B200s (one process per GPU).
+
+One "step" = one satisfiability check of the whole batch against the relation.
+  value : whole-job gate-evaluations / s with the witness batch already resident in HBM
+  e2e   : the same through the C ABI call `zkb_evaluate` with HOST (pinned) witness buffers:
+          H2D of the witnesses + all kernels + D2H of the verdicts inside the timed region
+  --impl reference : the CPU restatement of the reference's evaluator (oracle/plaintext_flat.c;
+          the Rust binary cannot be built in this image) on all host threads, bounded sample.
+Relation flattening / levelization / program upload is one-off preparation, reported as prep_s.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-gates", type=int, default=24)
+    ap.add_argument("--witnesses", type=int, default=4096)
+    ap.add_argument("--inputs", type=int, default=1024)
+    ap.add_argument("--field", default="bls381", choices=["bls381", "bn254", "goldilocks"])
+    ap.add_argument("--cpu-sample-log2-gates", type=int, default=22)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+FIELD = {"bls381": 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
+         "bn254": 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
+         "goldilocks": (1 << 64) - (1 << 32) + 1}
+SEED = 0x5EED0003
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def host_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
+def cpu_reference_rate(circ_mod, flat, p, circuit, n_threads, log2_sample_gates, steps, warmup):
+    """Times the oracle (restatement of Evaluator<PlaintextBackend>) on a bounded sample:
+    the first 2^k counted gates of the SAME relation x n_threads witnesses, one witness per thread."""
+    g = circuit.gates
+    counted = np.isin(g["op"], [circ_mod.G_ADD, circ_mod.G_MUL, circ_mod.G_ASSERT_ZERO])
+    cum = np.cumsum(counted)
+    want = min(1 << log2_sample_gates, int(cum[-1]))
+    cut = int(np.searchsorted(cum, want, side="left")) + 1
+    sub = g[:cut]
+    n_counted = int(cum[cut - 1])
+    w = circ_mod.make_witnesses(circuit, n_threads, seed=SEED + 99)
+    eb = circ_mod.elem_bytes(p)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = flat.eval_batch(sub, circuit.const_pool, p.to_bytes(eb, "little"), None, w, n_threads, n_threads=n_threads)
+        dt = time.perf_counter() - t0
+        assert (res["status"] == 0).all(), "oracle found an unsatisfied witness in the baseline sample"
+        if it >= warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    rate = n_counted * n_threads / per_step
+    sample = f"first {n_counted} counted gates of the 2^{int(np.log2(circuit.n_gates))}-gate relation x {n_threads} witnesses (1 per thread)"
+    return rate, per_step, sample
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    p = FIELD[args.field]
+    n_gates = 1 << args.log2_gates
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    import zkb_loader
+    import importlib
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        zkb_loader.load()
+        circ_mod = importlib.import_module("zkir_b200.circuits")
+        from oracle import flat
+        flat.build()
+        circuit = circ_mod.random_circuit(n_gates, args.inputs, p, SEED)
+        nt = host_threads()
+        rate, per_step, sample = cpu_reference_rate(circ_mod, flat, p, circuit, nt, args.cpu_sample_log2_gates,
+                                                    args.steps, max(1, min(args.warmup, 1)))
+        line = {
+            "impl": "reference", "metric": "field gates evaluated/sec", "value": rate, "unit": "gate-evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field)",
+            "data": "synthetic",
+            "config": {"workload": f"C3: 2^{args.log2_gates}-gate random Add/Mul/AssertZero circuit, {args.field}, "
+                                   f"{args.witnesses} witnesses", "field": args.field},
+            "cpu_baseline": {"value": rate, "unit": "gate-evals/s", "cores": nt, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "gate-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of zki_sieve 3.0.0 Evaluator<PlaintextBackend> (oracle/plaintext_flat.c), not the Rust binary",
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    z = zkb_loader.load()
+    circ_mod = importlib.import_module("zkir_b200.circuits")
+
+    # ---- one-off preparation: relation -> levelized device program ---------------------------
+    t0 = time.perf_counter()
+    circuit = circ_mod.random_circuit(n_gates, args.inputs, p, SEED)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    be = z.GpuBackend(local_rank)
+    be.set_field(p)
+    be.push_gates(circuit.gates, circuit.const_pool)
+    be.finalize(keep_all_values=False)
+    t_prep = time.perf_counter() - t0
+    st = be.stats()
+
+    # ---- this rank's shard of the witness batch (contiguous block) ---------------------------
+    total_w = args.witnesses
+    lo = total_w * rank // world
+    hi = total_w * (rank + 1) // world
+    n_local = hi - lo
+    # 1 % of the witnesses are corrupted; their first failing assertion is known by construction
+    rng = np.random.default_rng(SEED + 1)
+    bad = rng.choice(total_w, size=max(1, total_w // 100), replace=False)
+    corrupt_global = {int(j): int(rng.integers(0, max(circuit.n_ties, 1))) for j in bad} if circuit.n_ties else {}
+    corrupt_local = {j - lo: k for j, k in corrupt_global.items() if lo <= j < hi}
+    w_np = circ_mod.make_witnesses(circuit, n_local, seed=SEED + 7 + rank, corrupt=corrupt_local)
+    eb = circ_mod.elem_bytes(p)
+    w_pinned = torch.empty(w_np.shape, dtype=torch.uint8, pin_memory=True)
+    w_pinned.numpy()[...] = w_np
+    w_host = w_pinned.numpy()
+    expected = circ_mod.expected_first_fail(circuit, n_local, corrupt_local)
+
+    def verdict_allreduce(v):
+        """the path's only collective: MIN-reduce of first_fail over the whole batch (NCCL over NVLink)"""
+        ff = np.where(v["ok"] == 1, np.int64(1) << 40, v["first_fail_seq"].astype(np.int64))
+        if world == 1:
+            return ff
+        full = torch.full((total_w,), 1 << 40, dtype=torch.int64, device="cuda")
+        full[lo:hi] = torch.from_numpy(ff).cuda()
+        dist.all_reduce(full, op=dist.ReduceOp.MIN)
+        return full.cpu().numpy()
+
+    def check(ff_local):
+        got = np.where(ff_local >= (1 << 40), -1, ff_local)
+        assert (got == expected).all(), f"rank {rank}: verdicts differ from the constructed expectation"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gate_evals_local = circuit.n_gates * n_local
+    gate_evals_total = circuit.n_gates * total_w
+
+    def timed(fn, steps):
+        barrier()
+        dev_ms = 0.0
+        lv_ms = 0.0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            v = fn()
+            tm = be.timing()
+            dev_ms += tm["total_ms"]
+            lv_ms += tm["levels_ms"]
+            ff = verdict_allreduce(v)
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([dev_ms, wall * 1e3, lv_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item(), t[1].item(), t[2].item(), ff, v
+
+    # ---- value: inputs resident in HBM -----------------------------------------------------------
+    be.upload_inputs(None, w_host, n_local)
+    for _ in range(args.warmup):
+        v = be.run()
+    check(np.where(v["ok"] == 1, np.int64(1) << 40, v["first_fail_seq"].astype(np.int64)))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, wall_ms, lv_ms, ff, v = timed(be.run, args.steps)
+    launches = be.timing()["kernel_launches"] * args.steps
+    level_launches = be.timing()["level_launches"]
+    ms_per_step = dev_ms / args.steps
+    value = gate_evals_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI --------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        be.evaluate(None, w_host, n_local)
+    e_dev_ms, e_wall_ms, _, ff2, v2 = timed(lambda: be.evaluate(None, w_host, n_local), args.steps)
+    sampler.stop_flag = True
+    e2e_ms = max(e_dev_ms, 0.0) / args.steps
+    e2e_value = gate_evals_total / (e2e_ms * 1e-3)
+    check(np.where(v2["ok"] == 1, np.int64(1) << 40, v2["first_fail_seq"].astype(np.int64)))
+    if world > 1:
+        n_false = int((ff2 < (1 << 40)).sum())
+        assert n_false == len(corrupt_global), (n_false, len(corrupt_global))
+
+    # ---- roofline of the dominant kernel (k_level<8,false>) ----------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    algo_bytes_step = st["algo_bytes_per_witness"] * n_local            # this rank
+    lv_ms_step = lv_ms / args.steps
+    achieved = algo_bytes_step / (lv_ms_step * 1e-3) / 1e9 if lv_ms_step > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_level<8,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes_step / max(level_launches, 1),
+                "avg_launch_ms": lv_ms_step / max(level_launches, 1), "launches_per_step": level_launches,
+                "bytes_per_gate_eval": st["algo_bytes_per_witness"] / circuit.n_gates}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("k_level_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import flat
+        nt = host_threads()
+        rate, per_step, sample = cpu_reference_rate(circ_mod, flat, p, circuit, nt, args.cpu_sample_log2_gates, 1, 0)
+        cpu_baseline = {"value": rate, "unit": "gate-evals/s", "cores": nt, "kind": "port", "sample": sample,
+                        "seconds": per_step}
+
+    if rank == 0:
+        line = {
+            "metric": "field gates evaluated/sec", "value": value, "unit": "gate-evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field, Montgomery)" if eb == 32 else f"u32x{eb // 4}",
+            "data": "synthetic",
+            "config": {"workload": f"C3: 2^{args.log2_gates}-gate random Add/Mul/AssertZero circuit over {args.field}, "
+                                   f"{total_w} witnesses sharded over {world} GPU(s)",
+                       "gates": circuit.n_gates, "gate_histogram": circuit.hist, "witnesses": total_w,
+                       "witness_inputs": args.inputs, "levels": st["n_levels"], "tile_witnesses": st["tile_witnesses"],
+                       "tiles_per_rank": st["n_tiles"], "wire_store_gb": st["n_slots"] * eb * st["tile_witnesses"] / 1e9,
+                       "l2": "working set (wire store) is >> L2, no flush needed", "parallelism": f"witness-shard x{world}"},
+            "e2e": {"value": e2e_value, "unit": "gate-evals/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(w_host.nbytes) * world, "d2h_bytes_per_step": 4 * total_w + 4 * world},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary(),
+            "prep_s": {"generate_circuit": t_gen, "flatten_levelize_upload": t_prep},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "verdicts": {"true": int((ff >= (1 << 40)).sum()), "false": int((ff < (1 << 40)).sum())},
+        }
+        print(json.dumps(line))
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,237 @@
+/* zkb.h — C ABI of the B200 satisfiability evaluator for the zkInterface SIEVE IR.
+ *
+ * This is the drop-in boundary for ONE path of the reference (dryajov/zkinterface-ir,
+ * `zki_sieve` 3.0.0): what `zki_sieve evaluate` does through
+ * `Evaluator<PlaintextBackend>` (rust/src/consumers/evaluator.rs), i.e. gate-by-gate
+ * evaluation of a relation against instance/witness values, for a whole BATCH of
+ * witnesses at once on the GPU.  Plain pointers and sizes only; every entry point
+ * cites the reference interface it replaces.  A Rust `impl ZKBackend for GpuBackend`
+ * binds section 2 one-to-one; section 4 mirrors `Evaluator` +
+ * `Source` for callers that start from `.sieve` bytes.
+ *
+ * Conventions
+ *   - every function returns ZKB_OK (0) or a negative zkb_status; the message is
+ *     available from zkb_last_error(ctx) until the next call on that ctx.
+ *     (reference: `Result<T> = Result<T, Box<dyn Error>>`, rust/src/lib.rs:47)
+ *   - an UNSATISFIED statement is not an error: it is reported in zkb_verdict.
+ *   - field elements cross the boundary as little-endian byte strings
+ *     (`Value`, rust/src/structs/value.rs:11); trailing zeros optional.
+ *   - the caller owns all buffers it passes; the library copies what it keeps.
+ *   - one ctx = one host thread + one device.  Not thread-safe; contexts are independent.
+ *   - there is NO CPU fallback: evaluation entry points fail with ZKB_E_CUDA when the
+ *     context has no CUDA device.
+ */
+#ifndef ZKB_H
+#define ZKB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ZKB_OK = 0,
+    ZKB_E_ARG = -1,          /* bad argument / call order */
+    ZKB_E_FORMAT = -2,       /* malformed .sieve message (reference: Err("Missing ...")) */
+    ZKB_E_SEMANTIC = -3,     /* evaluation error the reference reports as a violation string */
+    ZKB_E_CUDA = -4,         /* CUDA runtime failure or no device */
+    ZKB_E_FATAL = -5,        /* condition on which the reference PANICS (same text) */
+    ZKB_E_UNSUPPORTED = -6   /* outside the device path (field wider than 256 bits, even modulus != 2, ...) */
+} zkb_status;
+
+typedef struct zkb_ctx zkb_ctx;
+
+/* ZKBackend::Wire of the GPU backend: an SSA value handle (evaluator.rs:18). */
+typedef uint64_t zkb_wire;
+
+/* ------------------------------------------------------------------ 1. lifecycle */
+/* device >= 0: CUDA device ordinal.  device < 0: host-only context (record / plan /
+ * inspect; every evaluation call fails with ZKB_E_CUDA). */
+zkb_ctx* zkb_create(int device);
+void zkb_destroy(zkb_ctx* ctx);
+const char* zkb_last_error(zkb_ctx* ctx);
+
+/* ------------------------------------------------------------------ 2. ZKBackend seam
+ * One function per method of `trait ZKBackend` (evaluator.rs:17-76).  The backend is
+ * DEFERRED: each call records one SSA op and returns its handle; nothing is computed
+ * until zkb_evaluate.  `assert_zero` therefore always returns ZKB_OK — the verdict
+ * (which assertion failed first, per witness) comes back from zkb_evaluate. */
+
+/* ZKBackend::set_field (evaluator.rs:28; PlaintextBackend :866-875: "Modulus cannot be
+ * zero." / "Field should be of degree 1"). */
+int zkb_set_field(zkb_ctx* ctx, const uint8_t* modulus_le, size_t len, uint32_t degree, int is_boolean);
+/* ZKBackend::one / minus_one / zero (evaluator.rs:31-35): little-endian bytes into out[cap]. */
+int zkb_one(zkb_ctx* ctx, uint8_t* out_le, size_t cap, size_t* len);
+int zkb_minus_one(zkb_ctx* ctx, uint8_t* out_le, size_t cap, size_t* len);
+int zkb_zero(zkb_ctx* ctx, uint8_t* out_le, size_t cap, size_t* len);
+/* ZKBackend::copy (evaluator.rs:38) — an alias: returns the same handle. */
+int zkb_copy(zkb_ctx* ctx, zkb_wire a, zkb_wire* out);
+/* ZKBackend::constant (evaluator.rs:41). */
+int zkb_constant(zkb_ctx* ctx, const uint8_t* val_le, size_t len, zkb_wire* out);
+/* ZKBackend::assert_zero (evaluator.rs:46).  src_wire_id: the IR wire id the Evaluator
+ * would print in "Wire_{id} (may be weighted) should be 0, while it is not" (:357-362). */
+int zkb_assert_zero(zkb_ctx* ctx, zkb_wire a, uint64_t src_wire_id);
+/* ZKBackend::add / multiply / add_constant / mul_constant (evaluator.rs:49-55). */
+int zkb_add(zkb_ctx* ctx, zkb_wire a, zkb_wire b, zkb_wire* out);
+int zkb_multiply(zkb_ctx* ctx, zkb_wire a, zkb_wire b, zkb_wire* out);
+int zkb_add_constant(zkb_ctx* ctx, zkb_wire a, const uint8_t* val_le, size_t len, zkb_wire* out);
+int zkb_mul_constant(zkb_ctx* ctx, zkb_wire a, const uint8_t* val_le, size_t len, zkb_wire* out);
+/* ZKBackend::and / xor / not (evaluator.rs:58-62). */
+int zkb_and(zkb_ctx* ctx, zkb_wire a, zkb_wire b, zkb_wire* out);
+int zkb_xor(zkb_ctx* ctx, zkb_wire a, zkb_wire b, zkb_wire* out);
+int zkb_not(zkb_ctx* ctx, zkb_wire a, zkb_wire* out);
+/* ZKBackend::instance / witness (evaluator.rs:66-75).  The VALUE is not passed here: the
+ * call reserves the next position of the instance / witness stream, and the values of all
+ * witnesses of a batch are supplied to zkb_evaluate (consumption is data-independent, so
+ * one recorded program serves every witness). */
+int zkb_instance(zkb_ctx* ctx, zkb_wire* out);
+int zkb_witness(zkb_ctx* ctx, zkb_wire* out);
+
+/* ------------------------------------------------------------------ 3. bulk gates, evaluation */
+
+/* Flat gates = the simple arms of Evaluator::ingest_gate (evaluator.rs:344-439), as an
+ * array.  Wire ids are IR wire ids of ONE scope (re-usable after FREE); errors and their
+ * texts follow evaluator.rs:775-797 ("Wire_{id} already has a value in this scope." /
+ * "No value given for wire_{id}"). */
+typedef enum {
+    ZKB_G_CONSTANT = 1, /* out, b = index into the constant pool      gates.rs:20 */
+    ZKB_G_ASSERT_ZERO,  /* a                                            gates.rs:22 */
+    ZKB_G_COPY,         /* out, a */
+    ZKB_G_ADD,          /* out, a, b */
+    ZKB_G_MUL,          /* out, a, b */
+    ZKB_G_ADD_CONSTANT, /* out, a, b = constant-pool index */
+    ZKB_G_MUL_CONSTANT, /* out, a, b = constant-pool index */
+    ZKB_G_AND,          /* out, a, b */
+    ZKB_G_XOR,          /* out, a, b */
+    ZKB_G_NOT,          /* out, a */
+    ZKB_G_INSTANCE,     /* out */
+    ZKB_G_WITNESS,      /* out */
+    ZKB_G_FREE          /* a = first, b = last (inclusive; b < a frees nothing) */
+} zkb_gate_op;          /* same numbering as DirectiveSet 1..13, sieve_ir_generated.rs:422-442 */
+
+typedef struct {
+    uint8_t op; /* zkb_gate_op */
+    uint8_t pad[3];
+    uint32_t out;
+    uint32_t a;
+    uint32_t b;
+} zkb_gate;
+
+/* const_pool_le: n_consts values of const_stride bytes each (little-endian). */
+int zkb_push_gates(zkb_ctx* ctx, const zkb_gate* gates, uint64_t n_gates, const uint8_t* const_pool_le,
+                   size_t const_stride, uint64_t n_consts);
+
+/* Host preparation: levelize the recorded SSA list into wavefronts, assign wire-store slots,
+ * fuse assertions, upload the device program.  keep_all_values != 0 keeps every recorded
+ * value readable through zkb_read_values (needed for wire-by-wire parity checks). */
+int zkb_finalize(zkb_ctx* ctx, int keep_all_values);
+
+typedef struct {
+    uint8_t ok; /* 1: every assertion holds for this witness (the statement is TRUE) */
+    uint8_t pad[7];
+    uint64_t first_fail_seq; /* index (program order) of the first failing assert_zero; UINT64_MAX if none */
+} zkb_verdict;
+
+/* Evaluate the program for n_batch independent (instance, witness) pairs.
+ *   instances_le : n_instance values of value_stride bytes per pair; pair j at
+ *                  instances_le + j*instance_set_stride (instance_set_stride 0: one shared vector)
+ *   witnesses_le : likewise for the short witness.
+ * Timed end-to-end by bench.py: H2D of inputs, all kernels, D2H of the verdicts.
+ * Replaces the per-gate loop Evaluator::ingest_relation -> ingest_gate -> PlaintextBackend
+ * (evaluator.rs:288-301, 318-439, 908-938). */
+int zkb_evaluate(zkb_ctx* ctx, const uint8_t* instances_le, uint64_t instance_set_stride, const uint8_t* witnesses_le,
+                 uint64_t witness_set_stride, uint32_t value_stride, uint32_t n_batch, zkb_verdict* out);
+/* The same in two steps, so a caller can keep inputs resident in HBM and re-run. */
+int zkb_upload_inputs(zkb_ctx* ctx, const uint8_t* instances_le, uint64_t instance_set_stride, const uint8_t* witnesses_le,
+                      uint64_t witness_set_stride, uint32_t value_stride, uint32_t n_batch);
+int zkb_run(zkb_ctx* ctx, zkb_verdict* out);
+
+/* IR wire id recorded with assertion `seq` (for the reference's violation text). */
+int zkb_assert_info(zkb_ctx* ctx, uint64_t seq, uint64_t* src_wire_id);
+/* Error found while RECORDING (e.g. "No value given for wire_7"); the reference reports it as
+ * the violation unless an assertion failed earlier in program order.  NULL if none. */
+const char* zkb_pending_error(zkb_ctx* ctx);
+
+/* Canonical residues (little-endian, `stride` bytes each, zero padded) of recorded values for
+ * witness batch_idx of the last evaluation — what Evaluator::get (evaluator.rs:750-752) returns
+ * for wires bound to those values.  Requires zkb_finalize(ctx, 1). */
+int zkb_read_values(zkb_ctx* ctx, uint32_t batch_idx, const zkb_wire* values, uint64_t n, uint8_t* out_le, size_t stride);
+/* value currently bound to IR wire id `wire` in the flat scope of zkb_push_gates */
+int zkb_scope_lookup(zkb_ctx* ctx, uint64_t wire, zkb_wire* out);
+
+typedef struct {
+    uint64_t n_values;      /* SSA values recorded */
+    uint64_t n_asserts;
+    uint64_t n_instance;    /* values consumed from the instance stream per pair */
+    uint64_t n_witness;
+    uint64_t n_consts;
+    uint64_t ir_gates;      /* Add/Mul/AddConstant/MulConstant/And/Xor/Not/AssertZero gates ingested */
+    uint64_t callbacks[12]; /* constant, instance, witness, add, mul, addc, mulc, and, xor, not, copy, assert_zero */
+    uint64_t n_slots;       /* wire-store slots (after finalize) */
+    uint64_t n_levels;
+    uint64_t n_device_ops;
+    uint64_t algo_bytes_per_witness; /* SURVEY.md section 8d algorithmic bytes */
+    uint32_t nlimb;         /* 32-bit limbs per element (0 before set_field) */
+    uint32_t binary;        /* p == 2 */
+    uint32_t tile_witnesses;/* witnesses resident per pass (after upload) */
+    uint32_t n_tiles;
+} zkb_stats;
+int zkb_get_stats(zkb_ctx* ctx, zkb_stats* out);
+
+typedef struct {
+    float h2d_ms;       /* input upload */
+    float load_ms;      /* input-conversion kernels */
+    float levels_ms;    /* all level kernels (CUDA events on the library's stream) */
+    float total_ms;     /* first byte uploaded .. verdicts on host */
+    uint64_t level_launches;
+    uint64_t kernel_launches;
+} zkb_timing;
+int zkb_get_timing(zkb_ctx* ctx, zkb_timing* out);
+
+/* ------------------------------------------------------------------ 4. Evaluator / Source
+ * Mirror of `Evaluator<B>` (evaluator.rs:158-753) driven from `.sieve` bytes, with `Source`
+ * (rust/src/consumers/source.rs:59-118) file discovery and ordering.  The evaluator records
+ * into `backend`; get_violations triggers the GPU evaluation and reproduces the reference's
+ * violation strings (evaluator.rs:199-208, 357-362). */
+typedef struct zkb_evaluator zkb_evaluator;
+zkb_evaluator* zkb_evaluator_create(zkb_ctx* backend);
+void zkb_evaluator_destroy(zkb_evaluator* ev);
+/* Evaluator::ingest_message on ONE size-prefixed FlatBuffers message (Message::try_from). */
+int zkb_evaluator_ingest_message(zkb_evaluator* ev, const uint8_t* buf, size_t len);
+/* Source::from_buffers + iter_messages: a concatenation of size-prefixed messages. */
+int zkb_evaluator_ingest_buffer(zkb_evaluator* ev, const uint8_t* buf, size_t len);
+/* Source::from_dirs_and_files + Evaluator::from_messages: files / directories of *.sieve,
+ * ordered instance < witness < relation (source.rs:69-89). */
+int zkb_evaluator_ingest_paths(zkb_evaluator* ev, const char* const* paths, size_t n_paths);
+/* Evaluator::get_violations: evaluates (once) and returns the number of violation strings. */
+int zkb_evaluator_get_violations(zkb_evaluator* ev, size_t* n_violations);
+const char* zkb_evaluator_violation(zkb_evaluator* ev, size_t i);
+/* Evaluator::get(id): canonical little-endian residue of a live top-scope wire. */
+int zkb_evaluator_get_wire(zkb_evaluator* ev, uint64_t wire_id, uint8_t* out_le, size_t cap, size_t* len);
+const char* zkb_evaluator_last_error(zkb_evaluator* ev);
+
+/* ------------------------------------------------------------------ 5. R1CS (Az o Bz = Cz)
+ * The satisfiability check that `zkif-to-ir` + `evaluate` performs gate by gate on an R1CS
+ * (rust/src/producers/from_r1cs.rs:110-125), done as three CSR sparse mod-p mat-vecs and a
+ * fused Hadamard check.  Row r holds  (A_r . z)(B_r . z) - (C_r . z) == 0 (mod p). */
+typedef struct {
+    uint64_t n_rows;
+    const uint64_t* row_ptr;  /* n_rows + 1 */
+    const uint32_t* col;      /* variable ids, nnz */
+    const uint32_t* coef_idx; /* index into the coefficient table, nnz */
+} zkb_csr;
+int zkb_r1cs_load(zkb_ctx* ctx, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C, const uint8_t* coef_table_le,
+                  size_t coef_stride, uint64_t n_coefs, uint64_t n_vars);
+/* z_le: n_batch assignment vectors of n_vars values (z[0] must be 1), value_stride bytes each.
+ * verdict.first_fail_seq = first violated row. */
+int zkb_r1cs_check(zkb_ctx* ctx, const uint8_t* z_le, uint64_t z_set_stride, uint32_t value_stride, uint32_t n_batch,
+                   zkb_verdict* out);
+int zkb_r1cs_upload(zkb_ctx* ctx, const uint8_t* z_le, uint64_t z_set_stride, uint32_t value_stride, uint32_t n_batch);
+int zkb_r1cs_run(zkb_ctx* ctx, zkb_verdict* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB_H */

@@ -1,0 +1,183 @@
+"""GPU parity of flat relations: CUDA path (through the C ABI) vs the C/Python oracle.
+Bit-exact verdicts, first failing assertion and wire values."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import FIELDS, circuits, random_flat_program, zkb
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import flat
+    return flat
+
+
+def _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0,), keep_all=True):
+    z = zkb()
+    flat = _oracle()
+    eb = c.elem_bytes(p)
+    b = z.GpuBackend(0)
+    b.set_field(p)
+    b.push_gates(gates, pool)
+    b.finalize(keep_all_values=keep_all)
+    v = b.evaluate(inst, wit, n_batch)
+    ref = flat.eval_batch(gates, pool, p.to_bytes(eb, "little"), inst, wit, n_batch, n_threads=4)
+    for j in range(n_batch):
+        ok_ref = int(ref[j]["status"]) == flat.EV_TRUE
+        assert bool(v[j]["ok"]) == ok_ref, (j, v[j], ref[j])
+        if not ok_ref:
+            assert int(ref[j]["status"]) == flat.EV_ASSERT_FAILED
+            assert int(v[j]["first_fail_seq"]) == int(ref[j]["fail_assert_seq"]), (j, v[j], ref[j])
+            assert b.assert_wire(int(v[j]["first_fail_seq"])) == int(ref[j]["fail_wire"])
+    for j in sample:
+        if int(ref[j]["status"]) != flat.EV_TRUE:
+            continue   # wires after the first failure are undefined in the reference
+        _, dump = flat.eval_dump(gates, pool, p.to_bytes(eb, "little"), None if inst is None else (inst if inst.ndim == 2 else inst[j]),
+                                 None if wit is None else wit[j], n_wires, stride=eb)
+        live = [i for i in range(n_wires) if not (dump[i] == 0xFF).all() or p == (1 << 256) - 1]
+        if keep_all:
+            vals = b.read_values(j, [b.scope_lookup(i) for i in live], eb)
+            for i, val in zip(live, vals):
+                assert val == int.from_bytes(dump[i].tobytes(), "little"), (j, i)
+    st = b.stats()
+    b.close()
+    return v, ref, st
+
+
+@pytest.mark.parametrize("name", list(FIELDS))
+@pytest.mark.parametrize("n_batch", [1, 37])
+def test_random_circuit_all_fields(name, n_batch):
+    c = circuits()
+    p = FIELDS[name]
+    circ = c.random_circuit(3000, 48, p, seed=11 + n_batch, n_ties=6)
+    corrupt = {0: 1} if n_batch == 1 else {2: 0, 5: 3, 36: 5}
+    w = c.make_witnesses(circ, n_batch, seed=5, corrupt=corrupt)
+    v, ref, _ = _check(c, circ.gates, circ.const_pool, p, None, w, n_batch, circ.n_wires,
+                       sample=(0, 1) if n_batch > 1 else (0,))
+    exp = c.expected_first_fail(circ, n_batch, corrupt)
+    for j in range(n_batch):
+        assert (int(v[j]["first_fail_seq"]) if not v[j]["ok"] else -1) == exp[j]
+
+
+def test_true_single_witness_values():
+    c = circuits()
+    p = FIELDS["bls381"]
+    circ = c.random_circuit(5000, 32, p, seed=3, n_ties=4)
+    w = c.make_witnesses(circ, 1, seed=9)
+    v, _, st = _check(c, circ.gates, circ.const_pool, p, None, w, 1, circ.n_wires)
+    assert v[0]["ok"] == 1
+    assert st["ir_gates"] == 5000
+
+
+@pytest.mark.parametrize("tile_log2", ["0", "2", "5"])
+def test_multi_tile_batches(tile_log2, monkeypatch):
+    # force small tiles so a batch takes several passes, with a ragged last tile
+    monkeypatch.setenv("ZKB_TILE_LOG2", tile_log2)
+    c = circuits()
+    p = FIELDS["bn254"]
+    circ = c.random_circuit(1500, 40, p, seed=21, n_ties=5)
+    n_batch = 77
+    corrupt = {0: 0, 31: 2, 32: 4, 76: 1}
+    w = c.make_witnesses(circ, n_batch, seed=6, corrupt=corrupt)
+    v, _, st = _check(c, circ.gates, circ.const_pool, p, None, w, n_batch, circ.n_wires, sample=(1, 33, 75))
+    assert st["tile_witnesses"] == 1 << int(tile_log2)
+
+
+@pytest.mark.parametrize("name", ["p101", "goldilocks", "bls381", "p256full"])
+@pytest.mark.parametrize("bool_ops", [False, True])
+def test_every_gate_kind_with_wire_reuse(name, bool_ops):
+    c = circuits()
+    p = FIELDS[name]
+    eb = c.elem_bytes(p)
+    gates, pool, n_wires = random_flat_program(p, 1200, 5, 7, seed=hash(name) % 1000 + bool_ops, bool_ops=bool_ops)
+    rng = np.random.default_rng(4)
+    n_batch = 9
+    inst = c.random_field_elements(rng, (5,), p)            # shared instance
+    wit = c.random_field_elements(rng, (n_batch, 7), p)
+    _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0, 8))
+    inst2 = c.random_field_elements(rng, (n_batch, 5), p)   # per-witness instances
+    _check(c, gates, pool, p, inst2, wit, n_batch, n_wires, sample=(3,))
+
+
+def test_binary_field_flat():
+    c = circuits()
+    p = 2
+    gates, pool, n_wires = random_flat_program(p, 2000, 6, 10, seed=77, bool_ops=True)
+    rng = np.random.default_rng(1)
+    n_batch = 70
+    inst = rng.integers(0, 2, size=(n_batch, 6, 1), dtype=np.uint8)
+    wit = rng.integers(0, 2, size=(n_batch, 10, 1), dtype=np.uint8)
+    _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0, 31, 32, 69))
+
+
+def test_structural_errors_match_reference_text():
+    z = zkb()
+    c = circuits()
+    g = np.zeros(2, dtype=c.GATE_DTYPE)
+    g["op"] = [c.G_WITNESS, c.G_ADD]
+    g["out"] = [0, 1]
+    g["a"] = [0, 0]
+    g["b"] = [0, 7]
+    b = z.GpuBackend(0)
+    b.set_field(101)
+    with pytest.raises(z.ZkbError) as e:
+        b.push_gates(g)
+    assert str(e.value) == "No value given for wire_7"
+    assert b.pending_error() == "No value given for wire_7"
+    b2 = z.GpuBackend(0)
+    b2.set_field(101)
+    g["b"] = [0, 0]
+    g["out"] = [0, 0]
+    with pytest.raises(z.ZkbError) as e:
+        b2.push_gates(g)
+    assert str(e.value) == "Wire_0 already has a value in this scope."
+
+
+def test_unreduced_inputs_keep_raw_semantics():
+    # SURVEY.md 8a trap 1: a witness equal to p fails AssertZero in the reference (raw integer != 0)
+    z = zkb()
+    c = circuits()
+    flat = _oracle()
+    p = 101
+    g = np.zeros(5, dtype=c.GATE_DTYPE)
+    g["op"] = [c.G_WITNESS, c.G_WITNESS, c.G_ADD, c.G_ASSERT_ZERO, c.G_ASSERT_ZERO]
+    g["out"] = [0, 1, 2, 0, 0]
+    g["a"] = [0, 0, 0, 2, 1]
+    g["b"] = [0, 0, 1, 0, 0]
+    wit = np.zeros((3, 2, 4), dtype=np.uint8)
+    wit[0, 0, 0], wit[0, 1, 0] = 0, 0        # TRUE
+    wit[1, 0, 0], wit[1, 1, 0] = 101, 0      # 101 + 0 = 0 mod p: first assert holds; TRUE
+    wit[2, 0, 0], wit[2, 1, 0] = 0, 101      # second assert tests the RAW witness 101 != 0: FALSE at seq 1
+    b = z.GpuBackend(0)
+    b.set_field(p)
+    b.push_gates(g)
+    b.finalize(True)
+    v = b.evaluate(None, wit, 3)
+    ref = flat.eval_batch(g, None, bytes([101]), None, wit, 3)
+    assert [int(r["status"]) for r in ref] == [0, 0, 1]
+    assert [int(x["ok"]) for x in v] == [1, 1, 0]
+    assert int(v[2]["first_fail_seq"]) == 1 == int(ref[2]["fail_assert_seq"])
+    # read-back of an unreduced input returns the raw value, like Evaluator::get
+    assert b.read_values(1, [b.scope_lookup(0)], 4) == [101]
+
+
+def test_run_twice_device_resident():
+    z = zkb()
+    c = circuits()
+    p = FIELDS["bls381"]
+    circ = c.random_circuit(2000, 32, p, seed=5, n_ties=4)
+    w = c.make_witnesses(circ, 16, seed=1, corrupt={7: 1})
+    b = z.GpuBackend(0)
+    b.set_field(p)
+    b.push_gates(circ.gates, circ.const_pool)
+    b.finalize(False)
+    b.upload_inputs(None, w, 16)
+    v1 = b.run()
+    v2 = b.run()
+    assert (v1 == v2).all()
+    assert int(v1[7]["first_fail_seq"]) == int(circ.tie_assert_seq[1])
+    t = b.timing()
+    assert t["level_launches"] > 0 and t["levels_ms"] > 0

@@ -1,0 +1,442 @@
+"""zkb — B200-native satisfiability evaluator for the zkInterface SIEVE IR.
+
+Host-side mirror of the reference's evaluation interface, over the C ABI of
+`libzkb.so` (include/zkb.h):
+
+  GpuBackend   `trait ZKBackend` (rust/src/consumers/evaluator.rs:17-76): same
+               method names and argument meaning; deferred (records SSA ops),
+               evaluated for a whole batch of witnesses by `evaluate`.
+  Evaluator    `Evaluator<B>` (evaluator.rs:158-753): from_messages /
+               ingest_message / get_violations / get, driven from `.sieve` bytes.
+  Source       `Source` (rust/src/consumers/source.rs:59-118).
+
+There is NO CPU fallback: without the CUDA library this module fails to import,
+and without a GPU every evaluation call raises `ZkbError`.
+
+The directory name contains a hyphen, so import it through `zkb_loader.load()`
+(repo root) or `importlib`; it registers itself as module `zkir_b200`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+_lib = C.CDLL(LIB_PATH)
+
+ZKB_OK, ZKB_E_ARG, ZKB_E_FORMAT, ZKB_E_SEMANTIC, ZKB_E_CUDA, ZKB_E_FATAL, ZKB_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+UINT64_MAX = (1 << 64) - 1
+
+# zkb_gate_op
+(G_CONSTANT, G_ASSERT_ZERO, G_COPY, G_ADD, G_MUL, G_ADD_CONSTANT, G_MUL_CONSTANT, G_AND, G_XOR, G_NOT, G_INSTANCE,
+ G_WITNESS, G_FREE) = range(1, 14)
+
+GATE_DTYPE = np.dtype([("op", "u1"), ("pad", "u1", (3,)), ("out", "<u4"), ("a", "<u4"), ("b", "<u4")])
+VERDICT_DTYPE = np.dtype([("ok", "u1"), ("pad", "u1", (7,)), ("first_fail_seq", "<u8")])
+
+
+class ZkbStats(C.Structure):
+    _fields_ = [("n_values", C.c_uint64), ("n_asserts", C.c_uint64), ("n_instance", C.c_uint64),
+                ("n_witness", C.c_uint64), ("n_consts", C.c_uint64), ("ir_gates", C.c_uint64),
+                ("callbacks", C.c_uint64 * 12), ("n_slots", C.c_uint64), ("n_levels", C.c_uint64),
+                ("n_device_ops", C.c_uint64), ("algo_bytes_per_witness", C.c_uint64), ("nlimb", C.c_uint32),
+                ("binary", C.c_uint32), ("tile_witnesses", C.c_uint32), ("n_tiles", C.c_uint32)]
+
+
+class ZkbTiming(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("load_ms", C.c_float), ("levels_ms", C.c_float), ("total_ms", C.c_float),
+                ("level_launches", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+class ZkbCsr(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("row_ptr", C.c_void_p), ("col", C.c_void_p), ("coef_idx", C.c_void_p)]
+
+
+CALLBACK_NAMES = ["constant", "instance", "witness", "add", "mul", "addc", "mulc", "and", "xor", "not", "copy",
+                  "assert_zero"]
+
+# every symbol include/zkb.h declares (tests check the library exports all of them)
+EXPORTED = [
+    "zkb_create", "zkb_destroy", "zkb_last_error", "zkb_set_field", "zkb_one", "zkb_minus_one", "zkb_zero", "zkb_copy",
+    "zkb_constant", "zkb_assert_zero", "zkb_add", "zkb_multiply", "zkb_add_constant", "zkb_mul_constant", "zkb_and",
+    "zkb_xor", "zkb_not", "zkb_instance", "zkb_witness", "zkb_push_gates", "zkb_finalize", "zkb_evaluate",
+    "zkb_upload_inputs", "zkb_run", "zkb_assert_info", "zkb_pending_error", "zkb_read_values", "zkb_scope_lookup",
+    "zkb_get_stats", "zkb_get_timing", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
+    "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
+    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
+    "zkb_r1cs_upload", "zkb_r1cs_run",
+]
+
+_vp, _u8p, _sz, _u64, _u32, _i = C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
+_u64p = C.POINTER(C.c_uint64)
+
+
+def _sig(name, restype, *argtypes):
+    f = getattr(_lib, name)
+    f.restype = restype
+    f.argtypes = list(argtypes)
+    return f
+
+
+_sig("zkb_create", _vp, _i)
+_sig("zkb_destroy", None, _vp)
+_sig("zkb_last_error", C.c_char_p, _vp)
+_sig("zkb_pending_error", C.c_char_p, _vp)
+_sig("zkb_set_field", _i, _vp, _u8p, _sz, _u32, _i)
+for _n in ("zkb_one", "zkb_minus_one", "zkb_zero"):
+    _sig(_n, _i, _vp, _u8p, _sz, C.POINTER(C.c_size_t))
+_sig("zkb_copy", _i, _vp, _u64, _u64p)
+_sig("zkb_constant", _i, _vp, _u8p, _sz, _u64p)
+_sig("zkb_assert_zero", _i, _vp, _u64, _u64)
+for _n in ("zkb_add", "zkb_multiply", "zkb_and", "zkb_xor"):
+    _sig(_n, _i, _vp, _u64, _u64, _u64p)
+for _n in ("zkb_add_constant", "zkb_mul_constant"):
+    _sig(_n, _i, _vp, _u64, _u8p, _sz, _u64p)
+_sig("zkb_not", _i, _vp, _u64, _u64p)
+_sig("zkb_instance", _i, _vp, _u64p)
+_sig("zkb_witness", _i, _vp, _u64p)
+_sig("zkb_push_gates", _i, _vp, _vp, _u64, _u8p, _sz, _u64)
+_sig("zkb_finalize", _i, _vp, _i)
+_sig("zkb_evaluate", _i, _vp, _u8p, _u64, _u8p, _u64, _u32, _u32, _vp)
+_sig("zkb_upload_inputs", _i, _vp, _u8p, _u64, _u8p, _u64, _u32, _u32)
+_sig("zkb_run", _i, _vp, _vp)
+_sig("zkb_assert_info", _i, _vp, _u64, _u64p)
+_sig("zkb_read_values", _i, _vp, _u32, _vp, _u64, _u8p, _sz)
+_sig("zkb_scope_lookup", _i, _vp, _u64, _u64p)
+_sig("zkb_get_stats", _i, _vp, C.POINTER(ZkbStats))
+_sig("zkb_get_timing", _i, _vp, C.POINTER(ZkbTiming))
+_sig("zkb_evaluator_create", _vp, _vp)
+_sig("zkb_evaluator_destroy", None, _vp)
+_sig("zkb_evaluator_ingest_message", _i, _vp, _u8p, _sz)
+_sig("zkb_evaluator_ingest_buffer", _i, _vp, _u8p, _sz)
+_sig("zkb_evaluator_ingest_paths", _i, _vp, C.POINTER(C.c_char_p), _sz)
+_sig("zkb_evaluator_get_violations", _i, _vp, C.POINTER(C.c_size_t))
+_sig("zkb_evaluator_violation", C.c_char_p, _vp, _sz)
+_sig("zkb_evaluator_get_wire", _i, _vp, _u64, _u8p, _sz, C.POINTER(C.c_size_t))
+_sig("zkb_evaluator_last_error", C.c_char_p, _vp)
+_sig("zkb_r1cs_load", _i, _vp, C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), _u8p, _sz, _u64, _u64)
+_sig("zkb_r1cs_check", _i, _vp, _u8p, _u64, _u32, _u32, _vp)
+_sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
+_sig("zkb_r1cs_run", _i, _vp, _vp)
+
+
+class ZkbError(Exception):
+    """Non-zero zkb_status; `.code` is the status, str() the library's message
+    (the reference's own error text where the reference has one)."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _buf(b) -> C.c_void_p:
+    """pointer to the bytes of a bytes / bytearray / numpy array (kept alive by the caller)"""
+    if b is None:
+        return None
+    if isinstance(b, np.ndarray):
+        return b.ctypes.data_as(C.c_void_p)
+    if isinstance(b, bytes):
+        return C.cast(C.c_char_p(b), C.c_void_p)  # points into `b`, which the caller keeps alive
+    if isinstance(b, bytearray):
+        return C.cast((C.c_char * len(b)).from_buffer(b), C.c_void_p)
+    raise TypeError(type(b))
+
+
+def _le(v, n=None) -> bytes:
+    if isinstance(v, (bytes, bytearray)):
+        return bytes(v)
+    v = int(v)
+    if n is None:
+        n = max(1, (v.bit_length() + 7) // 8)
+    return v.to_bytes(n, "little")
+
+
+class GpuBackend:
+    """Deferred, batched `ZKBackend` (evaluator.rs:17-76).  `Wire` = int (SSA handle),
+    `FieldElement` = little-endian bytes or int."""
+
+    def __init__(self, device: int = 0):
+        self._c = _lib.zkb_create(device)
+        self.device = device
+        err = _lib.zkb_last_error(self._c).decode()
+        if device >= 0 and err:
+            _lib.zkb_destroy(self._c)
+            self._c = None
+            raise ZkbError(ZKB_E_CUDA, err)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_c", None):
+            _lib.zkb_destroy(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != ZKB_OK:
+            raise ZkbError(rc, _lib.zkb_last_error(self._c).decode())
+
+    # ---- ZKBackend methods -------------------------------------------------
+    @staticmethod
+    def from_bytes_le(val: bytes) -> bytes:
+        return bytes(val)
+
+    def set_field(self, modulus, degree: int = 1, is_boolean: bool = False):
+        m = _le(modulus)
+        self._chk(_lib.zkb_set_field(self._c, _buf(m), len(m), degree, int(is_boolean)))
+
+    def _elem(self, fn) -> bytes:
+        out = C.create_string_buffer(64)
+        n = C.c_size_t()
+        self._chk(fn(self._c, C.cast(out, C.c_void_p), 64, C.byref(n)))
+        return out.raw[:n.value]
+
+    def one(self):
+        return self._elem(_lib.zkb_one)
+
+    def minus_one(self):
+        return self._elem(_lib.zkb_minus_one)
+
+    def zero(self):
+        return self._elem(_lib.zkb_zero)
+
+    def _w1(self, fn, *args):
+        out = C.c_uint64()
+        self._chk(fn(self._c, *args, C.byref(out)))
+        return out.value
+
+    def copy(self, a):
+        return self._w1(_lib.zkb_copy, a)
+
+    def constant(self, val):
+        v = _le(val)
+        return self._w1(_lib.zkb_constant, _buf(v), len(v))
+
+    def assert_zero(self, a, src_wire_id: int = 0):
+        self._chk(_lib.zkb_assert_zero(self._c, a, src_wire_id))
+
+    def add(self, a, b):
+        return self._w1(_lib.zkb_add, a, b)
+
+    def multiply(self, a, b):
+        return self._w1(_lib.zkb_multiply, a, b)
+
+    def add_constant(self, a, val):
+        v = _le(val)
+        return self._w1(_lib.zkb_add_constant, a, _buf(v), len(v))
+
+    def mul_constant(self, a, val):
+        v = _le(val)
+        return self._w1(_lib.zkb_mul_constant, a, _buf(v), len(v))
+
+    def and_(self, a, b):
+        return self._w1(_lib.zkb_and, a, b)
+
+    def xor(self, a, b):
+        return self._w1(_lib.zkb_xor, a, b)
+
+    def not_(self, a):
+        return self._w1(_lib.zkb_not, a)
+
+    def instance(self, val=None):
+        return self._w1(_lib.zkb_instance)
+
+    def witness(self, val=None):
+        return self._w1(_lib.zkb_witness)
+
+    # ---- bulk gates / evaluation --------------------------------------------
+    def push_gates(self, gates: np.ndarray, const_pool: Optional[np.ndarray] = None):
+        """gates: GATE_DTYPE array; const_pool: uint8 [n_consts, stride]"""
+        gates = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+        if const_pool is None:
+            const_pool = np.zeros((0, 1), dtype=np.uint8)
+        const_pool = np.ascontiguousarray(const_pool, dtype=np.uint8)
+        self._chk(_lib.zkb_push_gates(self._c, _buf(gates), len(gates), _buf(const_pool), const_pool.shape[1],
+                                      const_pool.shape[0]))
+
+    def finalize(self, keep_all_values: bool = False):
+        self._chk(_lib.zkb_finalize(self._c, int(keep_all_values)))
+
+    @staticmethod
+    def _pack_inputs(x):
+        """[n_batch, n_vals, stride] or [n_vals, stride] (shared) uint8 -> (array, set_stride, stride)"""
+        if x is None:
+            return None, 0, 0
+        x = np.ascontiguousarray(x, dtype=np.uint8)
+        if x.ndim == 2:
+            return x, 0, x.shape[1]
+        return x, x.shape[1] * x.shape[2], x.shape[2]
+
+    def _strides(self, instances, witnesses):
+        inst, iss, istr = self._pack_inputs(instances)
+        wit, wss, wstr = self._pack_inputs(witnesses)
+        stride = wstr or istr or 1
+        if istr and wstr and istr != wstr:
+            raise ValueError("instance and witness value strides differ")
+        return inst, iss, wit, wss, stride
+
+    def evaluate(self, instances, witnesses, n_batch: int) -> np.ndarray:
+        """End-to-end: host buffers in, verdicts out (VERDICT_DTYPE array)."""
+        inst, iss, wit, wss, stride = self._strides(instances, witnesses)
+        out = np.zeros(n_batch, dtype=VERDICT_DTYPE)
+        self._chk(_lib.zkb_evaluate(self._c, _buf(inst), iss, _buf(wit), wss, stride, n_batch, _buf(out)))
+        return out
+
+    def upload_inputs(self, instances, witnesses, n_batch: int):
+        inst, iss, wit, wss, stride = self._strides(instances, witnesses)
+        self._chk(_lib.zkb_upload_inputs(self._c, _buf(inst), iss, _buf(wit), wss, stride, n_batch))
+        self._n_batch = n_batch
+
+    def run(self) -> np.ndarray:
+        out = np.zeros(self._n_batch, dtype=VERDICT_DTYPE)
+        self._chk(_lib.zkb_run(self._c, _buf(out)))
+        return out
+
+    def assert_wire(self, seq: int) -> int:
+        out = C.c_uint64()
+        self._chk(_lib.zkb_assert_info(self._c, seq, C.byref(out)))
+        return out.value
+
+    def pending_error(self) -> Optional[str]:
+        e = _lib.zkb_pending_error(self._c)
+        return e.decode() if e else None
+
+    def read_values(self, batch_idx: int, values: Sequence[int], stride: int = 32) -> List[int]:
+        vals = np.ascontiguousarray(values, dtype=np.uint64)
+        out = np.zeros((len(vals), stride), dtype=np.uint8)
+        self._chk(_lib.zkb_read_values(self._c, batch_idx, _buf(vals), len(vals), _buf(out), stride))
+        return [int.from_bytes(out[i].tobytes(), "little") for i in range(len(vals))]
+
+    def scope_lookup(self, wire: int) -> int:
+        out = C.c_uint64()
+        self._chk(_lib.zkb_scope_lookup(self._c, wire, C.byref(out)))
+        return out.value
+
+    def stats(self) -> dict:
+        s = ZkbStats()
+        self._chk(_lib.zkb_get_stats(self._c, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in ZkbStats._fields_ if k != "callbacks"}
+        d["callbacks"] = {n: s.callbacks[i] for i, n in enumerate(CALLBACK_NAMES)}
+        return d
+
+    def timing(self) -> dict:
+        t = ZkbTiming()
+        self._chk(_lib.zkb_get_timing(self._c, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in ZkbTiming._fields_}
+
+    # ---- R1CS -----------------------------------------------------------------
+    def r1cs_load(self, A, B, Cm, coef_table: np.ndarray, n_vars: int):
+        """A, B, Cm: (row_ptr uint64[n_rows+1], col uint32[nnz], coef_idx uint32[nnz])"""
+        keep = []
+
+        def mk(m):
+            rp = np.ascontiguousarray(m[0], dtype=np.uint64)
+            col = np.ascontiguousarray(m[1], dtype=np.uint32)
+            ci = np.ascontiguousarray(m[2], dtype=np.uint32)
+            keep.extend([rp, col, ci])
+            return ZkbCsr(len(rp) - 1, rp.ctypes.data, col.ctypes.data, ci.ctypes.data)
+
+        a, b, c = mk(A), mk(B), mk(Cm)
+        coef_table = np.ascontiguousarray(coef_table, dtype=np.uint8)
+        self._chk(_lib.zkb_r1cs_load(self._c, C.byref(a), C.byref(b), C.byref(c), _buf(coef_table),
+                                     coef_table.shape[1], coef_table.shape[0], n_vars))
+
+    def r1cs_check(self, z: np.ndarray) -> np.ndarray:
+        """z: uint8 [n_batch, n_vars, stride]"""
+        z = np.ascontiguousarray(z, dtype=np.uint8)
+        out = np.zeros(z.shape[0], dtype=VERDICT_DTYPE)
+        self._chk(_lib.zkb_r1cs_check(self._c, _buf(z), z.shape[1] * z.shape[2], z.shape[2], z.shape[0], _buf(out)))
+        return out
+
+    def r1cs_upload(self, z: np.ndarray):
+        z = np.ascontiguousarray(z, dtype=np.uint8)
+        self._chk(_lib.zkb_r1cs_upload(self._c, _buf(z), z.shape[1] * z.shape[2], z.shape[2], z.shape[0]))
+        self._n_batch = z.shape[0]
+
+    def r1cs_run(self) -> np.ndarray:
+        out = np.zeros(self._n_batch, dtype=VERDICT_DTYPE)
+        self._chk(_lib.zkb_r1cs_run(self._c, _buf(out)))
+        return out
+
+
+class Source:
+    """`Source` (rust/src/consumers/source.rs:45-118): where `.sieve` messages come from."""
+
+    def __init__(self, paths=None, buffers=None):
+        self.paths = paths
+        self.buffers = buffers
+
+    @classmethod
+    def from_directory(cls, path):
+        return cls(paths=[str(path)])
+
+    @classmethod
+    def from_dirs_and_files(cls, paths):
+        return cls(paths=[str(p) for p in paths])
+
+    @classmethod
+    def from_buffers(cls, buffers: Iterable[bytes]):
+        return cls(buffers=[bytes(b) for b in buffers])
+
+
+class Evaluator:
+    """`Evaluator<GpuBackend>` (evaluator.rs:158-753) over `.sieve` bytes."""
+
+    def __init__(self, backend: Optional[GpuBackend] = None, device: int = 0):
+        self.backend = backend or GpuBackend(device)
+        self._e = _lib.zkb_evaluator_create(self.backend._c)
+
+    def close(self):
+        if getattr(self, "_e", None):
+            _lib.zkb_evaluator_destroy(self._e)
+            self._e = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != ZKB_OK:
+            raise ZkbError(rc, _lib.zkb_evaluator_last_error(self._e).decode())
+
+    @classmethod
+    def from_messages(cls, source: Source, backend: Optional[GpuBackend] = None, device: int = 0):
+        ev = cls(backend, device)
+        ev.ingest_source(source)
+        return ev
+
+    def ingest_source(self, source: Source):
+        if source.buffers is not None:
+            for b in source.buffers:
+                self._chk(_lib.zkb_evaluator_ingest_buffer(self._e, _buf(b), len(b)))
+        else:
+            arr = (C.c_char_p * len(source.paths))(*[p.encode() for p in source.paths])
+            self._chk(_lib.zkb_evaluator_ingest_paths(self._e, arr, len(source.paths)))
+
+    def ingest_message(self, buf: bytes):
+        self._chk(_lib.zkb_evaluator_ingest_message(self._e, _buf(buf), len(buf)))
+
+    def get_violations(self) -> List[str]:
+        n = C.c_size_t()
+        self._chk(_lib.zkb_evaluator_get_violations(self._e, C.byref(n)))
+        return [_lib.zkb_evaluator_violation(self._e, i).decode() for i in range(n.value)]
+
+    def get(self, wire_id: int) -> int:
+        out = C.create_string_buffer(64)
+        n = C.c_size_t()
+        self._chk(_lib.zkb_evaluator_get_wire(self._e, wire_id, C.cast(out, C.c_void_p), 64, C.byref(n)))
+        return int.from_bytes(out.raw[:n.value], "little")

@@ -1,0 +1,676 @@
+// zkb_ctx: recording backend + batched GPU evaluation (sections 1-3 of include/zkb.h).
+//
+// Reference seam: `trait ZKBackend` + `PlaintextBackend` (rust/src/consumers/evaluator.rs:17-76,
+// 848-947) and the simple arms of `Evaluator::ingest_gate` (:344-439).  The backend is deferred:
+// callbacks record SSA values (program.h); zkb_finalize levelizes; zkb_run streams tiles of
+// witnesses through one kernel launch per wavefront.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "context.h"
+
+using namespace zkb;
+
+#define CUDA_TRY(c, expr)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return (c)->fail(ZKB_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr); \
+    } while (0)
+
+namespace zkb {
+
+bool ctx_record_ok(zkb_ctx* c) { return !c->has_pending; }
+
+void ctx_latch(zkb_ctx* c, const std::string& msg) {
+    if (!c->has_pending) {
+        c->has_pending = true;
+        c->pending_error = msg;
+    }
+}
+
+template <class T>
+static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
+    if (dptr) {
+        cudaFree(dptr);
+        dptr = nullptr;
+    }
+    if (v.empty()) return ZKB_OK;
+    CUDA_TRY(c, cudaMalloc((void**)&dptr, v.size() * sizeof(T)));
+    CUDA_TRY(c, cudaMemcpyAsync(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return ZKB_OK;
+}
+
+int ctx_finalize(zkb_ctx* c, bool keep_all) {
+    if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
+    // observable values: whatever is still bound in the flat scope, plus the Evaluator's live wires
+    std::vector<uint32_t> live = c->live_values;
+    c->flat_scope.for_each([&](uint64_t, uint32_t v) { live.push_back(v); });
+    c->plan.build(c->prog, keep_all, &live);
+    c->keep_all = keep_all;
+    c->finalized = true;
+    c->resident_tile = -1;
+    c->inputs_uploaded = false;
+    if (!c->has_gpu) return ZKB_OK;  // host-only context: plan can be inspected, not run
+    int rc;
+    if ((rc = upload_vec(c, c->d_ops, c->plan.ops)) != ZKB_OK) return rc;
+    if ((rc = upload_vec(c, c->d_aseq, c->plan.op_assert_seq)) != ZKB_OK) return rc;
+    if ((rc = upload_vec(c, c->d_loads, c->plan.loads)) != ZKB_OK) return rc;
+    if ((rc = upload_vec(c, c->d_consts, c->prog.const_limbs)) != ZKB_OK) return rc;
+    if (!c->prog.binary) launch_to_mont(c->prog.nlimb, c->d_consts, c->prog.n_consts(), c->prog.fp, c->stream);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ZKB_OK;
+}
+
+}  // namespace zkb
+
+// ------------------------------------------------------------------------------------------
+// 1. lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" zkb_ctx* zkb_create(int device) {
+    zkb_ctx* c = new zkb_ctx();
+    c->device = device;
+    if (device < 0) return c;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        c->err = std::string("zkb_create: no usable CUDA device: ") + cudaGetErrorString(e);
+        return c;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        c->err = std::string("zkb_create: ") + cudaGetErrorString(e);
+        return c;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        c->err = std::string("zkb_create: ") + cudaGetErrorString(e);
+        return c;
+    }
+    for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev[i]);
+    cudaMalloc((void**)&c->d_unreduced, sizeof(uint32_t));
+    c->has_gpu = true;
+    return c;
+}
+
+extern "C" void zkb_destroy(zkb_ctx* c) {
+    if (!c) return;
+    if (c->has_gpu) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(c->d_ops);
+        cudaFree(c->d_aseq);
+        cudaFree(c->d_loads);
+        cudaFree(c->d_consts);
+        cudaFree(c->d_store);
+        cudaFree(c->d_inst);
+        cudaFree(c->d_wit);
+        cudaFree(c->d_first_fail);
+        cudaFree(c->d_scratch_fail);
+        cudaFree(c->d_unreduced);
+        r1cs_free(c);
+        for (int i = 0; i < 4; i++)
+            if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        for (auto e : c->tile_ev) cudaEventDestroy(e);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+extern "C" const char* zkb_last_error(zkb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" const char* zkb_pending_error(zkb_ctx* c) { return (c && c->has_pending) ? c->pending_error.c_str() : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+// 2. ZKBackend seam
+// ------------------------------------------------------------------------------------------
+extern "C" int zkb_set_field(zkb_ctx* c, const uint8_t* modulus_le, size_t len, uint32_t degree, int is_boolean) {
+    std::string err;
+    if (!c->prog.set_field(modulus_le, len, degree, err)) {
+        bool ref_err = err.rfind("zkb:", 0) != 0;
+        return c->fail(ref_err ? ZKB_E_SEMANTIC : ZKB_E_UNSUPPORTED, err);
+    }
+    c->is_boolean = is_boolean != 0;
+    return ZKB_OK;
+}
+
+static int write_le(zkb_ctx* c, const std::vector<uint8_t>& v, uint8_t* out, size_t cap, size_t* len) {
+    if (cap < v.size()) return c->fail(ZKB_E_ARG, "output buffer too small");
+    memcpy(out, v.data(), v.size());
+    if (len) *len = v.size();
+    return ZKB_OK;
+}
+
+extern "C" int zkb_one(zkb_ctx* c, uint8_t* out, size_t cap, size_t* len) { return write_le(c, {1}, out, cap, len); }
+extern "C" int zkb_zero(zkb_ctx* c, uint8_t* out, size_t cap, size_t* len) { return write_le(c, {0}, out, cap, len); }
+extern "C" int zkb_minus_one(zkb_ctx* c, uint8_t* out, size_t cap, size_t* len) {
+    // PlaintextBackend::minus_one, evaluator.rs:881-886
+    if (!c->prog.field_set) return c->fail(ZKB_E_SEMANTIC, "Modulus is not initiated, used `set_field()` before calling.");
+    return write_le(c, c->prog.minus_one_le(), out, cap, len);
+}
+
+#define REC_PROLOGUE(c)                                                                         \
+    if (!(c)->prog.field_set) return (c)->fail(ZKB_E_ARG, "set_field must be called before recording"); \
+    if ((c)->finalized) return (c)->fail(ZKB_E_ARG, "program already finalized");               \
+    if ((c)->prog.n_values() >= 0xFFFFFFF0u) return (c)->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 values")
+#define CHECK_WIRE(c, w) \
+    if ((w) >= (c)->prog.n_values()) return (c)->fail(ZKB_E_ARG, "unknown wire handle")
+
+extern "C" int zkb_copy(zkb_ctx* c, zkb_wire a, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    CHECK_WIRE(c, a);
+    *out = c->prog.copy((uint32_t)a);
+    return ZKB_OK;
+}
+extern "C" int zkb_constant(zkb_ctx* c, const uint8_t* v, size_t len, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    *out = c->prog.constant(v, len);
+    return ZKB_OK;
+}
+extern "C" int zkb_assert_zero(zkb_ctx* c, zkb_wire a, uint64_t src_wire_id) {
+    REC_PROLOGUE(c);
+    CHECK_WIRE(c, a);
+    c->prog.assert_zero((uint32_t)a, src_wire_id);
+    return ZKB_OK;
+}
+#define BINOP(NAME, METHOD)                                                        \
+    extern "C" int NAME(zkb_ctx* c, zkb_wire a, zkb_wire b, zkb_wire* out) {       \
+        REC_PROLOGUE(c);                                                           \
+        CHECK_WIRE(c, a);                                                          \
+        CHECK_WIRE(c, b);                                                          \
+        *out = c->prog.METHOD((uint32_t)a, (uint32_t)b);                           \
+        return ZKB_OK;                                                             \
+    }
+BINOP(zkb_add, add)
+BINOP(zkb_multiply, multiply)
+BINOP(zkb_and, and_)
+BINOP(zkb_xor, xor_)
+extern "C" int zkb_add_constant(zkb_ctx* c, zkb_wire a, const uint8_t* v, size_t len, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    CHECK_WIRE(c, a);
+    *out = c->prog.add_constant((uint32_t)a, v, len);
+    return ZKB_OK;
+}
+extern "C" int zkb_mul_constant(zkb_ctx* c, zkb_wire a, const uint8_t* v, size_t len, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    CHECK_WIRE(c, a);
+    *out = c->prog.mul_constant((uint32_t)a, v, len);
+    return ZKB_OK;
+}
+extern "C" int zkb_not(zkb_ctx* c, zkb_wire a, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    CHECK_WIRE(c, a);
+    *out = c->prog.not_((uint32_t)a);
+    return ZKB_OK;
+}
+extern "C" int zkb_instance(zkb_ctx* c, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    *out = c->prog.instance();
+    return ZKB_OK;
+}
+extern "C" int zkb_witness(zkb_ctx* c, zkb_wire* out) {
+    REC_PROLOGUE(c);
+    *out = c->prog.witness();
+    return ZKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. bulk flat gates — the simple arms of Evaluator::ingest_gate (evaluator.rs:344-439)
+// ------------------------------------------------------------------------------------------
+extern "C" int zkb_push_gates(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gates, const uint8_t* pool, size_t cstride,
+                              uint64_t n_consts) {
+    REC_PROLOGUE(c);
+    if (c->has_pending) return c->fail(ZKB_E_SEMANTIC, c->pending_error);  // evaluator.rs:214-216: latched
+    Program& p = c->prog;
+    Scope& sc = c->flat_scope;
+    char buf[96];
+    auto no_value = [&](uint64_t id) {
+        snprintf(buf, sizeof buf, "No value given for wire_%llu", (unsigned long long)id);  // evaluator.rs:787-797
+        ctx_latch(c, buf);
+        return c->fail(ZKB_E_SEMANTIC, buf);
+    };
+    auto already = [&](uint64_t id) {
+        snprintf(buf, sizeof buf, "Wire_%llu already has a value in this scope.", (unsigned long long)id);  // :775-785
+        ctx_latch(c, buf);
+        return c->fail(ZKB_E_SEMANTIC, buf);
+    };
+    // constants of this call are interned once
+    std::vector<uint32_t> cidx(n_consts);
+    for (uint64_t i = 0; i < n_consts; i++) cidx[i] = p.intern_const(pool + i * cstride, cstride);
+    p.kind.reserve(p.kind.size() + n_gates);
+    p.opa.reserve(p.opa.size() + n_gates);
+    p.opb.reserve(p.opb.size() + n_gates);
+    for (uint64_t i = 0; i < n_gates; i++) {
+        const zkb_gate& g = gates[i];
+        if (p.n_values() >= 0xFFFFFFF0u) return c->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 values");
+        uint32_t va = 0, vb = 0, res = 0;
+        switch (g.op) {
+            case ZKB_G_CONSTANT:
+                if (g.b >= n_consts) return c->fail(ZKB_E_ARG, "constant index out of range");
+                p.cb_count[CB_CONSTANT]++;
+                res = p.push_value(V_CONST, 0, cidx[g.b]);
+                if (!sc.set(g.out, res)) return already(g.out);
+                break;
+            case ZKB_G_ASSERT_ZERO:
+                if ((va = sc.get(g.a)) == Scope::kNone) return no_value(g.a);
+                p.copy(va);  // evaluator.rs:355: unweighted asserts test a copy
+                p.assert_zero(va, g.a);
+                p.ir_gates++;
+                break;
+            case ZKB_G_COPY:
+                if ((va = sc.get(g.a)) == Scope::kNone) return no_value(g.a);
+                if (!sc.set(g.out, p.copy(va))) return already(g.out);
+                break;
+            case ZKB_G_ADD:
+            case ZKB_G_MUL:
+            case ZKB_G_AND:
+            case ZKB_G_XOR:
+                if ((va = sc.get(g.a)) == Scope::kNone) return no_value(g.a);
+                if ((vb = sc.get(g.b)) == Scope::kNone) return no_value(g.b);
+                res = g.op == ZKB_G_ADD ? p.add(va, vb) : g.op == ZKB_G_MUL ? p.multiply(va, vb)
+                      : g.op == ZKB_G_AND ? p.and_(va, vb) : p.xor_(va, vb);
+                p.ir_gates++;
+                if (!sc.set(g.out, res)) return already(g.out);
+                break;
+            case ZKB_G_ADD_CONSTANT:
+            case ZKB_G_MUL_CONSTANT:
+                if ((va = sc.get(g.a)) == Scope::kNone) return no_value(g.a);
+                if (g.b >= n_consts) return c->fail(ZKB_E_ARG, "constant index out of range");
+                p.cb_count[g.op == ZKB_G_ADD_CONSTANT ? CB_ADDC : CB_MULC]++;
+                res = p.push_value(g.op == ZKB_G_ADD_CONSTANT ? V_ADDC : V_MULC, va, cidx[g.b]);
+                p.ir_gates++;
+                if (!sc.set(g.out, res)) return already(g.out);
+                break;
+            case ZKB_G_NOT:
+                if ((va = sc.get(g.a)) == Scope::kNone) return no_value(g.a);
+                res = p.not_(va);
+                p.ir_gates++;
+                if (!sc.set(g.out, res)) return already(g.out);
+                break;
+            case ZKB_G_INSTANCE:
+                if (!sc.set(g.out, p.instance())) return already(g.out);
+                break;
+            case ZKB_G_WITNESS:
+                if (!sc.set(g.out, p.witness())) return already(g.out);
+                break;
+            case ZKB_G_FREE:
+                for (uint64_t w = g.a; w <= (uint64_t)g.b; w++)
+                    if (!sc.remove(w)) return no_value(w);
+                break;
+            default:
+                return c->fail(ZKB_E_ARG, "unknown gate opcode");
+        }
+    }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_scope_lookup(zkb_ctx* c, uint64_t wire, zkb_wire* out) {
+    uint32_t v = c->flat_scope.get(wire);
+    if (v == Scope::kNone) {
+        char buf[64];
+        snprintf(buf, sizeof buf, "No value given for wire_%llu", (unsigned long long)wire);
+        return c->fail(ZKB_E_SEMANTIC, buf);
+    }
+    *out = v;
+    return ZKB_OK;
+}
+
+extern "C" int zkb_finalize(zkb_ctx* c, int keep_all_values) {
+    if (c->finalized) return c->fail(ZKB_E_ARG, "program already finalized");
+    return ctx_finalize(c, keep_all_values != 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------
+static size_t elem_bytes(const zkb_ctx* c) { return (size_t)c->prog.nlimb * 4; }
+
+// bytes of wire store for a tile of 2^log2_wt witnesses
+static size_t store_bytes_for(const zkb_ctx* c, uint32_t log2_wt) {
+    if (c->prog.binary) return (size_t)std::max<uint32_t>(c->plan.n_slots, 1) * ((size_t)1 << log2_wt) / 8;
+    return (size_t)std::max<uint32_t>(c->plan.n_slots, 1) * elem_bytes(c) * ((size_t)1 << log2_wt);
+}
+
+static int choose_tile(zkb_ctx* c, uint32_t n_batch) {
+    uint32_t want = 0;
+    while (((uint64_t)1 << want) < n_batch) want++;
+    uint32_t min_l2 = c->prog.binary ? 5 : 0;
+    if (want < min_l2) want = min_l2;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = free_b + c->store_bytes;  // our own store will be released/reused
+    budget = budget > ((size_t)768 << 20) ? budget - ((size_t)768 << 20) : budget / 2;
+    if (const char* s = getenv("ZKB_MAX_STORE_MB")) budget = std::min(budget, (size_t)atoll(s) << 20);
+    uint32_t l2 = want;
+    while (l2 > min_l2 && store_bytes_for(c, l2) > budget) l2--;
+    if (const char* s = getenv("ZKB_TILE_LOG2")) {
+        uint32_t f = (uint32_t)atoi(s);
+        if (f >= min_l2 && f < l2) l2 = f;
+    }
+    if (store_bytes_for(c, l2) > budget)
+        return c->fail(ZKB_E_CUDA, "wire store does not fit in device memory even for the smallest tile");
+    size_t need = store_bytes_for(c, l2);
+    if (need > c->store_bytes || c->store_bytes > need * 4) {
+        if (c->d_store) cudaFree(c->d_store);
+        c->d_store = nullptr;
+        c->store_bytes = 0;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_store, need));
+        c->store_bytes = need;
+    }
+    c->log2_wt = l2;
+    c->resident_tile = -1;
+    return ZKB_OK;
+}
+
+static int ensure_bytes(zkb_ctx* c, uint8_t*& d, size_t& cap, size_t need) {
+    if (need <= cap && d) return ZKB_OK;
+    if (d) cudaFree(d);
+    d = nullptr;
+    cap = 0;
+    if (need == 0) need = 16;
+    CUDA_TRY(c, cudaMalloc((void**)&d, need));
+    cap = need;
+    return ZKB_OK;
+}
+
+extern "C" int zkb_upload_inputs(zkb_ctx* c, const uint8_t* inst, uint64_t inst_set_stride, const uint8_t* wit,
+                                 uint64_t wit_set_stride, uint32_t value_stride, uint32_t n_batch) {
+    if (!c->finalized) return c->fail(ZKB_E_ARG, "zkb_finalize must be called before evaluation");
+    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
+    if (n_batch == 0) return c->fail(ZKB_E_ARG, "n_batch must be > 0");
+    const Program& p = c->prog;
+    if (value_stride == 0 && (p.n_instance || p.n_witness)) return c->fail(ZKB_E_ARG, "value_stride must be > 0");
+    // the reference consumes values from queues: too few instances is an Err string (evaluator.rs:420-427),
+    // a missing witness value is a panic (evaluator.rs:944-946).  Callers state the counts via the strides.
+    if (p.n_instance && !inst) return c->fail(ZKB_E_SEMANTIC, "Not enough instance to consume");
+    if (p.n_witness && !wit) return c->fail(ZKB_E_FATAL, "Missing witness value for PlaintextBackend");
+    if (inst_set_stride != 0 && inst_set_stride < (uint64_t)p.n_instance * value_stride)
+        return c->fail(ZKB_E_SEMANTIC, "Not enough instance to consume");
+    if (wit_set_stride != 0 && wit_set_stride < (uint64_t)p.n_witness * value_stride)
+        return c->fail(ZKB_E_FATAL, "Missing witness value for PlaintextBackend");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = choose_tile(c, n_batch);
+    if (rc != ZKB_OK) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+    size_t ib = p.n_instance ? (inst_set_stride ? (size_t)inst_set_stride * n_batch : (size_t)p.n_instance * value_stride) : 0;
+    size_t wb = p.n_witness ? (wit_set_stride ? (size_t)wit_set_stride * n_batch : (size_t)p.n_witness * value_stride) : 0;
+    if ((rc = ensure_bytes(c, c->d_inst, c->inst_bytes, ib)) != ZKB_OK) return rc;
+    if ((rc = ensure_bytes(c, c->d_wit, c->wit_bytes, wb)) != ZKB_OK) return rc;
+    if (ib) CUDA_TRY(c, cudaMemcpyAsync(c->d_inst, inst, ib, cudaMemcpyHostToDevice, c->stream));
+    if (wb) CUDA_TRY(c, cudaMemcpyAsync(c->d_wit, wit, wb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+    c->in.inst = c->d_inst;
+    c->in.wit = c->d_wit;
+    c->in.inst_set_stride = inst_set_stride;
+    c->in.wit_set_stride = wit_set_stride;
+    c->in.stride = value_stride;
+    c->n_batch = n_batch;
+    if (n_batch > c->first_fail_cap) {
+        if (c->d_first_fail) cudaFree(c->d_first_fail);
+        if (c->d_scratch_fail) cudaFree(c->d_scratch_fail);
+        c->d_first_fail = c->d_scratch_fail = nullptr;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_first_fail, (size_t)n_batch * 4));
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_scratch_fail, (size_t)n_batch * 4));
+        c->first_fail_cap = n_batch;
+    }
+    c->inputs_uploaded = true;
+    c->resident_tile = -1;
+    return ZKB_OK;
+}
+
+// run one tile of witnesses through every wavefront
+static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* launches, uint64_t* level_launches) {
+    const Plan& pl = c->plan;
+    const Program& p = c->prog;
+    TileGeom g;
+    g.log2_wt = c->log2_wt;
+    g.batch0 = tile << c->log2_wt;
+    uint32_t wt = 1u << c->log2_wt;
+    g.n_valid = std::min<uint32_t>(wt, c->n_batch - g.batch0);
+    g.pad = 0;
+    if (p.binary)
+        launch_bool_load_inputs(c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, c->stream);
+    else
+        launch_load_inputs(p.nlimb, c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, p.fp,
+                           c->stream);
+    (*launches)++;
+    const bool timed = level_launches != nullptr && d_fail == c->d_first_fail;
+    if (timed) {
+        while (c->tile_ev.size() < 2 * (size_t)(tile + 1)) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            c->tile_ev.push_back(e);
+        }
+        cudaEventRecord(c->tile_ev[2 * tile], c->stream);
+    }
+    for (uint32_t l = 0; l < pl.n_levels; l++) {
+        uint64_t lo = pl.level_off[l], mid = pl.level_rare[l], hi = pl.level_off[l + 1];
+        if (p.binary) {
+            if (hi > lo) {
+                launch_bool_level(c->d_ops + lo, c->d_aseq + lo, hi - lo, c->d_store, c->d_consts, d_fail, g, c->sm_count, c->stream);
+                (*launches)++;
+                (*level_launches)++;
+            }
+            continue;
+        }
+        if (mid > lo) {
+            launch_level(p.nlimb, c->d_ops + lo, c->d_aseq + lo, mid - lo, c->d_store, c->d_consts, d_fail, g, p.fp, c->sm_count, false,
+                         c->stream);
+            (*launches)++;
+            (*level_launches)++;
+        }
+        if (hi > mid) {
+            launch_level(p.nlimb, c->d_ops + mid, c->d_aseq + mid, hi - mid, c->d_store, c->d_consts, d_fail, g, p.fp, c->sm_count, true,
+                         c->stream);
+            (*launches)++;
+            (*level_launches)++;
+        }
+    }
+    if (timed) cudaEventRecord(c->tile_ev[2 * tile + 1], c->stream);
+    c->resident_tile = tile;
+}
+
+// SURVEY.md §8a trap 1: values >= p stay RAW in the reference.  The device works on residues, which
+// is exact for add/mul; the raw-sensitive consumers of an input value are resolved here, on the
+// (rare) path where the load kernel counted at least one unreduced input.
+static int resolve_unreduced(zkb_ctx* c, std::vector<uint32_t>& first_fail) {
+    const Program& p = c->prog;
+    const Plan& pl = c->plan;
+    // and / xor / not reading an input value directly would need the raw integer on device
+    for (uint32_t v = 0; v < p.n_values(); v++) {
+        uint8_t k = p.kind[v];
+        if (k == V_AND || k == V_XOR || k == V_NOT) {
+            bool direct = p.kind[p.opa[v]] <= V_WITNESS && p.kind[p.opa[v]] != V_CONST;
+            if (k != V_NOT) direct = direct || (p.kind[p.opb[v]] <= V_WITNESS && p.kind[p.opb[v]] != V_CONST);
+            if (direct)
+                return c->fail(ZKB_E_UNSUPPORTED,
+                               "zkb: an instance/witness value >= p feeds a bitwise gate directly; the reference evaluates that on the "
+                               "unreduced integer, which the device path does not hold");
+        }
+    }
+    if (pl.input_assert_value.empty()) return ZKB_OK;
+    // bring the raw inputs back and test them
+    std::vector<uint8_t> hi(c->inst_bytes ? c->inst_bytes : 1), hw(c->wit_bytes ? c->wit_bytes : 1);
+    CUDA_TRY(c, cudaMemcpy(hi.data(), c->d_inst, c->inst_bytes, cudaMemcpyDeviceToHost));
+    CUDA_TRY(c, cudaMemcpy(hw.data(), c->d_wit, c->wit_bytes, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < pl.input_assert_value.size(); i++) {
+        uint32_t v = pl.input_assert_value[i], seq = pl.input_assert_seq[i];
+        if (p.kind[v] == V_CONST) continue;  // handled statically in zkb_run
+        for (uint32_t j = 0; j < c->n_batch; j++) {
+            const uint8_t* src = p.kind[v] == V_INSTANCE ? hi.data() + (size_t)j * c->in.inst_set_stride
+                                                         : hw.data() + (size_t)j * c->in.wit_set_stride;
+            src += (size_t)p.opb[v] * c->in.stride;
+            BigU raw = BigU::from_bytes_le(src, c->in.stride);
+            if (raw >= p.modulus && seq < first_fail[j]) first_fail[j] = seq;  // raw != 0: the assertion fails
+        }
+    }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
+    if (!c->finalized) return c->fail(ZKB_E_ARG, "zkb_finalize must be called before evaluation");
+    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
+    if (!c->inputs_uploaded) return c->fail(ZKB_E_ARG, "zkb_upload_inputs must be called before zkb_run");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const uint32_t wt = 1u << c->log2_wt;
+    const uint32_t n_tiles = (c->n_batch + wt - 1) / wt;
+    uint64_t launches = 0, level_launches = 0;
+    CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+    launch_fill_u32(c->d_first_fail, 0xFFFFFFFFu, c->n_batch, c->stream);
+    CUDA_TRY(c, cudaMemsetAsync(c->d_unreduced, 0, 4, c->stream));
+    launches++;
+    for (uint32_t t = 0; t < n_tiles; t++) run_tile(c, t, c->d_first_fail, &launches, &level_launches);
+    c->h_first_fail.resize(c->n_batch);
+    uint32_t unreduced = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_first_fail.data(), c->d_first_fail, (size_t)c->n_batch * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(&unreduced, c->d_unreduced, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+    c->timing.total_ms = ms;
+    c->timing.h2d_ms = 0;
+    float lv = 0;
+    for (uint32_t t = 0; t < n_tiles; t++) {
+        float x = 0;
+        cudaEventElapsedTime(&x, c->tile_ev[2 * t], c->tile_ev[2 * t + 1]);
+        lv += x;
+    }
+    c->timing.levels_ms = lv;       // level kernels only, summed over tiles
+    c->timing.load_ms = ms - lv;    // input conversion, verdict fill/copy, gaps
+    c->timing.level_launches = level_launches;
+    c->timing.kernel_launches = launches;
+    // constants >= p that are asserted directly fail for every witness (raw integer != 0)
+    for (size_t i = 0; i < c->plan.input_assert_value.size(); i++) {
+        uint32_t v = c->plan.input_assert_value[i];
+        if (c->prog.kind[v] == V_CONST && c->prog.const_unreduced[c->prog.opb[v]])
+            for (auto& f : c->h_first_fail) f = std::min(f, c->plan.input_assert_seq[i]);
+    }
+    if (unreduced) {
+        int rc = resolve_unreduced(c, c->h_first_fail);
+        if (rc != ZKB_OK) return rc;
+    }
+    if (out)
+        for (uint32_t j = 0; j < c->n_batch; j++) {
+            uint32_t f = c->h_first_fail[j];
+            memset(&out[j], 0, sizeof(zkb_verdict));
+            out[j].ok = (f == 0xFFFFFFFFu) && !c->has_pending;
+            out[j].first_fail_seq = f == 0xFFFFFFFFu ? UINT64_MAX : f;
+        }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_evaluate(zkb_ctx* c, const uint8_t* inst, uint64_t inst_set_stride, const uint8_t* wit, uint64_t wit_set_stride,
+                            uint32_t value_stride, uint32_t n_batch, zkb_verdict* out) {
+    int rc = zkb_upload_inputs(c, inst, inst_set_stride, wit, wit_set_stride, value_stride, n_batch);
+    if (rc != ZKB_OK) return rc;
+    rc = zkb_run(c, out);
+    if (rc != ZKB_OK) return rc;
+    float h2d = 0, total = 0;
+    cudaEventElapsedTime(&h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&total, c->ev[0], c->ev[3]);
+    c->timing.h2d_ms = h2d;
+    c->timing.total_ms = total;
+    return ZKB_OK;
+}
+
+extern "C" int zkb_assert_info(zkb_ctx* c, uint64_t seq, uint64_t* src_wire_id) {
+    if (seq >= c->prog.asserts.size()) return c->fail(ZKB_E_ARG, "assert index out of range");
+    *src_wire_id = c->prog.asserts[seq].src_wire;
+    return ZKB_OK;
+}
+
+extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* values, uint64_t n, uint8_t* out, size_t stride) {
+    if (!c->finalized || !c->inputs_uploaded) return c->fail(ZKB_E_ARG, "nothing has been evaluated yet");
+    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
+    if (batch_idx >= c->n_batch) return c->fail(ZKB_E_ARG, "batch index out of range");
+    const Program& p = c->prog;
+    const size_t eb = p.binary ? 4 : elem_bytes(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    uint32_t tile = batch_idx >> c->log2_wt;
+    if (c->resident_tile != (int64_t)tile) {
+        uint64_t a = 0, b = 0;
+        launch_fill_u32(c->d_scratch_fail, 0xFFFFFFFFu, c->n_batch, c->stream);
+        run_tile(c, tile, c->d_scratch_fail, &a, &b);
+    }
+    std::vector<uint32_t> slots(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (values[i] >= p.n_values()) return c->fail(ZKB_E_ARG, "unknown wire handle");
+        uint32_t s = c->plan.slot_of_value[values[i]];
+        if (s == kNoSlot)
+            return c->fail(ZKB_E_ARG, "value was not kept on device (finalize with keep_all_values = 1 to read every value)");
+        slots[i] = s;
+    }
+    uint32_t *d_slots = nullptr, *d_out = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&d_slots, std::max<size_t>(n, 1) * 4));
+    CUDA_TRY(c, cudaMalloc((void**)&d_out, std::max<size_t>(n, 1) * eb));
+    CUDA_TRY(c, cudaMemcpyAsync(d_slots, slots.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t lane = batch_idx & ((1u << c->log2_wt) - 1);
+    if (p.binary) launch_bool_read_values(d_slots, (uint32_t)n, c->d_store, lane, c->log2_wt, d_out, c->stream);
+    else launch_read_values(p.nlimb, d_slots, (uint32_t)n, c->d_store, lane, c->log2_wt, d_out, p.fp, c->stream);
+    std::vector<uint8_t> host(std::max<size_t>(n, 1) * eb);
+    CUDA_TRY(c, cudaMemcpyAsync(host.data(), d_out, n * eb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_slots);
+    cudaFree(d_out);
+    // raw inputs for the trap-1 case: an input value is reported as the reference holds it (unreduced)
+    std::vector<uint8_t> raw_in;
+    for (uint64_t i = 0; i < n; i++) {
+        uint8_t* dst = out + i * stride;
+        memset(dst, 0, stride);
+        const uint8_t* src = host.data() + i * eb;
+        size_t nb = eb;
+        uint32_t v = (uint32_t)values[i];
+        std::vector<uint8_t> tmp;
+        if (p.kind[v] == V_CONST && p.const_unreduced[p.opb[v]]) {
+            src = p.const_raw[p.opb[v]].data();
+            nb = p.const_raw[p.opb[v]].size();
+        } else if (p.kind[v] == V_INSTANCE || p.kind[v] == V_WITNESS) {
+            bool is_inst = p.kind[v] == V_INSTANCE;
+            size_t off = (size_t)batch_idx * (is_inst ? c->in.inst_set_stride : c->in.wit_set_stride) + (size_t)p.opb[v] * c->in.stride;
+            tmp.resize(c->in.stride);
+            CUDA_TRY(c, cudaMemcpy(tmp.data(), (is_inst ? c->d_inst : c->d_wit) + off, c->in.stride, cudaMemcpyDeviceToHost));
+            raw_in.swap(tmp);
+            src = raw_in.data();
+            nb = raw_in.size();
+        }
+        while (nb > 0 && src[nb - 1] == 0) nb--;
+        if (nb > stride) return c->fail(ZKB_E_ARG, "output stride too small for the value");
+        memcpy(dst, src, nb);
+    }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
+    memset(s, 0, sizeof(*s));
+    const Program& p = c->prog;
+    s->n_values = p.n_values();
+    s->n_asserts = p.asserts.size();
+    s->n_instance = p.n_instance;
+    s->n_witness = p.n_witness;
+    s->n_consts = p.n_consts();
+    s->ir_gates = p.ir_gates;
+    for (int i = 0; i < CB_KINDS; i++) s->callbacks[i] = p.cb_count[i];
+    s->nlimb = (uint32_t)p.nlimb;
+    s->binary = p.binary;
+    if (c->finalized) {
+        s->n_slots = c->plan.n_slots;
+        s->n_levels = c->plan.n_levels;
+        s->n_device_ops = c->plan.ops.size();
+        s->algo_bytes_per_witness = c->plan.algo_bytes_per_witness;
+    }
+    if (c->inputs_uploaded) {
+        s->tile_witnesses = 1u << c->log2_wt;
+        s->n_tiles = (c->n_batch + s->tile_witnesses - 1) / s->tile_witnesses;
+    }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_get_timing(zkb_ctx* c, zkb_timing* t) {
+    *t = c->timing;
+    return ZKB_OK;
+}

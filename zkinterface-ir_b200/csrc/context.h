@@ -1,0 +1,133 @@
+// Internal: the context behind zkb_ctx (one host thread + one device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/zkb.h"
+#include "kernels.cuh"
+#include "program.h"
+
+namespace zkb {
+
+// wire id -> SSA value map of one scope: dense vector for small ids, hash map beyond
+class Scope {
+public:
+    static constexpr uint32_t kNone = 0xFFFFFFFFu;
+    static constexpr uint64_t kDenseLimit = 1ull << 28;
+    std::vector<uint32_t> dense;
+    std::unordered_map<uint64_t, uint32_t> sparse;
+    uint64_t live = 0;
+
+    uint32_t get(uint64_t id) const {
+        if (id < dense.size()) return dense[id];
+        if (id < kDenseLimit) return kNone;
+        auto it = sparse.find(id);
+        return it == sparse.end() ? kNone : it->second;
+    }
+    // returns false if the id already had a value (the new value is stored anyway, like HashMap::insert)
+    bool set(uint64_t id, uint32_t v) {
+        if (id < kDenseLimit) {
+            if (id >= dense.size()) {
+                size_t n = dense.size() ? dense.size() : 16;
+                while (n <= id) n *= 2;
+                dense.resize(n, kNone);
+            }
+            bool fresh = dense[id] == kNone;
+            dense[id] = v;
+            if (fresh) live++;
+            return fresh;
+        }
+        auto r = sparse.insert({id, v});
+        if (!r.second) r.first->second = v;
+        else live++;
+        return r.second;
+    }
+    bool remove(uint64_t id) {
+        if (id < kDenseLimit) {
+            if (id >= dense.size() || dense[id] == kNone) return false;
+            dense[id] = kNone;
+            live--;
+            return true;
+        }
+        if (sparse.erase(id)) {
+            live--;
+            return true;
+        }
+        return false;
+    }
+    void clear() {
+        std::fill(dense.begin(), dense.end(), kNone);
+        sparse.clear();
+        live = 0;
+    }
+    template <class F>
+    void for_each(F f) const {
+        for (size_t i = 0; i < dense.size(); i++)
+            if (dense[i] != kNone) f((uint64_t)i, dense[i]);
+        for (auto& kv : sparse) f(kv.first, kv.second);
+    }
+};
+
+struct R1csDev;  // r1cs.cu
+
+}  // namespace zkb
+
+struct zkb_ctx {
+    int device = -1;
+    bool has_gpu = false;
+    int sm_count = 148;
+    std::string err;
+
+    zkb::Program prog;
+    zkb::Plan plan;
+    bool is_boolean = false;
+    bool finalized = false;
+    bool keep_all = false;
+    zkb::Scope flat_scope;           // zkb_push_gates
+    std::vector<uint32_t> live_values;  // observable values supplied by the Evaluator at finalize
+    bool has_pending = false;
+    std::string pending_error;       // first recording error (latched)
+
+    // device state
+    cudaStream_t stream = nullptr;
+    zkb::GateOp* d_ops = nullptr;
+    uint32_t* d_aseq = nullptr;
+    zkb::InputLoad* d_loads = nullptr;
+    uint32_t* d_consts = nullptr;
+    uint32_t* d_store = nullptr;
+    size_t store_bytes = 0;
+    uint32_t log2_wt = 0;
+    uint8_t* d_inst = nullptr;
+    uint8_t* d_wit = nullptr;
+    size_t inst_bytes = 0, wit_bytes = 0;
+    zkb::InputDesc in{};
+    uint32_t n_batch = 0;
+    uint32_t* d_first_fail = nullptr;
+    uint32_t* d_scratch_fail = nullptr;
+    size_t first_fail_cap = 0;
+    uint32_t* d_unreduced = nullptr;
+    int64_t resident_tile = -1;
+    bool inputs_uploaded = false;
+    std::vector<uint32_t> h_first_fail;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> tile_ev;
+    zkb_timing timing{};
+
+    zkb::R1csDev* r1cs = nullptr;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+};
+
+namespace zkb {
+// shared helpers implemented in backend.cu
+int ctx_finalize(zkb_ctx* c, bool keep_all);
+bool ctx_record_ok(zkb_ctx* c);  // false when a recording error is latched
+void ctx_latch(zkb_ctx* c, const std::string& msg);
+void r1cs_free(zkb_ctx* c);
+}  // namespace zkb

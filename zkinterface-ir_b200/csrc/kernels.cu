@@ -1,0 +1,424 @@
+// sm_100a kernels of the gate-evaluation hot path.
+//
+// What they replace (reference, rust/src/consumers/evaluator.rs):
+//   k_level        one wavefront of PlaintextBackend::{add, multiply, add_constant, mul_constant,
+//                  and, xor, not} (:908-938) with `assert_zero` (:900-906) fused into the
+//                  producing gate, for a whole tile of witnesses at once
+//   k_load_inputs  `constant` / `instance` / `witness` (:896-898, 940-946): raw little-endian
+//                  values -> Montgomery residues in the wire store
+//   k_read_values  what `Evaluator::get` (:750-752) returns: canonical residues of chosen wires
+//   k_bool_*       the same for p = 2, bit-sliced (32 witnesses per word)
+//
+// No tensor cores on purpose: nothing on this path is a dense contraction.  The work is HBM-bound
+// streaming of wire limbs plus 32-bit integer multiply-add chains (IMAD), see DESIGN.md.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "field.cuh"
+#include "field_ptx.cuh"
+#include "kernels.cuh"
+
+namespace zkb {
+
+// ---------------------------------------------------------------------------------------------
+// wire-store element access
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct Elem {
+    static constexpr int CW = N < 4 ? N : 4;  // limbs per chunk
+    static constexpr int NC = N / CW;         // chunks per element
+};
+
+template <int CW>
+struct Vec;
+template <>
+struct Vec<1> {
+    using T = uint32_t;
+};
+template <>
+struct Vec<2> {
+    using T = uint2;
+};
+template <>
+struct Vec<4> {
+    using T = uint4;
+};
+
+__device__ __forceinline__ void unpack(uint32_t v, uint32_t* o) { o[0] = v; }
+__device__ __forceinline__ void unpack(uint2 v, uint32_t* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void unpack(uint4 v, uint32_t* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void pack(uint32_t& v, const uint32_t* o) { v = o[0]; }
+__device__ __forceinline__ void pack(uint2& v, const uint32_t* o) { v = make_uint2(o[0], o[1]); }
+__device__ __forceinline__ void pack(uint4& v, const uint32_t* o) { v = make_uint4(o[0], o[1], o[2], o[3]); }
+
+// streaming (read-once) loads: operands are written by an earlier launch and never by this one
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint2 ld_stream(const uint2* p) { return __ldg(p); }
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldg(p); }
+
+template <int N>
+__device__ __forceinline__ void load_elem(uint32_t* r, const uint32_t* store, uint32_t slot, uint32_t lane, uint32_t log2_wt) {
+    using V = typename Vec<Elem<N>::CW>::T;
+    const V* base = reinterpret_cast<const V*>(store);
+#pragma unroll
+    for (int c = 0; c < Elem<N>::NC; c++) {
+        size_t idx = (((size_t)slot * Elem<N>::NC + c) << log2_wt) + lane;
+        unpack(ld_stream(base + idx), r + c * Elem<N>::CW);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void store_elem(uint32_t* store, uint32_t slot, uint32_t lane, uint32_t log2_wt, const uint32_t* r) {
+    using V = typename Vec<Elem<N>::CW>::T;
+    V* base = reinterpret_cast<V*>(store);
+#pragma unroll
+    for (int c = 0; c < Elem<N>::NC; c++) {
+        size_t idx = (((size_t)slot * Elem<N>::NC + c) << log2_wt) + lane;
+        V v;
+        pack(v, r + c * Elem<N>::CW);
+        base[idx] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AssertZero reporting: first failing assertion (program order) per witness.
+// Failures are found with one warp ballot; only failing lanes touch memory.  When all lanes of a
+// warp belong to the same witness (single-witness, gate-parallel tiles) the warp first reduces its
+// minimum with redux.sync and issues a single atomicMin.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void report_fail(bool fail, uint32_t seq, uint32_t* first_fail, uint32_t widx, bool single_witness) {
+    unsigned act = __activemask();
+    unsigned fm = __ballot_sync(act, fail);
+    if (fm == 0) return;
+    if (single_witness) {
+        uint32_t m = __reduce_min_sync(act, fail ? seq : 0xFFFFFFFFu);
+        if ((threadIdx.x & 31) == (__ffs(act) - 1)) atomicMin(first_fail + widx, m);
+    } else if (fail) {
+        atomicMin(first_fail + widx, seq);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// constants: canonical residues -> Montgomery form (once per program upload)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void k_to_mont(uint32_t* consts, uint32_t n, FieldParams fp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a[N], r[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) a[k] = consts[(size_t)i * N + k];
+    fe_mont_mul<N>(r, a, fp.r2, fp.p, fp.n0inv);
+#pragma unroll
+    for (int k = 0; k < N; k++) consts[(size_t)i * N + k] = r[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// inputs: raw LE bytes -> Montgomery residues, witness-minor
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256)
+k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* __restrict__ store,
+              const uint32_t* __restrict__ consts_mont, InputDesc in, TileGeom g, uint32_t* unreduced_count, FieldParams fp) {
+    const uint64_t total = (uint64_t)n_loads << g.log2_wt;
+    const uint32_t wt_mask = (1u << g.log2_wt) - 1;
+    for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
+         tid += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lane = (uint32_t)tid & wt_mask;
+        InputLoad ld = loads[tid >> g.log2_wt];
+        uint32_t v[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = 0;
+        if (lane < g.n_valid) {
+            if (ld.kind == V_CONST) {
+#pragma unroll
+                for (int k = 0; k < N; k++) v[k] = consts_mont[(size_t)ld.index * N + k];
+            } else {
+                const uint8_t* src = (ld.kind == V_INSTANCE)
+                                         ? in.inst + (uint64_t)(g.batch0 + lane) * in.inst_set_stride
+                                         : in.wit + (uint64_t)(g.batch0 + lane) * in.wit_set_stride;
+                src += (uint64_t)ld.index * in.stride;
+                bool wide = false;
+                if (in.stride == 4 * N && ((uintptr_t)src & 3) == 0) {
+                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+                    for (int k = 0; k < N; k++) v[k] = s32[k];
+                } else {
+                    for (uint32_t b = 0; b < in.stride; b++) {
+                        uint32_t byte = src[b];
+                        if (b < 4 * N) v[b >> 2] |= byte << (8 * (b & 3));
+                        else if (byte) wide = true;
+                    }
+                }
+                // raw value >= p (or wider than the element): the reference keeps it unreduced
+                // (evaluator.rs:862-864, 896-898); the host resolves raw semantics, see backend.cu
+                uint32_t d[N];
+                uint32_t borrow = 0;
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    uint64_t t = (uint64_t)v[k] - fp.p[k] - borrow;
+                    d[k] = (uint32_t)t;
+                    borrow = (uint32_t)(t >> 63);
+                }
+                (void)d;
+                if (wide || borrow == 0) atomicAdd(unreduced_count, 1u);
+                uint32_t m[N];
+                fe_mont_mul<N>(m, v, fp.r2, fp.p, fp.n0inv);  // also reduces v in [p, 2^(32N)) mod p
+#pragma unroll
+                for (int k = 0; k < N; k++) v[k] = m[k];
+            }
+        }
+        store_elem<N>(store, ld.slot, lane, g.log2_wt, v);
+    }
+}
+
+// Gates that are rare on the arithmetic path; they run in their own kernel (k_level<N, true>) so the
+// hot ADD/MUL kernel stays small.  A level's ops are opcode-sorted, so the split is two sub-ranges.
+//   AND / XOR act on canonical residues (evaluator.rs:924-930): leave Montgomery form, operate, re-enter.
+//   NOT is (a == 0) ? 1 : 0 (evaluator.rs:932-938); zero is zero in Montgomery form too.
+//   ASSERT passes the operand through so the caller tests it.
+template <int N>
+__device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t opc, const FieldParams& fp) {
+    if (opc == D_AND || opc == D_XOR) {
+        uint32_t one[N], ca[N], cb[N], x[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) one[k] = (k == 0);
+        fe_mont_mul<N>(ca, a, one, fp.p, fp.n0inv);
+        fe_mont_mul<N>(cb, b, one, fp.p, fp.n0inv);
+        if (opc == D_AND) fe_and_canon<N>(x, ca, cb);
+        else fe_xor_canon<N>(x, ca, cb, fp.p);
+        fe_mont_mul<N>(r, x, fp.r2, fp.p, fp.n0inv);
+    } else if (opc == D_NOT) {
+        bool z = fe_is_zero<N>(a);
+#pragma unroll
+        for (int k = 0; k < N; k++) r[k] = z ? fp.one[k] : 0u;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; k++) r[k] = a[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one wavefront of gates for one tile of witnesses
+// thread <-> (gate, witness lane); lane is the fast index, so a warp works on ONE gate for 32
+// consecutive witnesses whenever the tile holds >= 32 witnesses (no divergence, coalesced rows).
+// ---------------------------------------------------------------------------------------------
+template <int N, bool RARE>
+__global__ void __launch_bounds__(256)
+k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
+        const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
+    const uint64_t total = n_ops << g.log2_wt;
+    const uint32_t wt_mask = (1u << g.log2_wt) - 1;
+    const bool single = g.log2_wt == 0;
+    for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
+         tid += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t lane = (uint32_t)tid & wt_mask;
+        const uint64_t gi = tid >> g.log2_wt;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ops) + gi);
+        const uint32_t opc = raw.w & 0xff;
+        uint32_t a[N], b[N], r[N];
+        load_elem<N>(a, store, raw.x, lane, g.log2_wt);
+        // second operand: a wire (ADD/MUL/AND/XOR) or an entry of the Montgomery constant table
+        if (!RARE) {
+            if (opc == D_ADDC || opc == D_MULC) {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)raw.y * N + k);
+            } else {
+                load_elem<N>(b, store, raw.y, lane, g.log2_wt);
+            }
+            if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
+            else fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
+        } else {
+            if (opc == D_AND || opc == D_XOR) {
+                load_elem<N>(b, store, raw.y, lane, g.log2_wt);
+            } else {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = 0;
+            }
+            rare_gate<N>(r, a, b, opc, fp);
+        }
+        if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
+        if (raw.w & F_ASSERT) {
+            bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
+            report_fail(fail, __ldg(aseq + gi), first_fail, g.batch0 + lane, single);
+        }
+    }
+}
+
+template <int N>
+__global__ void k_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
+                              uint32_t log2_wt, uint32_t* __restrict__ out, FieldParams fp) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a[N], one[N], r[N];
+    load_elem<N>(a, store, slots[i], lane, log2_wt);
+#pragma unroll
+    for (int k = 0; k < N; k++) one[k] = (k == 0);
+    fe_mont_mul<N>(r, a, one, fp.p, fp.n0inv);  // leave Montgomery form: canonical residue
+#pragma unroll
+    for (int k = 0; k < N; k++) out[(size_t)i * N + k] = r[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// p = 2, bit-sliced: word w of slot s holds witnesses 32w .. 32w+31
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bool_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* __restrict__ store,
+                   const uint32_t* __restrict__ const_bits, InputDesc in, TileGeom g, uint32_t* unreduced_count) {
+    const uint32_t log2_words = g.log2_wt - 5;
+    const uint64_t total = ((uint64_t)n_loads << g.log2_wt);  // one thread per (load, lane), ballot packs
+    for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
+         tid += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lane = (uint32_t)tid & ((1u << g.log2_wt) - 1);
+        InputLoad ld = loads[tid >> g.log2_wt];
+        uint32_t bit = 0;
+        if (lane < g.n_valid) {
+            if (ld.kind == V_CONST) {
+                bit = const_bits[ld.index] & 1;
+            } else {
+                const uint8_t* src = (ld.kind == V_INSTANCE)
+                                         ? in.inst + (uint64_t)(g.batch0 + lane) * in.inst_set_stride
+                                         : in.wit + (uint64_t)(g.batch0 + lane) * in.wit_set_stride;
+                src += (uint64_t)ld.index * in.stride;
+                uint32_t hi = 0;
+                for (uint32_t b = 0; b < in.stride; b++) hi |= (b == 0) ? (uint32_t)(src[0] >> 1) : (uint32_t)src[b];
+                bit = src[0] & 1;
+                if (hi) atomicAdd(unreduced_count, 1u);
+            }
+        }
+        // blockDim is a multiple of 32 and total a multiple of 32: full warps only
+        uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+        if ((lane & 31) == 0) store[((size_t)ld.slot << log2_words) + (lane >> 5)] = word;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
+             const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail, TileGeom g) {
+    const uint32_t log2_words = g.log2_wt - 5;
+    const uint64_t total = n_ops << log2_words;
+    const uint32_t wmask = (1u << log2_words) - 1;
+    for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
+         tid += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)tid & wmask;
+        const uint64_t gi = tid >> log2_words;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ops) + gi);
+        const uint32_t opc = raw.w & 0xff;
+        const uint32_t a = store[((size_t)raw.x << log2_words) + w];
+        uint32_t r;
+        switch (opc) {
+            case D_ADD:
+            case D_XOR: r = a ^ store[((size_t)raw.y << log2_words) + w]; break;
+            case D_MUL:
+            case D_AND: r = a & store[((size_t)raw.y << log2_words) + w]; break;
+            case D_ADDC: r = a ^ (0u - (__ldg(const_bits + raw.y) & 1)); break;
+            case D_MULC: r = a & (0u - (__ldg(const_bits + raw.y) & 1)); break;
+            case D_NOT: r = ~a; break;
+            default: r = a; break;
+        }
+        if (!(raw.w & F_NOSTORE)) store[((size_t)raw.z << log2_words) + w] = r;
+        if (raw.w & F_ASSERT) {
+            uint32_t first_lane = w << 5;
+            uint32_t valid = g.n_valid > first_lane ? (g.n_valid - first_lane >= 32 ? 0xFFFFFFFFu : ((1u << (g.n_valid - first_lane)) - 1)) : 0u;
+            uint32_t bad = r & valid;
+            if (bad) {
+                uint32_t seq = __ldg(aseq + gi);
+                while (bad) {
+                    int bpos = __ffs(bad) - 1;
+                    bad &= bad - 1;
+                    atomicMin(first_fail + g.batch0 + first_lane + bpos, seq);
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_bool_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
+                                   uint32_t log2_wt, uint32_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t word = store[((size_t)slots[i] << (log2_wt - 5)) + (lane >> 5)];
+    out[i] = (word >> (lane & 31)) & 1;
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------------------------
+static inline unsigned grid_for(uint64_t total, int sm_count, int per_sm) {
+    uint64_t blocks = (total + 255) / 256;
+    uint64_t cap = (uint64_t)sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (unsigned)blocks;
+}
+
+#define ZKB_DISPATCH_N(nlimb, CALL)         \
+    switch (nlimb) {                        \
+        case 1: { constexpr int N = 1; CALL; } break; \
+        case 2: { constexpr int N = 2; CALL; } break; \
+        case 4: { constexpr int N = 4; CALL; } break; \
+        default: { constexpr int N = 8; CALL; } break; \
+    }
+
+void launch_to_mont(int nlimb, uint32_t* consts, uint32_t n, const FieldParams& fp, cudaStream_t s) {
+    if (n == 0) return;
+    ZKB_DISPATCH_N(nlimb, (k_to_mont<N><<<(n + 127) / 128, 128, 0, s>>>(consts, n, fp)));
+}
+
+void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* consts_mont,
+                        InputDesc in, TileGeom g, uint32_t* unreduced_count, const FieldParams& fp, cudaStream_t s) {
+    if (n_loads == 0) return;
+    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 16);
+    ZKB_DISPATCH_N(nlimb, (k_load_inputs<N><<<grid, 256, 0, s>>>(loads, n_loads, store, consts_mont, in, g, unreduced_count, fp)));
+}
+
+void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
+                  const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp, int sm_count,
+                  bool rare, cudaStream_t s) {
+    if (n_ops == 0) return;
+    // persistent-style grid: a whole number of CTAs per SM (148 SMs x 8 CTAs of 256 threads fills
+    // the 2048-thread SM when the kernel stays <= 32 registers/thread; fewer resident otherwise)
+    unsigned grid = grid_for(n_ops << g.log2_wt, sm_count, 8);
+    if (!rare) {
+        ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+    } else {
+        ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+    }
+}
+
+void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
+                        uint32_t* out, const FieldParams& fp, cudaStream_t s) {
+    if (n == 0) return;
+    ZKB_DISPATCH_N(nlimb, (k_read_values<N><<<(n + 127) / 128, 128, 0, s>>>(slots, n, store, lane, log2_wt, out, fp)));
+}
+
+void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* const_bits, InputDesc in,
+                             TileGeom g, uint32_t* unreduced_count, cudaStream_t s) {
+    if (n_loads == 0) return;
+    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 16);
+    k_bool_load_inputs<<<grid, 256, 0, s>>>(loads, n_loads, store, const_bits, in, g, unreduced_count);
+}
+
+void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
+                       uint32_t* first_fail, TileGeom g, int sm_count, cudaStream_t s) {
+    if (n_ops == 0) return;
+    unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, 8);
+    k_bool_level<<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, g);
+}
+
+void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
+                             uint32_t* out, cudaStream_t s) {
+    if (n == 0) return;
+    k_bool_read_values<<<(n + 127) / 128, 128, 0, s>>>(slots, n, store, lane, log2_wt, out);
+}
+
+void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s) {
+    if (n == 0) return;
+    k_fill_u32<<<grid_for(n, 148, 8), 256, 0, s>>>(p, v, n);
+}
+
+}  // namespace zkb

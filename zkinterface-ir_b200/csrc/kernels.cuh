@@ -1,0 +1,52 @@
+// Launch wrappers of the sm_100a kernels (kernels.cu).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "field.cuh"
+#include "program.h"
+
+namespace zkb {
+
+// Wire store layout (limb-chunk-major, witness-minor):
+//   an element of N 32-bit limbs is split in NC = max(1, N/4) chunks of CW = min(N, 4) limbs;
+//   chunk c of slot s for witness lane j lives at  ((s*NC + c) * Wt + j) * CW  (uint32 units),
+//   so a warp reading one chunk of one slot for 32 consecutive witnesses issues one fully
+//   coalesced 16-byte-per-lane (512 B) request when N >= 4.
+struct TileGeom {
+    uint32_t log2_wt;   // witnesses per tile (power of two)
+    uint32_t n_valid;   // lanes of this tile that hold real witnesses
+    uint32_t batch0;    // global index of lane 0
+    uint32_t pad;
+};
+
+struct InputDesc {
+    const uint8_t* inst;      // instance values, raw little-endian, `stride` bytes each
+    const uint8_t* wit;       // witness values
+    uint64_t inst_set_stride; // bytes between consecutive witnesses' instance vectors (0: shared)
+    uint64_t wit_set_stride;  // bytes between consecutive witnesses' witness vectors
+    uint32_t stride;          // bytes per value
+    uint32_t pad;
+};
+
+// arithmetic fields (odd p, Montgomery form)
+void launch_to_mont(int nlimb, uint32_t* consts, uint32_t n, const FieldParams& fp, cudaStream_t s);
+void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* consts_mont,
+                        InputDesc in, TileGeom g, uint32_t* unreduced_count, const FieldParams& fp, cudaStream_t s);
+void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
+                  const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp, int sm_count,
+                  bool rare, cudaStream_t s);
+void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
+                        uint32_t* out, const FieldParams& fp, cudaStream_t s);
+
+// p = 2: bit-sliced, one uint32 word = 32 witnesses
+void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* const_bits, InputDesc in,
+                             TileGeom g, uint32_t* unreduced_count, cudaStream_t s);
+void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
+                       uint32_t* first_fail, TileGeom g, int sm_count, cudaStream_t s);
+void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
+                             uint32_t* out, cudaStream_t s);
+
+void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
+
+}  // namespace zkb

@@ -1,0 +1,246 @@
+#include "program.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace zkb {
+
+bool Program::set_field(const uint8_t* mod_le, size_t len, uint32_t degree, std::string& err) {
+    BigU m = BigU::from_bytes_le(mod_le, len);
+    // PlaintextBackend::set_field, evaluator.rs:866-875 — same two errors, same order
+    if (m.is_zero()) {
+        err = "Modulus cannot be zero.";
+        return false;
+    }
+    if (degree != 1) {
+        err = "Field should be of degree 1";
+        return false;
+    }
+    if (field_set) {
+        if (!(m == modulus) && n_values() > 0) {
+            err = "zkb: the field characteristic changed between relation messages (unsupported on device)";
+            return false;
+        }
+        if (m == modulus) return true;
+    }
+    if (m.is_one()) {
+        // SURVEY.md §8a trap 10: p = 1 makes the reference's `exp` recurse forever on a Switch
+        err = "zkb: modulus 1 is not a field (the reference would not terminate on a Switch)";
+        return false;
+    }
+    if (m.bits() > 32 * kMaxLimbs) {
+        err = "zkb: field characteristic wider than 256 bits is not supported on device";
+        return false;
+    }
+    bool is_two = (m.w.size() == 1 && m.w[0] == 2);
+    if (!m.bit(0) && !is_two) {
+        err = "zkb: even modulus other than 2 is not supported on device (Montgomery form needs an odd modulus)";
+        return false;
+    }
+    modulus = m;
+    modulus_le.assign(mod_le, mod_le + len);
+    binary = is_two;
+    size_t bits = m.bits();
+    nlimb = bits <= 32 ? 1 : bits <= 64 ? 2 : bits <= 128 ? 4 : 8;
+    memset(&fp, 0, sizeof(fp));
+    fp.nlimb = (uint32_t)nlimb;
+    m.to_limbs(fp.p, kMaxLimbs);
+    if (!binary) {
+        // n0inv = -p^{-1} mod 2^32 (Newton iteration on the odd low limb)
+        uint32_t p0 = fp.p[0], inv = 1;
+        for (int i = 0; i < 5; i++) inv *= 2 - p0 * inv;
+        fp.n0inv = (uint32_t)(0u - inv);
+        BigU R;
+        R.w.assign((size_t)nlimb + 1, 0);
+        R.w[nlimb] = 1;
+        BigU Rm = R.mod(m);
+        BigU R2 = BigU::mulmod(Rm, Rm, m);
+        Rm.to_limbs(fp.one, kMaxLimbs);
+        R2.to_limbs(fp.r2, kMaxLimbs);
+    } else {
+        fp.one[0] = 1;
+        fp.r2[0] = 1;
+    }
+    field_set = true;
+    return true;
+}
+
+uint32_t Program::intern_const(const uint8_t* le, size_t n) {
+    while (n > 0 && le[n - 1] == 0) n--;
+    std::string key((const char*)le, n);
+    auto it = const_index.find(key);
+    if (it != const_index.end()) return it->second;
+    uint32_t idx = n_consts();
+    BigU v = BigU::from_bytes_le(le, n);
+    bool unreduced = field_set && (v >= modulus);
+    BigU r = unreduced ? v.mod(modulus) : v;
+    size_t base = const_limbs.size();
+    const_limbs.resize(base + (size_t)std::max(nlimb, 1), 0);
+    r.to_limbs(&const_limbs[base], std::max(nlimb, 1));
+    const_unreduced.push_back(unreduced ? 1 : 0);
+    const_raw.emplace_back();
+    if (unreduced) const_raw.back().assign(le, le + n);
+    const_index.emplace(std::move(key), idx);
+    return idx;
+}
+
+std::vector<uint8_t> Program::minus_one_le() const {
+    BigU m = modulus;
+    m.sub(BigU(1));
+    std::vector<uint8_t> out((size_t)nlimb * 4, 0);
+    for (size_t i = 0; i < out.size(); i++) out[i] = (uint8_t)(m.limb(i / 4) >> (8 * (i % 4)));
+    while (out.size() > 1 && out.back() == 0) out.pop_back();
+    return out;
+}
+
+static inline uint32_t dev_op_of(uint8_t k) {
+    switch (k) {
+        case V_ADD: return D_ADD;
+        case V_MUL: return D_MUL;
+        case V_ADDC: return D_ADDC;
+        case V_MULC: return D_MULC;
+        case V_AND: return D_AND;
+        case V_XOR: return D_XOR;
+        case V_NOT: return D_NOT;
+        default: return D_OPS;
+    }
+}
+
+void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>* live_values) {
+    const uint32_t n = prog.n_values();
+    const uint8_t* kind = prog.kind.data();
+    const uint32_t* opa = prog.opa.data();
+    const uint32_t* opb = prog.opb.data();
+
+    std::vector<uint32_t> level(n);
+    std::vector<uint8_t> used(n, 0);  // consumed by another value
+    uint32_t max_level = 0;
+    for (uint32_t v = 0; v < n; v++) {
+        uint8_t k = kind[v];
+        if (k <= V_WITNESS) {
+            level[v] = 0;
+            continue;
+        }
+        uint32_t la = level[opa[v]];
+        used[opa[v]] = 1;
+        bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
+        if (two) {
+            uint32_t lb = level[opb[v]];
+            used[opb[v]] = 1;
+            if (lb > la) la = lb;
+        }
+        level[v] = la + 1;
+        if (la + 1 > max_level) max_level = la + 1;
+    }
+    // earliest assert per value (a value that is non-zero fails at its first assert)
+    std::vector<uint32_t> aseq(n, kNoSeq);
+    for (size_t s = 0; s < prog.asserts.size(); s++) {
+        uint32_t v = prog.asserts[s].value;
+        if (aseq[v] == kNoSeq) aseq[v] = (uint32_t)s;  // asserts are in program order: first wins
+    }
+    std::vector<uint8_t> observable;
+    if (!keep_all) {
+        observable.assign(n, 0);
+        if (live_values)
+            for (uint32_t v : *live_values) observable[v] = 1;
+    }
+
+    // standalone asserts on level-0 values run in level 1
+    input_assert_seq.clear();
+    input_assert_value.clear();
+    for (uint32_t v = 0; v < n; v++)
+        if (kind[v] <= V_WITNESS && aseq[v] != kNoSeq) {
+            input_assert_seq.push_back(aseq[v]);
+            input_assert_value.push_back(v);
+        }
+    if (!input_assert_seq.empty() && max_level < 1) max_level = 1;
+    n_levels = max_level;
+
+    // counting sort of device ops by (level, opcode)
+    const size_t n_keys = (size_t)n_levels * D_OPS;
+    std::vector<uint64_t> cnt(n_keys + 1, 0);
+    for (uint32_t v = 0; v < n; v++)
+        if (kind[v] > V_WITNESS) cnt[(size_t)(level[v] - 1) * D_OPS + dev_op_of(kind[v]) + 1]++;
+    cnt[(size_t)0 * D_OPS + D_ASSERT + 1] += input_assert_seq.size();
+    for (size_t i = 0; i < n_keys; i++) cnt[i + 1] += cnt[i];
+    const uint64_t n_ops = cnt[n_keys];
+    level_off.assign((size_t)n_levels + 1, 0);
+    for (uint32_t l = 0; l <= n_levels; l++) level_off[l] = cnt[(size_t)l * D_OPS];
+    level_rare.assign((size_t)n_levels, 0);
+    for (uint32_t l = 0; l < n_levels; l++) level_rare[l] = cnt[(size_t)l * D_OPS + D_AND];
+    max_level_ops = 0;
+    for (uint32_t l = 0; l < n_levels; l++)
+        max_level_ops = (uint32_t)std::max<uint64_t>(max_level_ops, level_off[l + 1] - level_off[l]);
+
+    // pass 1: place values (order index) and assign slots in placement order
+    slot_of_value.assign(n, kNoSlot);
+    loads.clear();
+    uint32_t next_slot = 0;
+    for (uint32_t v = 0; v < n; v++)
+        if (kind[v] <= V_WITNESS) {
+            slot_of_value[v] = next_slot;
+            loads.push_back(InputLoad{next_slot, kind[v], opb[v], 0});
+            next_slot++;
+        }
+    std::vector<uint64_t> pos_of_value(n, 0);
+    {
+        std::vector<uint64_t> cur(cnt.begin(), cnt.end() - 1);
+        for (uint32_t v = 0; v < n; v++)
+            if (kind[v] > V_WITNESS) pos_of_value[v] = cur[(size_t)(level[v] - 1) * D_OPS + dev_op_of(kind[v])]++;
+    }
+    // slots must follow the sorted order, so walk ops by position
+    std::vector<uint32_t> value_at(n_ops, kNoSlot);
+    for (uint32_t v = 0; v < n; v++)
+        if (kind[v] > V_WITNESS) value_at[pos_of_value[v]] = v;
+    ops.assign(n_ops, GateOp{0, 0, 0, 0});
+    op_assert_seq.assign(n_ops, kNoSeq);
+    for (int i = 0; i < D_OPS; i++) n_dev_ops[i] = 0;
+    std::vector<uint32_t> meta_of(n_ops, 0);
+    for (uint64_t i = 0; i < n_ops; i++) {
+        uint32_t v = value_at[i];
+        if (v == kNoSlot) continue;  // standalone assert position
+        uint32_t meta = dev_op_of(kind[v]);
+        bool has_assert = aseq[v] != kNoSeq;
+        if (has_assert) meta |= F_ASSERT;
+        bool store = keep_all || used[v] || observable[v] || !has_assert;
+        if (!store) meta |= F_NOSTORE;
+        else slot_of_value[v] = next_slot++;
+        meta_of[i] = meta;
+    }
+    n_slots = next_slot;
+    // pass 2: emit ops with operand slots
+    for (uint64_t i = 0; i < n_ops; i++) {
+        uint32_t v = value_at[i];
+        if (v == kNoSlot) continue;
+        uint8_t k = kind[v];
+        GateOp g;
+        g.meta = meta_of[i];
+        g.a = slot_of_value[opa[v]];
+        bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
+        g.b = two ? slot_of_value[opb[v]] : opb[v];
+        g.out = slot_of_value[v];
+        ops[i] = g;
+        op_assert_seq[i] = aseq[v];
+        n_dev_ops[g.meta & 0xff]++;
+    }
+    {
+        uint64_t p = cnt[(size_t)0 * D_OPS + D_ASSERT];
+        for (size_t i = 0; i < input_assert_seq.size(); i++, p++) {
+            GateOp g;
+            g.meta = D_ASSERT | F_ASSERT | F_NOSTORE;
+            g.a = slot_of_value[input_assert_value[i]];
+            g.b = 0;
+            g.out = kNoSlot;
+            ops[p] = g;
+            op_assert_seq[p] = input_assert_seq[i];
+            n_dev_ops[D_ASSERT]++;
+        }
+    }
+    const uint64_t E = prog.binary ? 1 : (uint64_t)prog.nlimb * 4;
+    const uint64_t* c = prog.cb_count;
+    algo_bytes_per_witness = 3 * E * (c[CB_ADD] + c[CB_MUL] + c[CB_AND] + c[CB_XOR]) +
+                             2 * E * (c[CB_ADDC] + c[CB_MULC] + c[CB_NOT]) + E * c[CB_ASSERT_ZERO];
+}
+
+}  // namespace zkb

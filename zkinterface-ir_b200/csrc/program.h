@@ -1,0 +1,149 @@
+// Host-side recorded program and its levelized device plan.
+//
+// `Program` is the recording half of the deferred backend: every ZKBackend
+// callback of the reference (rust/src/consumers/evaluator.rs:17-76) appends one
+// SSA value instead of computing it — the same idea as the reference's own
+// `IRFlattener` (rust/src/consumers/flattening.rs:83-190).  `copy` is an alias
+// (no value is created: the copy of a wire has, by definition, the same value).
+//
+// `Plan` is the host-preparation pass of BASELINE.json:north_star: ASAP
+// levelization of the SSA list into wavefronts, per-level sorting by opcode,
+// slot assignment in level order (so every level writes one contiguous slot
+// range), and fusion of AssertZero into the producing gate.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "bigu.h"
+#include "field.cuh"
+
+namespace zkb {
+
+// SSA value kinds (what produced the value)
+enum ValKind : uint8_t {
+    V_CONST = 0,   // b = const-pool index
+    V_INSTANCE,    // b = index in the instance stream
+    V_WITNESS,     // b = index in the witness stream
+    V_ADD,
+    V_MUL,
+    V_ADDC,  // b = const-pool index
+    V_MULC,  // b = const-pool index
+    V_AND,
+    V_XOR,
+    V_NOT,
+    V_KINDS
+};
+
+// callback counters (one per ZKBackend method that the Evaluator drives)
+enum CbKind { CB_CONSTANT = 0, CB_INSTANCE, CB_WITNESS, CB_ADD, CB_MUL, CB_ADDC, CB_MULC, CB_AND, CB_XOR,
+              CB_NOT, CB_COPY, CB_ASSERT_ZERO, CB_KINDS };
+
+// device opcodes (GateOp.meta & 0xff)
+enum DevOp : uint32_t { D_ADD = 0, D_MUL, D_ADDC, D_MULC, D_AND, D_XOR, D_NOT, D_ASSERT, D_OPS };
+constexpr uint32_t F_ASSERT = 1u << 8;    // result must be zero; assert seq in Plan::op_assert_seq
+constexpr uint32_t F_NOSTORE = 1u << 9;   // value is consumed by nothing but the fused assert
+constexpr uint32_t kNoSeq = 0xFFFFFFFFu;
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+
+struct GateOp {  // 16 bytes, one per device gate
+    uint32_t a;     // operand slot
+    uint32_t b;     // operand slot, or const-pool index for ADDC/MULC
+    uint32_t out;   // destination slot
+    uint32_t meta;  // DevOp | flags
+};
+
+struct AssertRec {
+    uint32_t value;     // asserted SSA value
+    uint32_t pos;       // number of SSA values recorded before it (program position)
+    uint64_t src_wire;  // local-scope wire id of the AssertZero gate (evaluator.rs:357-362)
+};
+
+struct InputLoad {  // level-0 values: filled by the input kernel on every pass
+    uint32_t slot;
+    uint32_t kind;   // V_CONST / V_INSTANCE / V_WITNESS
+    uint32_t index;  // const-pool index or stream index
+    uint32_t pad;
+};
+
+class Program {
+public:
+    // ---- field -----------------------------------------------------------
+    bool field_set = false;
+    std::vector<uint8_t> modulus_le;  // as given (trailing zeros kept)
+    BigU modulus;
+    bool binary = false;  // p == 2: bit-sliced device path
+    int nlimb = 0;
+    FieldParams fp{};
+
+    // PlaintextBackend::set_field, evaluator.rs:866-875 (+ device limits)
+    bool set_field(const uint8_t* mod_le, size_t len, uint32_t degree, std::string& err);
+
+    // ---- recording -------------------------------------------------------
+    std::vector<uint8_t> kind;
+    std::vector<uint32_t> opa, opb;
+    std::vector<AssertRec> asserts;
+    uint64_t cb_count[CB_KINDS] = {0};
+    uint64_t ir_gates = 0;  // Add/Mul/AddC/MulC/And/Xor/Not/AssertZero IR gates ingested (metric numerator)
+    uint32_t n_instance = 0, n_witness = 0;
+
+    // const pool: canonical residues (< p), nlimb limbs each; unreduced inputs remembered raw
+    std::vector<uint32_t> const_limbs;
+    std::vector<uint8_t> const_unreduced;                 // 1 if the raw constant was >= p
+    std::vector<std::vector<uint8_t>> const_raw;          // raw bytes (only kept when unreduced)
+    std::unordered_map<std::string, uint32_t> const_index;
+    uint32_t n_consts() const { return (uint32_t)const_unreduced.size(); }
+    uint32_t intern_const(const uint8_t* le, size_t n);
+
+    uint32_t n_values() const { return (uint32_t)kind.size(); }
+    uint32_t push_value(uint8_t k, uint32_t a, uint32_t b) {
+        kind.push_back(k);
+        opa.push_back(a);
+        opb.push_back(b);
+        return (uint32_t)kind.size() - 1;
+    }
+    // ZKBackend-shaped recording methods
+    uint32_t constant(const uint8_t* le, size_t n) { cb_count[CB_CONSTANT]++; return push_value(V_CONST, 0, intern_const(le, n)); }
+    uint32_t instance() { cb_count[CB_INSTANCE]++; return push_value(V_INSTANCE, 0, n_instance++); }
+    uint32_t witness() { cb_count[CB_WITNESS]++; return push_value(V_WITNESS, 0, n_witness++); }
+    uint32_t copy(uint32_t a) { cb_count[CB_COPY]++; return a; }
+    uint32_t add(uint32_t a, uint32_t b) { cb_count[CB_ADD]++; return push_value(V_ADD, a, b); }
+    uint32_t multiply(uint32_t a, uint32_t b) { cb_count[CB_MUL]++; return push_value(V_MUL, a, b); }
+    uint32_t add_constant(uint32_t a, const uint8_t* le, size_t n) { cb_count[CB_ADDC]++; return push_value(V_ADDC, a, intern_const(le, n)); }
+    uint32_t mul_constant(uint32_t a, const uint8_t* le, size_t n) { cb_count[CB_MULC]++; return push_value(V_MULC, a, intern_const(le, n)); }
+    uint32_t and_(uint32_t a, uint32_t b) { cb_count[CB_AND]++; return push_value(V_AND, a, b); }
+    uint32_t xor_(uint32_t a, uint32_t b) { cb_count[CB_XOR]++; return push_value(V_XOR, a, b); }
+    uint32_t not_(uint32_t a) { cb_count[CB_NOT]++; return push_value(V_NOT, a, 0); }
+    void assert_zero(uint32_t v, uint64_t src_wire) {
+        cb_count[CB_ASSERT_ZERO]++;
+        asserts.push_back(AssertRec{v, n_values(), src_wire});
+    }
+    // constants the Evaluator needs: p-1 and 1 as little-endian bytes
+    std::vector<uint8_t> minus_one_le() const;
+};
+
+struct Plan {
+    uint32_t n_slots = 0;
+    uint32_t n_levels = 0;
+    std::vector<uint32_t> slot_of_value;  // SSA value -> slot (kNoSlot if never stored)
+    std::vector<GateOp> ops;              // level-major, opcode-sorted inside a level
+    std::vector<uint32_t> op_assert_seq;  // parallel to ops
+    std::vector<uint64_t> level_off;      // n_levels + 1 offsets into ops
+    std::vector<uint64_t> level_rare;     // per level: where the rare opcodes (>= D_AND) start
+    std::vector<InputLoad> loads;
+    // raw-semantics bookkeeping (SURVEY.md §8a trap 1): asserts applied directly to an input value
+    std::vector<uint32_t> input_assert_seq;    // assert seq ...
+    std::vector<uint32_t> input_assert_value;  // ... on this level-0 SSA value
+    // accounting for bench.py (algorithmic bytes per witness)
+    uint64_t n_dev_ops[D_OPS] = {0};
+    uint64_t algo_bytes_per_witness = 0;
+    uint32_t max_level_ops = 0;
+
+    // keep_all: every value stays readable (zkb_read_values); otherwise values consumed by
+    // nothing but their own assert are not stored.
+    void build(const Program& prog, bool keep_all, const std::vector<uint32_t>* live_values);
+};
+
+}  // namespace zkb
