@@ -180,6 +180,16 @@ typedef struct {
 } zkb_stats;
 int zkb_get_stats(zkb_ctx* ctx, zkb_stats* out);
 
+/* Inspection of the recorded SSA program (host preparation parity checks): values
+ * [first, first+n) -> kind (0 const, 1 instance, 2 witness, 3 add, 4 mul, 5 addc, 6 mulc, 7 and,
+ * 8 xor, 9 not), operand a (value handle), operand b (value handle, or constant-pool index for
+ * const/addc/mulc, or stream position for instance/witness). */
+int zkb_get_program(zkb_ctx* ctx, uint64_t first, uint64_t n, uint8_t* kinds, uint32_t* a, uint32_t* b);
+/* canonical residue of constant-pool entry idx (little-endian) */
+int zkb_get_const(zkb_ctx* ctx, uint64_t idx, uint8_t* out_le, size_t cap, size_t* len);
+/* asserted value handle of assertion seq */
+int zkb_assert_value(zkb_ctx* ctx, uint64_t seq, zkb_wire* value);
+
 typedef struct {
     float h2d_ms;       /* input upload */
     float load_ms;      /* input-conversion kernels */

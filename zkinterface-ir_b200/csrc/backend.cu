@@ -674,3 +674,30 @@ extern "C" int zkb_get_timing(zkb_ctx* c, zkb_timing* t) {
     *t = c->timing;
     return ZKB_OK;
 }
+
+extern "C" int zkb_get_program(zkb_ctx* c, uint64_t first, uint64_t n, uint8_t* kinds, uint32_t* a, uint32_t* b) {
+    const Program& p = c->prog;
+    if (first + n > p.n_values()) return c->fail(ZKB_E_ARG, "program range out of bounds");
+    for (uint64_t i = 0; i < n; i++) {
+        kinds[i] = p.kind[first + i];
+        a[i] = p.opa[first + i];
+        b[i] = p.opb[first + i];
+    }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_get_const(zkb_ctx* c, uint64_t idx, uint8_t* out, size_t cap, size_t* len) {
+    const Program& p = c->prog;
+    if (idx >= p.n_consts()) return c->fail(ZKB_E_ARG, "constant index out of range");
+    size_t nb = (size_t)p.nlimb * 4;
+    if (cap < nb) return c->fail(ZKB_E_ARG, "output buffer too small");
+    memcpy(out, &p.const_limbs[idx * (size_t)p.nlimb], nb);
+    if (len) *len = nb;
+    return ZKB_OK;
+}
+
+extern "C" int zkb_assert_value(zkb_ctx* c, uint64_t seq, zkb_wire* value) {
+    if (seq >= c->prog.asserts.size()) return c->fail(ZKB_E_ARG, "assert index out of range");
+    *value = c->prog.asserts[seq].value;
+    return ZKB_OK;
+}
