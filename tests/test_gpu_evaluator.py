@@ -44,7 +44,7 @@ def test_statement_true_and_every_value(name):
     assert viol == ev.evaluate(msgs) == []
     o = check_all_values(b, msgs)
     for wid, val in o.values.items():            # Evaluator::get on the live top-scope wires
-        assert e.get(wid) == val
+        assert e.get(wid) == val[1]
 
 
 def test_example_wrong_witness_exact_text():
@@ -129,9 +129,9 @@ def test_nested_structures_random(seed=5):
         gates += [("Free", 3, 8), ("Add", 3, 9, 14), ("AddConstant", 4, 3, b"\x09"), ("Free", 9, 13)]
         rel = ir.Relation(h, ir.ARITH, ir.FOR_FUNCTION_SWITCH, [sq, two, inner], gates)
         for trial in range(4):
-            wit = [ir.le_bytes(int(rng.integers(0, 3))) for _ in range(2)] + [ir.le_bytes(int(rng.integers(0, p))) for _ in range(12)]
+            wit = [ir.le_bytes(int(rng.integers(0, 3))) for _ in range(2)] + [ir.le_bytes(int.from_bytes(rng.bytes(16), "little") % p) for _ in range(12)]
             wit[1] = ir.le_bytes(int(rng.integers(1, 3)))
-            inst = [ir.le_bytes(int(rng.integers(0, p))) for _ in range(6)]
+            inst = [ir.le_bytes(int.from_bytes(rng.bytes(16), "little") % p) for _ in range(6)]
             msgs = [ir.Instance(h, inst), ir.Witness(h, wit), rel]
             expected = ev.evaluate(msgs)
             z, b, e, viol = run_gpu(msgs)
@@ -139,7 +139,7 @@ def test_nested_structures_random(seed=5):
             if not expected:
                 o = check_all_values(b, msgs)
                 for wid, val in o.values.items():
-                    assert e.get(wid) == val
+                    assert e.get(wid) == val[1]
 
 
 def test_batch_through_evaluator_program():

@@ -206,3 +206,105 @@ def algorithmic_bytes_per_witness(c: FlatCircuit) -> int:
     """Add/Mul = 3E, AssertZero = E"""
     E = elem_bytes(c.p)
     return 3 * E * (c.hist["add"] + c.hist["mul"]) + E * c.hist["assert_zero"]
+
+
+# ---------------------------------------------------------------------------------------------
+# C4: "multiplication-gate" shaped R1CS (SURVEY.md section 8d)
+# ---------------------------------------------------------------------------------------------
+class R1cs:
+    def __init__(self):
+        self.p = 0
+        self.n_rows = 0
+        self.n_vars = 0
+        self.n_free = 0
+        self.A = self.B = self.C = None   # (row_ptr uint64, col uint32, coef_idx uint32)
+        self.coef_table = None            # uint8 [n_coefs, elem_bytes]
+        self.coefs = None                 # python ints
+        self.nnz = 0
+
+
+def random_r1cs(n_rows: int, n_free: int, p: int, seed: int) -> R1cs:
+    """Row r: (A_r . z)(B_r . z) = z[s_r] with s_r = n_free + 1 + r a fresh slack variable.
+    A_r, B_r: 1 + Poisson(2) terms (capped at 8) over uniformly chosen ids < s_r; coefficients from a
+    seeded 256-entry table plus {1, p-1}.  Variable 0 is the constant one."""
+    rng = np.random.default_rng(seed)
+    eb = elem_bytes(p)
+    coefs = [1, p - 1] + [int.from_bytes(rng.bytes(eb), "little") % p for _ in range(256)]
+    r = R1cs()
+    r.p = p
+    r.n_rows = n_rows
+    r.n_free = n_free
+    r.n_vars = 1 + n_free + n_rows
+    r.coefs = coefs
+    r.coef_table = np.stack([le_bytes(c, eb) for c in coefs])
+    mats = []
+    for _ in range(2):
+        cnt = np.minimum(1 + rng.poisson(2.0, size=n_rows), 8).astype(np.int64)
+        row_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+        nnz = int(row_ptr[-1])
+        rows = np.repeat(np.arange(n_rows, dtype=np.int64), cnt)
+        limit = n_free + 1 + rows                       # ids < s_r
+        col = (rng.random(nnz) * limit).astype(np.int64).astype(np.uint32)
+        ci = rng.integers(0, len(coefs), size=nnz).astype(np.uint32)
+        # half of the coefficients are the literal 1, as in real R1CS
+        ci[rng.random(nnz) < 0.5] = 0
+        mats.append((row_ptr, col, ci))
+    r.A, r.B = mats
+    r.C = (np.arange(n_rows + 1, dtype=np.uint64), (n_free + 1 + np.arange(n_rows)).astype(np.uint32),
+           np.zeros(n_rows, dtype=np.uint32))
+    r.nnz = int(r.A[0][-1] + r.B[0][-1] + n_rows)
+    return r
+
+
+def r1cs_assignment(r: R1cs, seed: int):
+    """A satisfying assignment z (python ints): free variables random, slack z[s_r] := (A_r.z)(B_r.z) mod p."""
+    rng = np.random.default_rng(seed ^ 0xA551)
+    p = r.p
+    free = random_field_elements(rng, (r.n_free,), p)
+    z = [1] + [int.from_bytes(free[i].tobytes(), "little") for i in range(r.n_free)] + [0] * r.n_rows
+    coefs = r.coefs
+    (rpa, ca, ia), (rpb, cb, ib) = r.A, r.B
+    rpa, ca, ia, rpb, cb, ib = (x.tolist() for x in (rpa, ca, ia, rpb, cb, ib))
+    base = r.n_free + 1
+    for row in range(r.n_rows):
+        a = 0
+        for e in range(rpa[row], rpa[row + 1]):
+            a += coefs[ia[e]] * z[ca[e]]
+        b = 0
+        for e in range(rpb[row], rpb[row + 1]):
+            b += coefs[ib[e]] * z[cb[e]]
+        z[base + row] = (a % p) * (b % p) % p
+    return z
+
+
+def assignment_bytes(z, p: int) -> np.ndarray:
+    eb = elem_bytes(p)
+    buf = b"".join(int(v).to_bytes(eb, "little") for v in z)
+    return np.frombuffer(buf, dtype=np.uint8).reshape(len(z), eb).copy()
+
+
+def r1cs_first_row_reading(r: R1cs, var: int) -> int:
+    """first row whose A, B or C mentions variable `var`"""
+    best = r.n_rows
+    for rp, col, _ in (r.A, r.B, r.C):
+        hits = np.flatnonzero(col == var)
+        if len(hits):
+            row = int(np.searchsorted(rp, hits[0], side="right") - 1)
+            best = min(best, row)
+    return best
+
+
+def r1cs_algorithmic_bytes(r: R1cs) -> int:
+    """per nnz 4 B col + 4 B coef index + E gathered z; per row 3 x 4 B row_ptr"""
+    return (8 + elem_bytes(r.p)) * r.nnz + 12 * r.n_rows
+
+
+def r1cs_gate_equivalent(r: R1cs) -> int:
+    """gates `zkif-to-ir` emits for this system: 2 per term with id != 0 (Constant + Mul), 1 per id-0 term,
+    (terms - 1) Adds per LC, 4 per row (from_r1cs.rs:71-125)"""
+    total = 0
+    for rp, col, _ in (r.A, r.B, r.C):
+        total += int(2 * (col != 0).sum() + (col == 0).sum())
+        cnt = np.diff(rp.astype(np.int64))
+        total += int(np.maximum(cnt - 1, 0).sum() + (cnt == 0).sum())
+    return total + 4 * r.n_rows
