@@ -177,8 +177,8 @@ def main():
 
     # ---- this rank's shard of the witness batch (contiguous block) ---------------------------
     total_w = args.witnesses
-    lo = total_w * rank // world
-    hi = total_w * (rank + 1) // world
+    shard = importlib.import_module("zkir_b200.sharding")
+    lo, hi = shard.shard_range(total_w, rank, world)
     n_local = hi - lo
     # 1 % of the witnesses are corrupted; their first failing assertion is known by construction
     rng = np.random.default_rng(SEED + 1)
@@ -194,16 +194,10 @@ def main():
 
     def verdict_allreduce(v):
         """the path's only collective: MIN-reduce of first_fail over the whole batch (NCCL over NVLink)"""
-        ff = np.where(v["ok"] == 1, np.int64(1) << 40, v["first_fail_seq"].astype(np.int64))
-        if world == 1:
-            return ff
-        full = torch.full((total_w,), 1 << 40, dtype=torch.int64, device="cuda")
-        full[lo:hi] = torch.from_numpy(ff).cuda()
-        dist.all_reduce(full, op=dist.ReduceOp.MIN)
-        return full.cpu().numpy()
+        return shard.allreduce_first_fail(shard.first_fail_vector(v), lo, hi, total_w)
 
     def check(ff_local):
-        got = np.where(ff_local >= (1 << 40), -1, ff_local)
+        got = np.where(ff_local >= (1 << 40), -1, ff_local)[:n_local]
         assert (got == expected).all(), f"rank {rank}: verdicts differ from the constructed expectation"
 
     def barrier():
@@ -234,6 +228,7 @@ def main():
 
     # ---- value: inputs resident in HBM -----------------------------------------------------------
     be.upload_inputs(None, w_host, n_local)
+    st = be.stats()
     for _ in range(args.warmup):
         v = be.run()
     check(np.where(v["ok"] == 1, np.int64(1) << 40, v["first_fail_seq"].astype(np.int64)))

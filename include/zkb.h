@@ -220,6 +220,8 @@ int zkb_evaluator_get_violations(zkb_evaluator* ev, size_t* n_violations);
 const char* zkb_evaluator_violation(zkb_evaluator* ev, size_t i);
 /* Evaluator::get(id): canonical little-endian residue of a live top-scope wire. */
 int zkb_evaluator_get_wire(zkb_evaluator* ev, uint64_t wire_id, uint8_t* out_le, size_t cap, size_t* len);
+/* value handle (for zkb_read_values on any witness of a batch) bound to a live top-scope wire */
+int zkb_evaluator_lookup(zkb_evaluator* ev, uint64_t wire_id, zkb_wire* out);
 const char* zkb_evaluator_last_error(zkb_evaluator* ev);
 
 /* ------------------------------------------------------------------ 5. R1CS (Az o Bz = Cz)

@@ -71,7 +71,7 @@ EXPORTED = [
     "zkb_upload_inputs", "zkb_run", "zkb_assert_info", "zkb_pending_error", "zkb_read_values", "zkb_scope_lookup",
     "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
     "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
-    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
+    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
     "zkb_r1cs_upload", "zkb_r1cs_run",
 ]
 
@@ -124,6 +124,7 @@ _sig("zkb_evaluator_ingest_paths", _i, _vp, C.POINTER(C.c_char_p), _sz)
 _sig("zkb_evaluator_get_violations", _i, _vp, C.POINTER(C.c_size_t))
 _sig("zkb_evaluator_violation", C.c_char_p, _vp, _sz)
 _sig("zkb_evaluator_get_wire", _i, _vp, _u64, _u8p, _sz, C.POINTER(C.c_size_t))
+_sig("zkb_evaluator_lookup", _i, _vp, _u64, _u64p)
 _sig("zkb_evaluator_last_error", C.c_char_p, _vp)
 _sig("zkb_r1cs_load", _i, _vp, C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), _u8p, _sz, _u64, _u64)
 _sig("zkb_r1cs_check", _i, _vp, _u8p, _u64, _u32, _u32, _vp)
@@ -457,6 +458,12 @@ class Evaluator:
         n = C.c_size_t()
         self._chk(_lib.zkb_evaluator_get_violations(self._e, C.byref(n)))
         return [_lib.zkb_evaluator_violation(self._e, i).decode() for i in range(n.value)]
+
+    def value_handle(self, wire_id: int) -> int:
+        """SSA handle bound to a live top-scope wire (for GpuBackend.read_values on any batch element)"""
+        out = C.c_uint64()
+        self._chk(_lib.zkb_evaluator_lookup(self._e, wire_id, C.byref(out)))
+        return out.value
 
     def get(self, wire_id: int) -> int:
         out = C.create_string_buffer(64)

@@ -637,3 +637,10 @@ extern "C" int zkb_evaluator_get_wire(zkb_evaluator* ev, uint64_t wire_id, uint8
     if (len) *len = n;
     return ZKB_OK;
 }
+
+extern "C" int zkb_evaluator_lookup(zkb_evaluator* ev, uint64_t wire_id, zkb_wire* out) {
+    uint32_t v = ev->values.get(wire_id);
+    if (v == Scope::kNone) return ev->fail(ZKB_E_SEMANTIC, "No value given for wire_" + u64s(wire_id));
+    *out = v;
+    return ZKB_OK;
+}
