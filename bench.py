@@ -116,6 +116,11 @@ def cpu_reference_rate(circ_mod, flat, p, circuit, n_threads, log2_sample_gates,
     return rate, per_step, sample
 
 
+def workload_name(args):
+    return (f"C3: 2^{args.log2_gates}-gate random Add/Mul/AssertZero circuit over {args.field}, "
+            f"{args.witnesses} witnesses sharded over {args.gpus} GPU(s)")
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -144,10 +149,10 @@ def main():
         line = {
             "impl": "reference", "metric": "field gates evaluated/sec", "value": rate, "unit": "gate-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field)",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field, Montgomery)",
             "data": "synthetic",
-            "config": {"workload": f"C3: 2^{args.log2_gates}-gate random Add/Mul/AssertZero circuit, {args.field}, "
-                                   f"{args.witnesses} witnesses", "field": args.field},
+            "config": {"workload": workload_name(args), "gates": circuit.n_gates, "gate_histogram": circuit.hist,
+                       "witnesses": args.witnesses, "witness_inputs": args.inputs},
             "cpu_baseline": {"value": rate, "unit": "gate-evals/s", "cores": nt, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "gate-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of zki_sieve 3.0.0 Evaluator<PlaintextBackend> (oracle/plaintext_flat.c), not the Rust binary",
@@ -209,18 +214,27 @@ def main():
     gate_evals_total = circuit.n_gates * total_w
 
     def timed(fn, steps):
+        """device time of a step = the library's CUDA events (its own stream: H2D, kernels, verdict D2H)
+        + CUDA events around the verdict all-reduce (torch's stream); max over ranks."""
         barrier()
         dev_ms = 0.0
         lv_ms = 0.0
+        ar = []
         t0 = time.perf_counter()
         for _ in range(steps):
             v = fn()
             tm = be.timing()
             dev_ms += tm["total_ms"]
             lv_ms += tm["levels_ms"]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             ff = verdict_allreduce(v)
+            e1.record()
+            ar.append((e0, e1))
         barrier()
         wall = time.perf_counter() - t0
+        if world > 1:
+            dev_ms += sum(a.elapsed_time(b) for a, b in ar)
         t = torch.tensor([dev_ms, wall * 1e3, lv_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -272,7 +286,10 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("k_level_dram_bytes_per_launch")
+            ratio = json.load(open(prof))["traffic_over_algorithmic"]
+            roofline["traffic"] = ratio * roofline["algorithmic_bytes_per_launch"]
+            roofline["traffic_source"] = ("profiles/traffic.json: dram__bytes_read+write of 3 captured k_level launches = "
+                                          f"{ratio:.3f} x their algorithmic bytes, scaled to the average launch")
         except Exception:
             pass
 
@@ -290,8 +307,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field, Montgomery)" if eb == 32 else f"u32x{eb // 4}",
             "data": "synthetic",
-            "config": {"workload": f"C3: 2^{args.log2_gates}-gate random Add/Mul/AssertZero circuit over {args.field}, "
-                                   f"{total_w} witnesses sharded over {world} GPU(s)",
+            "config": {"workload": workload_name(args),
                        "gates": circuit.n_gates, "gate_histogram": circuit.hist, "witnesses": total_w,
                        "witness_inputs": args.inputs, "levels": st["n_levels"], "tile_witnesses": st["tile_witnesses"],
                        "tiles_per_rank": st["n_tiles"], "wire_store_gb": st["n_slots"] * eb * st["tile_witnesses"] / 1e9,

@@ -187,6 +187,10 @@ int zkb_get_stats(zkb_ctx* ctx, zkb_stats* out);
 int zkb_get_program(zkb_ctx* ctx, uint64_t first, uint64_t n, uint8_t* kinds, uint32_t* a, uint32_t* b);
 /* canonical residue of constant-pool entry idx (little-endian) */
 int zkb_get_const(zkb_ctx* ctx, uint64_t idx, uint8_t* out_le, size_t cap, size_t* len);
+/* wavefront `level` of the device plan: out[0] gates, out[1] of which Add/Mul/AddC/MulC, out[2] with a fused
+ * assertion, out[3] not stored, out[4] algorithmic bytes per witness (3E per two-operand gate, 2E per
+ * one-operand gate, E per assertion) */
+int zkb_level_info(zkb_ctx* ctx, uint64_t level, uint64_t out[5]);
 /* asserted value handle of assertion seq */
 int zkb_assert_value(zkb_ctx* ctx, uint64_t seq, zkb_wire* value);
 

@@ -69,7 +69,7 @@ EXPORTED = [
     "zkb_constant", "zkb_assert_zero", "zkb_add", "zkb_multiply", "zkb_add_constant", "zkb_mul_constant", "zkb_and",
     "zkb_xor", "zkb_not", "zkb_instance", "zkb_witness", "zkb_push_gates", "zkb_finalize", "zkb_evaluate",
     "zkb_upload_inputs", "zkb_run", "zkb_assert_info", "zkb_pending_error", "zkb_read_values", "zkb_scope_lookup",
-    "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
+    "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_level_info", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
     "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
     "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
     "zkb_r1cs_upload", "zkb_r1cs_run",
@@ -116,6 +116,7 @@ _sig("zkb_get_timing", _i, _vp, C.POINTER(ZkbTiming))
 _sig("zkb_get_program", _i, _vp, _u64, _u64, _vp, _vp, _vp)
 _sig("zkb_get_const", _i, _vp, _u64, _u8p, _sz, C.POINTER(C.c_size_t))
 _sig("zkb_assert_value", _i, _vp, _u64, _u64p)
+_sig("zkb_level_info", _i, _vp, _u64, _vp)
 _sig("zkb_evaluator_create", _vp, _vp)
 _sig("zkb_evaluator_destroy", None, _vp)
 _sig("zkb_evaluator_ingest_message", _i, _vp, _u8p, _sz)
@@ -342,6 +343,11 @@ class GpuBackend:
         n = C.c_size_t()
         self._chk(_lib.zkb_get_const(self._c, idx, C.cast(out, C.c_void_p), 64, C.byref(n)))
         return int.from_bytes(out.raw[:n.value], "little")
+
+    def level_info(self, level: int) -> dict:
+        out = np.zeros(5, dtype=np.uint64)
+        self._chk(_lib.zkb_level_info(self._c, level, _buf(out)))
+        return dict(zip(["gates", "arith", "fused_asserts", "not_stored", "algo_bytes_per_witness"], (int(x) for x in out)))
 
     def assert_value(self, seq: int) -> int:
         out = C.c_uint64()

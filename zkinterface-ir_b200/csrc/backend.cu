@@ -701,3 +701,21 @@ extern "C" int zkb_assert_value(zkb_ctx* c, uint64_t seq, zkb_wire* value) {
     *value = c->prog.asserts[seq].value;
     return ZKB_OK;
 }
+
+extern "C" int zkb_level_info(zkb_ctx* c, uint64_t level, uint64_t out[5]) {
+    if (!c->finalized || level >= c->plan.n_levels) return c->fail(ZKB_E_ARG, "level out of range");
+    const Plan& pl = c->plan;
+    const uint64_t E = c->prog.binary ? 1 : (uint64_t)c->prog.nlimb * 4;
+    uint64_t lo = pl.level_off[level], hi = pl.level_off[level + 1];
+    out[0] = hi - lo;
+    out[1] = pl.level_rare[level] - lo;
+    out[2] = out[3] = out[4] = 0;
+    for (uint64_t i = lo; i < hi; i++) {
+        uint32_t m = pl.ops[i].meta, opc = m & 0xff;
+        if (m & F_ASSERT) out[2]++;
+        if (m & F_NOSTORE) out[3]++;
+        if (opc == D_ASSERT) out[4] += E;
+        else out[4] += ((opc == D_ADD || opc == D_MUL || opc == D_AND || opc == D_XOR) ? 3 * E : 2 * E) + ((m & F_ASSERT) ? E : 0);
+    }
+    return ZKB_OK;
+}
