@@ -109,7 +109,8 @@ ZKB_HD void fe_mont_mul_portable(uint32_t* r, const uint32_t* a, const uint32_t*
     fe_cond_sub_p<N>(r, t, t[N], p);
 }
 
-#if !defined(ZKB_FIELD_PTX)
+// the device pass gets fe_mont_mul from field_ptx.cuh (PTX carry chains); host code and -DZKB_NO_PTX_FIELD use the portable one
+#if !(defined(__CUDA_ARCH__) && !defined(ZKB_NO_PTX_FIELD))
 template <int N>
 ZKB_HD void fe_mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t n0inv) {
     fe_mont_mul_portable<N>(r, a, b, p, n0inv);

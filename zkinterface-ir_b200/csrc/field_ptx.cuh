@@ -1,4 +1,186 @@
-// Device-only carry-chain Montgomery multiplication (PTX mad.lo.cc / madc.hi.cc).
-// Defines ZKB_FIELD_PTX and fe_mont_mul<N> when enabled; otherwise field.cuh's portable CIOS is used.
+// Device-only carry-chain field arithmetic (PTX add.cc / mad.lo.cc / madc.hi.cc), N = 4 and 8 limbs.
+//
+// Montgomery product, row-wise (CIOS) with TWO interleaved accumulators so that every 32x32->64
+// partial product lands on an aligned (lo, hi) register pair and one carry chain runs over the
+// pairs — ptxas turns each mad.lo.cc / madc.hi.cc pair into one IMAD.WIDE.U32(.X):
+//     E[j] sits at limb position j,  O[j] at position j + 1
+//     even-index limbs x[0], x[2], ... multiply into the pairs (E[1]:E[0]), (E[3]:E[2]), ...
+//     odd-index  limbs x[1], x[3], ... multiply into the pairs (O[1]:O[0]), (O[3]:O[2]), ...
+// After a row (T += a*b_i; m = T[0]*n0inv; T += p*m) limb 0 is zero and T is shifted down one limb:
+// O becomes the new E, E[2..] becomes the new O, E[1] is folded into the new E[0] and its carry
+// rides into the new O chain; the chains' carry-outs become the top limbs of the new O.
+// Works for every odd p < 2^(32N) (the value may transiently need N+1 limbs; the final conditional
+// subtraction takes the top carry).  Checked bit-for-bit against fe_mont_mul_portable by
+// tests/test_gpu_field.py (zkb_debug_field_ops) and by every GPU parity test.
 #pragma once
 #include "field.cuh"
+
+#if defined(__CUDA_ARCH__) && !defined(ZKB_NO_PTX_FIELD)
+#define ZKB_FIELD_PTX 1
+
+namespace zkb {
+
+// ---- N = 8: four (lo, hi) pairs per chain ---------------------------------------------------
+// acc pairs = x_k * y   (no accumulate: first row)
+__device__ __forceinline__ void mul_pairs4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+}
+
+// acc pairs += x_k * y with one carry chain; returns the carry out of the top pair
+__device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+    uint32_t c;
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+    return c;
+}
+
+// e0 = f0 + f1 (the folded limb), its carry continues into:  acc pairs += x_k * y ; returns carry out
+__device__ __forceinline__ uint32_t mad_chain4_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, uint32_t x0, uint32_t x1,
+                                                    uint32_t x2, uint32_t x3, uint32_t y) {
+    uint32_t c;
+    asm("add.cc.u32 %9, %10, %11;\n\t"
+        "madc.lo.cc.u32 %0, %12, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %12, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %13, %16, %2;\n\t"
+        "madc.hi.cc.u32 %3, %13, %16, %3;\n\t"
+        "madc.lo.cc.u32 %4, %14, %16, %4;\n\t"
+        "madc.hi.cc.u32 %5, %14, %16, %5;\n\t"
+        "madc.lo.cc.u32 %6, %15, %16, %6;\n\t"
+        "madc.hi.cc.u32 %7, %15, %16, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c),
+          "=r"(e0)
+        : "r"(f0), "r"(f1), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+    return c;
+}
+
+// ---- N = 4: two pairs per chain --------------------------------------------------------------
+__device__ __forceinline__ void mul_pairs2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y) {
+    asm("mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mul.lo.u32 %2, %5, %6;\n\t"
+        "mul.hi.u32 %3, %5, %6;"
+        : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
+        : "r"(x0), "r"(x1), "r"(y));
+}
+__device__ __forceinline__ uint32_t mad_chain2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y) {
+    uint32_t c;
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
+        : "r"(x0), "r"(x1), "r"(y));
+    return c;
+}
+__device__ __forceinline__ uint32_t mad_chain2_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, uint32_t x0, uint32_t x1,
+                                                    uint32_t y) {
+    uint32_t c;
+    asm("add.cc.u32 %5, %6, %7;\n\t"
+        "madc.lo.cc.u32 %0, %8, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c), "=r"(e0)
+        : "r"(f0), "r"(f1), "r"(x0), "r"(x1), "r"(y));
+    return c;
+}
+
+template <int N>
+struct PtxChains;
+template <>
+struct PtxChains<8> {
+    static __device__ __forceinline__ void mul_even(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs4(acc, x[0], x[2], x[4], x[6], y); }
+    static __device__ __forceinline__ void mul_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs4(acc, x[1], x[3], x[5], x[7], y); }
+    static __device__ __forceinline__ uint32_t mad_even(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain4(acc, x[0], x[2], x[4], x[6], y); }
+    static __device__ __forceinline__ uint32_t mad_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain4(acc, x[1], x[3], x[5], x[7], y); }
+    static __device__ __forceinline__ uint32_t mad_odd_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, const uint32_t* x, uint32_t y) {
+        return mad_chain4_fold(e0, f0, f1, acc, x[1], x[3], x[5], x[7], y);
+    }
+};
+template <>
+struct PtxChains<4> {
+    static __device__ __forceinline__ void mul_even(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs2(acc, x[0], x[2], y); }
+    static __device__ __forceinline__ void mul_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs2(acc, x[1], x[3], y); }
+    static __device__ __forceinline__ uint32_t mad_even(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain2(acc, x[0], x[2], y); }
+    static __device__ __forceinline__ uint32_t mad_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain2(acc, x[1], x[3], y); }
+    static __device__ __forceinline__ uint32_t mad_odd_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, const uint32_t* x, uint32_t y) {
+        return mad_chain2_fold(e0, f0, f1, acc, x[1], x[3], y);
+    }
+};
+
+template <int N>
+__device__ __forceinline__ void fe_mont_mul_chain(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t n0inv) {
+    using Ch = PtxChains<N>;
+    uint32_t E[N], O[N];
+    Ch::mul_even(E, a, b[0]);
+    Ch::mul_odd(O, a, b[0]);
+    uint32_t m = E[0] * n0inv;
+    uint32_t cE = Ch::mad_even(E, p, m);
+    uint32_t cO = Ch::mad_odd(O, p, m);
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+        // shift down one limb: new E = O (+ E[1] folded into limb 0), new O = E[2..] ++ (cE, cO)
+        uint32_t nE[N], nO[N];
+#pragma unroll
+        for (int j = 1; j < N; j++) nE[j] = O[j];
+#pragma unroll
+        for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
+        nO[N - 2] = cE;
+        nO[N - 1] = cO;
+        cO = Ch::mad_odd_fold(nE[0], O[0], E[1], nO, a, b[i]);   // nE[0] = O[0] + E[1]; carry rides into the odd chain
+        cE = Ch::mad_even(nE, a, b[i]);
+        m = nE[0] * n0inv;
+        cE += Ch::mad_even(nE, p, m);
+        cO += Ch::mad_odd(nO, p, m);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            E[j] = nE[j];
+            O[j] = nO[j];
+        }
+    }
+    // final shift + merge of the two accumulators: limb j = E[j+1] + O[j], limb N-1 = cE + O[N-1], top = cO
+    uint32_t t[N];
+    uint64_t c = (uint64_t)E[1] + O[0];
+    t[0] = (uint32_t)c;
+    c >>= 32;
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) {
+        c += (uint64_t)E[j + 1] + O[j];
+        t[j] = (uint32_t)c;
+        c >>= 32;
+    }
+    c += (uint64_t)cE + O[N - 1];
+    t[N - 1] = (uint32_t)c;
+    uint32_t top = (uint32_t)(c >> 32) + cO;
+    fe_cond_sub_p<N>(r, t, top, p);
+}
+
+template <int N>
+__device__ __forceinline__ void fe_mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t n0inv) {
+    if constexpr (N == 8 || N == 4) fe_mont_mul_chain<N>(r, a, b, p, n0inv);
+    else fe_mont_mul_portable<N>(r, a, b, p, n0inv);
+}
+
+}  // namespace zkb
+#endif
