@@ -13,6 +13,7 @@
 // streaming of wire limbs plus 32-bit integer multiply-add chains (IMAD), see DESIGN.md.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "device_util.cuh"
 #include "kernels.cuh"
@@ -166,6 +167,69 @@ k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint6
     }
 }
 
+// Software-pipelined variant of the hot kernel: the gate descriptor is fetched two iterations ahead and the
+// operand limbs one iteration ahead, so a thread always has the next gate's 4 x 16-byte loads in flight
+// while it runs the current gate's integer chain (the dependent descriptor -> operand latency and the
+// compute phase no longer serialise with the memory phase).
+template <int N>
+__device__ __forceinline__ void load_operands(uint32_t* a, uint32_t* b, const uint4& d, const uint32_t* __restrict__ store,
+                                              const uint32_t* __restrict__ consts_mont, uint32_t lane, uint32_t log2_wt) {
+    const uint32_t opc = d.w & 0xff;
+    load_elem<N>(a, store, d.x, lane, log2_wt);
+    if (opc == D_ADDC || opc == D_MULC) {
+#pragma unroll
+        for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)d.y * N + k);
+    } else {
+        load_elem<N>(b, store, d.y, lane, log2_wt);
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+k_level_pipe(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
+             const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
+    const uint64_t total = n_ops << g.log2_wt;
+    const uint32_t wt_mask = (1u << g.log2_wt) - 1;
+    const bool single = g.log2_wt == 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t0 >= total) return;
+    const uint4* dptr = reinterpret_cast<const uint4*>(ops);
+    uint64_t t1 = t0 + stride, t2 = t1 + stride;
+    uint4 d0 = __ldg(dptr + (t0 >> g.log2_wt));
+    uint4 d1 = t1 < total ? __ldg(dptr + (t1 >> g.log2_wt)) : make_uint4(0, 0, 0, 0);
+    uint32_t a0[N], b0[N], a1[N], b1[N];
+    load_operands<N>(a0, b0, d0, store, consts_mont, (uint32_t)t0 & wt_mask, g.log2_wt);
+    while (true) {
+        uint4 d2 = make_uint4(0, 0, 0, 0);
+        if (t2 < total) d2 = __ldg(dptr + (t2 >> g.log2_wt));
+        const bool more = t1 < total;
+        if (more) load_operands<N>(a1, b1, d1, store, consts_mont, (uint32_t)t1 & wt_mask, g.log2_wt);
+        // ---- current gate ----
+        const uint32_t opc = d0.w & 0xff;
+        const uint32_t lane = (uint32_t)t0 & wt_mask;
+        uint32_t r[N];
+        if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a0, b0, fp.p);
+        else fe_mont_mul<N>(r, a0, b0, fp.p, fp.n0inv);
+        if (!(d0.w & F_NOSTORE)) store_elem<N>(store, d0.z, lane, g.log2_wt, r);
+        if (d0.w & F_ASSERT) {
+            bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
+            report_fail(fail, __ldg(aseq + (t0 >> g.log2_wt)), first_fail, g.batch0 + lane, single);
+        }
+        if (!more) break;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            a0[k] = a1[k];
+            b0[k] = b1[k];
+        }
+        d0 = d1;
+        d1 = d2;
+        t0 = t1;
+        t1 = t2;
+        t2 += stride;
+    }
+}
+
 template <int N>
 __global__ void k_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
                               uint32_t log2_wt, uint32_t* __restrict__ out, FieldParams fp) {
@@ -269,6 +333,25 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) {
 // ---------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------
+// experiment knobs (environment, read once): ZKB_LEVEL_PIPE=0/1 selects the software-pipelined hot kernel,
+// ZKB_GRID_PER_SM the number of CTAs per SM of the persistent-style grids
+static bool level_pipe_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZKB_LEVEL_PIPE");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+static int grid_per_sm(int dflt) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZKB_GRID_PER_SM");
+        v = e ? atoi(e) : 0;
+    }
+    return v > 0 ? v : dflt;
+}
+
 static inline unsigned grid_for(uint64_t total, int sm_count, int per_sm) {
     uint64_t blocks = (total + 255) / 256;
     uint64_t cap = (uint64_t)sm_count * per_sm;
@@ -301,11 +384,17 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
                   const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp, int sm_count,
                   bool rare, cudaStream_t s) {
     if (n_ops == 0) return;
-    // persistent-style grid: a whole number of CTAs per SM (148 SMs x 8 CTAs of 256 threads fills
-    // the 2048-thread SM when the kernel stays <= 32 registers/thread; fewer resident otherwise)
-    unsigned grid = grid_for(n_ops << g.log2_wt, sm_count, 8);
+    // grid: a whole number of CTAs per SM (multiple of the SM count), grid-stride inside.  Measured on B200
+    // (scripts/ab_level.sh, C3): 8 CTAs/SM (exactly resident, static partition) 87 % of the HBM roofline,
+    // 64/SM 92.7 %, 256/SM 92.9 % — many more CTAs than are resident lets the hardware scheduler even out
+    // the DRAM-locality differences between SMs, while each thread still pipelines several gates.
+    unsigned grid = grid_for(n_ops << g.log2_wt, sm_count, grid_per_sm(256));
     if (!rare) {
-        ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+        if (level_pipe_enabled()) {
+            ZKB_DISPATCH_N(nlimb, (k_level_pipe<N><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+        } else {
+            ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+        }
     } else {
         ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
     }
