@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Secondary configs of BASELINE.json (C1, C2, C4, C5): parity check + device timing (CUDA events inside
+libzkb, inputs resident).  One JSON line per config.  The headline (C3) is bench.py."""
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import zkb_loader  # noqa: E402
+
+z = zkb_loader.load()
+c = importlib.import_module("zkir_b200.circuits")
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed_runs(fn, timing, k=5, warm=2):
+    for _ in range(warm):
+        fn()
+    tot, lv = [], []
+    for _ in range(k):
+        fn()
+        t = timing()
+        tot.append(t["total_ms"])
+        lv.append(t["levels_ms"])
+    return float(np.median(tot)), float(np.median(lv))
+
+
+def c1():
+    from oracle import fixtures as fx, sieve_fbs as F
+    msgs = [fx.example_instance(), fx.example_witness(), fx.example_relation()]
+    t0 = time.perf_counter()
+    ev = z.Evaluator.from_messages(z.Source.from_buffers([F.write_messages(msgs)]), device=0)
+    v = ev.get_violations()
+    dt = time.perf_counter() - t0
+    bad = z.Evaluator.from_messages(z.Source.from_buffers([F.write_messages(
+        [fx.example_instance(), fx.example_witness_incorrect(), fx.example_relation()])]), device=0).get_violations()
+    st = ev.backend.stats()
+    return {"config": "C1 zki_sieve example (p=101)", "violations": v, "incorrect_witness": bad, "wall_ms_incl_flatten": dt * 1e3,
+            "callbacks": sum(st["callbacks"].values()), "levels": st["n_levels"], "device_ms": ev.backend.timing()["total_ms"]}
+
+
+def c2(log2_gates, window):
+    p = c.GOLDILOCKS
+    circ = c.random_circuit(1 << log2_gates, 1024, p, 0x5EED0002, window=window)
+    b = z.GpuBackend(0)
+    b.set_field(p)
+    t0 = time.perf_counter()
+    b.push_gates(circ.gates, circ.const_pool)
+    b.finalize(False)
+    prep = time.perf_counter() - t0
+    good = c.make_witnesses(circ, 1, seed=3)
+    bad = c.make_witnesses(circ, 1, seed=3, corrupt={0: 5})
+    b.upload_inputs(None, bad, 1)
+    vb = b.run()
+    assert int(vb[0]["first_fail_seq"]) == int(circ.tie_assert_seq[5])
+    b.upload_inputs(None, good, 1)
+    assert int(b.run()[0]["ok"]) == 1
+    tot, lv = timed_runs(b.run, b.timing)
+    st = b.stats()
+    algo = 8 * 3 * (circ.hist["add"] + circ.hist["mul"]) + 8 * circ.hist["assert_zero"] + 16 * st["n_device_ops"]
+    return {"config": f"C2 2^{log2_gates}-gate Goldilocks, 1 witness, operands {'windowed ' + str(window) if window else 'global'}",
+            "gates_per_s": circ.n_gates / (tot * 1e-3), "ms": tot, "levels": st["n_levels"], "us_per_level": tot * 1e3 / st["n_levels"],
+            "algo_GBps_incl_descriptors": algo / (tot * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (tot * 1e-3) / 1e9 / PEAK,
+            "prep_s": prep, "note": "L2-resident, launch/latency bound (one launch per wavefront)"}
+
+
+def c4(log2_rows, log2_free, batch):
+    p = c.BN254_FR
+    r = c.random_r1cs(1 << log2_rows, 1 << log2_free, p, 0x5EED0004)
+    t0 = time.perf_counter()
+    zz = c.r1cs_assignment(r, 1)
+    gen = time.perf_counter() - t0
+    zb = c.assignment_bytes(zz, p)
+    bad_row = (1 << log2_rows) // 3
+    zbad = zb.copy()
+    zbad[r.n_free + 1 + bad_row, 0] ^= 1
+    b = z.GpuBackend(0)
+    b.set_field(p)
+    b.r1cs_load(r.A, r.B, r.C, r.coef_table, r.n_vars)
+    v = b.r1cs_check(np.stack([zb, zbad]))
+    assert int(v[0]["ok"]) == 1 and int(v[1]["first_fail_seq"]) == min(bad_row, c.r1cs_first_row_reading(r, r.n_free + 1 + bad_row))
+    batch_z = np.broadcast_to(zb, (batch,) + zb.shape).copy() if batch > 1 else zb[None]
+    b.r1cs_upload(batch_z)
+    tot, lv = timed_runs(b.r1cs_run, b.timing)
+    algo = c.r1cs_algorithmic_bytes(r) * batch
+    ge = c.r1cs_gate_equivalent(r)
+    return {"config": f"C4 R1CS 2^{log2_rows} constraints, BN254, batch {batch}", "constraints_per_s": r.n_rows * batch / (lv * 1e-3),
+            "gate_equivalent_per_s": ge * batch / (lv * 1e-3), "check_kernel_ms": lv, "total_ms_incl_z_conversion": tot, "nnz": r.nnz,
+            "n_vars": r.n_vars, "algo_GBps": algo / (lv * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (lv * 1e-3) / 1e9 / PEAK,
+            "assignment_gen_s": gen}
+
+
+def c5(lo, li, batch):
+    from oracle import ir, sieve_fbs as F, workloads as wl
+    n_wit = 4096
+    rel, n_leaf = wl.boolean_for_relation(lo, li, n_wit)
+    buf = F.write_messages([ir.Witness(rel.header, [b"\0"] * n_wit), rel])
+    b = z.GpuBackend(0)
+    ev = z.Evaluator(b)
+    t0 = time.perf_counter()
+    ev.ingest_source(z.Source.from_buffers([buf]))
+    flat_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    assert ev.get_violations() == []
+    first_s = time.perf_counter() - t0
+    rng = np.random.default_rng(5)
+    W = rng.integers(0, 2, size=(batch, n_wit, 1)).astype(np.uint8)
+    v = b.evaluate(None, W, batch)
+    block = 2 << li
+    for j in range(min(batch, 4)):
+        outs = wl.boolean_for_expected_outputs(W[j, :, 0], lo, li)
+        x = 0
+        for k in range(8):
+            x ^= int(outs[-1][k])
+        assert bool(v[j]["ok"]) == (x == 0)
+        probe = [n_wit + k for k in (0, 1, 12345 % (block << lo), block * 3 + 7)]
+        got = b.read_values(j, [ev.value_handle(w_) for w_ in probe], 4)
+        assert got == [int(outs.reshape(-1)[w_ - n_wit]) for w_ in probe]
+    b.upload_inputs(None, W, batch)
+    tot, lv = timed_runs(b.run, b.timing)
+    st = b.stats()
+    return {"config": f"C5 Boolean 2^{lo + li + 3} leaf gates (nested For 2^{lo} x 2^{li}), {batch} witness(es) bit-sliced",
+            "gates_per_s": n_leaf * batch / (tot * 1e-3), "ms": tot, "levels": st["n_levels"], "host_flatten_s": flat_s,
+            "finalize_and_first_eval_s": first_s, "values": st["n_values"],
+            "algo_GBps": (16 + 12) * st["n_device_ops"] * max(1, batch // 32) / (tot * 1e-3) / 1e9}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="c1,c2,c4,c5")
+    ap.add_argument("--small", action="store_true")
+    a = ap.parse_args()
+    todo = a.only.split(",")
+    if "c1" in todo:
+        print(json.dumps(c1()), flush=True)
+    if "c2" in todo:
+        print(json.dumps(c2(16 if a.small else 20, 0)), flush=True)
+        print(json.dumps(c2(16 if a.small else 20, 4096)), flush=True)
+    if "c4" in todo:
+        print(json.dumps(c4(14 if a.small else 22, 12 if a.small else 20, 1)), flush=True)
+        print(json.dumps(c4(14 if a.small else 18, 12 if a.small else 16, 64)), flush=True)
+    if "c5" in todo:
+        print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 1)), flush=True)
+        print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 64)), flush=True)

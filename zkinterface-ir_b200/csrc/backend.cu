@@ -60,6 +60,7 @@ int ctx_finalize(zkb_ctx* c, bool keep_all) {
     if ((rc = upload_vec(c, c->d_aseq, c->plan.op_assert_seq)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_loads, c->plan.loads)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_consts, c->prog.const_limbs)) != ZKB_OK) return rc;
+    if ((rc = upload_vec(c, c->d_level_off, c->plan.level_off)) != ZKB_OK) return rc;
     if (!c->prog.binary) launch_to_mont(c->prog.nlimb, c->d_consts, c->prog.n_consts(), c->prog.fp, c->stream);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ZKB_OK;
@@ -86,6 +87,7 @@ extern "C" zkb_ctx* zkb_create(int device) {
         return c;
     }
     c->sm_count = prop.multiProcessorCount;
+    c->coop_supported = prop.cooperativeLaunch != 0;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         c->err = std::string("zkb_create: ") + cudaGetErrorString(e);
@@ -106,6 +108,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_aseq);
         cudaFree(c->d_loads);
         cudaFree(c->d_consts);
+        cudaFree(c->d_level_off);
         cudaFree(c->d_store);
         cudaFree(c->d_inst);
         cudaFree(c->d_wit);
@@ -445,6 +448,23 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
             c->tile_ev.push_back(e);
         }
         cudaEventRecord(c->tile_ev[2 * tile], c->stream);
+    }
+    // launch-bound programs (levels far too small to fill the chip): all wavefronts in one cooperative launch
+    bool coop = !p.binary && pl.n_levels > 1 && ((uint64_t)pl.max_level_ops << c->log2_wt) <= (uint64_t)c->sm_count * 8192;
+    if (const char* e = getenv("ZKB_COOP")) coop = coop && atoi(e) != 0;
+    if (coop && c->coop_supported) {
+        cudaError_t e = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, g,
+                                           p.fp, c->sm_count, (uint64_t)pl.max_level_ops << c->log2_wt, c->stream);
+        if (e == cudaSuccess) {
+            (*launches)++;
+            if (level_launches) (*level_launches)++;
+            if (timed) cudaEventRecord(c->tile_ev[2 * tile + 1], c->stream);
+            c->resident_tile = tile;
+            return;
+        }
+        if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: cooperative launch failed: %s\n", cudaGetErrorString(e));
+        cudaGetLastError();          // not launchable cooperatively: fall through to one launch per level
+        c->coop_supported = false;
     }
     for (uint32_t l = 0; l < pl.n_levels; l++) {
         uint64_t lo = pl.level_off[l], mid = pl.level_rare[l], hi = pl.level_off[l + 1];

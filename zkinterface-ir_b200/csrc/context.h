@@ -97,6 +97,8 @@ struct zkb_ctx {
     uint32_t* d_aseq = nullptr;
     zkb::InputLoad* d_loads = nullptr;
     uint32_t* d_consts = nullptr;
+    uint64_t* d_level_off = nullptr;
+    bool coop_supported = false;
     uint32_t* d_store = nullptr;
     size_t store_bytes = 0;
     uint32_t log2_wt = 0;

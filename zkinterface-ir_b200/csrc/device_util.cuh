@@ -56,6 +56,22 @@ __device__ __forceinline__ void load_elem(uint32_t* r, const uint32_t* store, ui
     }
 }
 
+// L2-coherent variant (ld.global.cg): for kernels that read values written earlier in the SAME launch by
+// other SMs (the cooperative all-levels kernel), where a stale L1 line would be wrong
+__device__ __forceinline__ uint32_t ld_coherent(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ uint2 ld_coherent(const uint2* p) { return __ldcg(p); }
+__device__ __forceinline__ uint4 ld_coherent(const uint4* p) { return __ldcg(p); }
+template <int N>
+__device__ __forceinline__ void load_elem_coherent(uint32_t* r, const uint32_t* store, uint32_t slot, uint32_t lane, uint32_t log2_wt) {
+    using V = typename Vec<Elem<N>::CW>::T;
+    const V* base = reinterpret_cast<const V*>(store);
+#pragma unroll
+    for (int c = 0; c < Elem<N>::NC; c++) {
+        size_t idx = (((size_t)slot * Elem<N>::NC + c) << log2_wt) + lane;
+        unpack(ld_coherent(base + idx), r + c * Elem<N>::CW);
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void store_elem(uint32_t* store, uint32_t slot, uint32_t lane, uint32_t log2_wt, const uint32_t* r) {
     using V = typename Vec<Elem<N>::CW>::T;

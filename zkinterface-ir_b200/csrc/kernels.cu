@@ -15,8 +15,12 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "device_util.cuh"
 #include "kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace zkb {
 
@@ -230,6 +234,66 @@ k_level_pipe(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
     }
 }
 
+// All wavefronts in ONE cooperative launch, a grid barrier between levels.  For programs whose levels are
+// too small to fill the chip (single-witness statements, deep narrow circuits) the per-level launch latency
+// (~4-5 us) dominates; a grid.sync() costs ~1-2 us.  Operands are read with ld.global.cg because they were
+// written by other SMs earlier in this same launch.
+template <int N>
+__global__ void __launch_bounds__(256)
+k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
+              uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
+              TileGeom g, FieldParams fp) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t wt_mask = (1u << g.log2_wt) - 1;
+    const bool single = g.log2_wt == 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint4* dptr = reinterpret_cast<const uint4*>(ops);
+    // the first descriptor of each level is fetched BEFORE the barrier that precedes the level (descriptors
+    // do not depend on wire data), taking one memory latency off the per-level critical path
+    uint64_t lo = level_off[0], hi = n_levels ? level_off[1] : lo;
+    uint4 first = make_uint4(0, 0, 0, 0);
+    if (tid0 < ((hi - lo) << g.log2_wt)) first = __ldg(dptr + lo + (tid0 >> g.log2_wt));
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint64_t total = (hi - lo) << g.log2_wt;
+        uint64_t nlo = hi, nhi = hi;
+        uint4 next_first = make_uint4(0, 0, 0, 0);
+        if (l + 1 < n_levels) {
+            nhi = level_off[l + 2];
+            if (tid0 < ((nhi - nlo) << g.log2_wt)) next_first = __ldg(dptr + nlo + (tid0 >> g.log2_wt));
+        }
+        for (uint64_t tid = tid0; tid < total; tid += stride) {
+            const uint32_t lane = (uint32_t)tid & wt_mask;
+            const uint64_t gi = lo + (tid >> g.log2_wt);
+            const uint4 raw = tid == tid0 ? first : __ldg(dptr + gi);
+            const uint32_t opc = raw.w & 0xff;
+            uint32_t a[N], b[N], r[N];
+            load_elem_coherent<N>(a, store, raw.x, lane, g.log2_wt);
+            if (opc == D_ADDC || opc == D_MULC) {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)raw.y * N + k);
+            } else if (opc == D_ADD || opc == D_MUL || opc == D_AND || opc == D_XOR) {
+                load_elem_coherent<N>(b, store, raw.y, lane, g.log2_wt);
+            } else {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = 0;
+            }
+            if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
+            else if (opc == D_MUL || opc == D_MULC) fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
+            else rare_gate<N>(r, a, b, opc, fp);
+            if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
+            if (raw.w & F_ASSERT) {
+                bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
+                report_fail(fail, __ldg(aseq + gi), first_fail, g.batch0 + lane, single);
+            }
+        }
+        first = next_first;
+        lo = nlo;
+        hi = nhi;
+        if (l + 1 < n_levels) grid.sync();
+    }
+}
+
 template <int N>
 __global__ void k_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
                               uint32_t log2_wt, uint32_t* __restrict__ out, FieldParams fp) {
@@ -398,6 +462,35 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
     } else {
         ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
     }
+}
+
+template <int N>
+static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
+                                 const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, FieldParams fp, int sm_count,
+                                 uint64_t max_level_items, cudaStream_t s) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels_coop<N>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
+                    (void*)&first_fail, (void*)&g, (void*)&fp};
+    // the grid barrier costs more the more CTAs take part: use only as many CTAs (a multiple of the SM count)
+    // as the widest level can occupy
+    uint64_t want = (max_level_items + 255) / 256;
+    uint64_t blocks = ((want + sm_count - 1) / sm_count) * sm_count;
+    if (blocks < (uint64_t)sm_count) blocks = sm_count;
+    if (blocks > (uint64_t)sm_count * per_sm) blocks = (uint64_t)sm_count * per_sm;
+    if (const char* e = getenv("ZKB_COOP_BLOCKS")) blocks = (uint64_t)atoi(e);
+    return cudaLaunchCooperativeKernel((void*)k_levels_coop<N>, dim3((unsigned)blocks), dim3(256), args, 0, s);
+}
+
+cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp,
+                               int sm_count, uint64_t max_level_items, cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
+    ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, g, fp, sm_count,
+                                                max_level_items, s)));
+    return e;
 }
 
 void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,

@@ -36,6 +36,10 @@ void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uin
 void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
                   const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp, int sm_count,
                   bool rare, cudaStream_t s);
+// every wavefront in one cooperative launch (grid barrier between levels); for launch-bound programs
+cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp,
+                               int sm_count, uint64_t max_level_items, cudaStream_t s);
 void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                         uint32_t* out, const FieldParams& fp, cudaStream_t s);
 
