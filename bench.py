@@ -160,6 +160,9 @@ def main():
         print(json.dumps(line))
         return
 
+    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
