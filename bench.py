@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--field", default="bls381", choices=["bls381", "bn254", "goldilocks"])
     ap.add_argument("--cpu-sample-log2-gates", type=int, default=22)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verdicts-only", action="store_true",
+                    help="do not keep the live wires readable: slot re-use + dead-store elimination (not the headline)")
     return ap.parse_args()
 
 
@@ -179,7 +181,7 @@ def main():
     be = z.GpuBackend(local_rank)
     be.set_field(p)
     be.push_gates(circuit.gates, circuit.const_pool)
-    be.finalize(keep_all_values=False)
+    be.finalize(keep_all_values=False, verdicts_only=args.verdicts_only)
     t_prep = time.perf_counter() - t0
     st = be.stats()
 
@@ -281,7 +283,7 @@ def main():
     algo_bytes_step = st["algo_bytes_per_witness"] * n_local            # this rank
     lv_ms_step = lv_ms / args.steps
     achieved = algo_bytes_step / (lv_ms_step * 1e-3) / 1e9 if lv_ms_step > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_level<8,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_level_pipe<8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes_step / max(level_launches, 1),
                 "avg_launch_ms": lv_ms_step / max(level_launches, 1), "launches_per_step": level_launches,
@@ -314,7 +316,8 @@ def main():
                        "gates": circuit.n_gates, "gate_histogram": circuit.hist, "witnesses": total_w,
                        "witness_inputs": args.inputs, "levels": st["n_levels"], "tile_witnesses": st["tile_witnesses"],
                        "tiles_per_rank": st["n_tiles"], "wire_store_gb": st["n_slots"] * eb * st["tile_witnesses"] / 1e9,
-                       "l2": "working set (wire store) is >> L2, no flush needed", "parallelism": f"witness-shard x{world}"},
+                       "l2": "working set (wire store) is >> L2, no flush needed", "parallelism": f"witness-shard x{world}",
+                       "wires_kept_readable": "none (verdicts only)" if args.verdicts_only else "all live top-scope wires"},
             "e2e": {"value": e2e_value, "unit": "gate-evals/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(w_host.nbytes) * world, "d2h_bytes_per_step": 4 * total_w + 4 * world},
             "gpu_launches": int(launches),

@@ -123,10 +123,13 @@ typedef struct {
 int zkb_push_gates(zkb_ctx* ctx, const zkb_gate* gates, uint64_t n_gates, const uint8_t* const_pool_le,
                    size_t const_stride, uint64_t n_consts);
 
-/* Host preparation: levelize the recorded SSA list into wavefronts, assign wire-store slots,
- * fuse assertions, upload the device program.  keep_all_values != 0 keeps every recorded
- * value readable through zkb_read_values (needed for wire-by-wire parity checks). */
-int zkb_finalize(zkb_ctx* ctx, int keep_all_values);
+/* Host preparation: levelize the recorded SSA list into wavefronts, assign wire-store slots
+ * (liveness-based re-use), fuse assertions, upload the device program.  keep_values:
+ *   0  values bound to wires that are still live in the top scope stay readable (zkb_read_values,
+ *      Evaluator::get) — the state the reference's Evaluator holds when it finishes;
+ *   1  every recorded value stays readable (wire-by-wire parity checks; no slot re-use);
+ *   2  verdicts only: nothing is kept, slots are re-used as soon as their last reader ran. */
+int zkb_finalize(zkb_ctx* ctx, int keep_values);
 
 typedef struct {
     uint8_t ok; /* 1: every assertion holds for this witness (the statement is TRUE) */

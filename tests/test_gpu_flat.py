@@ -181,3 +181,43 @@ def test_run_twice_device_resident():
     assert int(v1[7]["first_fail_seq"]) == int(circ.tie_assert_seq[1])
     t = b.timing()
     assert t["level_launches"] > 0 and t["levels_ms"] > 0
+
+
+def test_slot_reuse_keeps_results(monkeypatch):
+    """liveness-based slot re-use (keep_all_values = 0): same verdicts and live wires with far fewer slots"""
+    z = zkb()
+    c = circuits()
+    flat = _oracle()
+    p = FIELDS["bn254"]
+    circ = c.random_circuit(20000, 64, p, seed=31, n_ties=8, window=256)
+    # free most wires so they are not observable: everything below the last 300 wire ids
+    g = np.zeros(1, dtype=c.GATE_DTYPE)
+    g["op"], g["a"], g["b"] = c.G_FREE, 0, circ.n_wires - 300
+    gates = np.concatenate([circ.gates, g])
+    n_batch = 19
+    corrupt = {4: 3, 18: 0}
+    w = c.make_witnesses(circ, n_batch, seed=2, corrupt=corrupt)
+    ref = flat.eval_batch(gates, circ.const_pool, p.to_bytes(32, "little"), None, w, n_batch, n_threads=4)
+    slots = {}
+    for reuse in ("0", "1"):
+        monkeypatch.setenv("ZKB_SLOT_REUSE", reuse)
+        b = z.GpuBackend(0)
+        b.set_field(p)
+        b.push_gates(gates, circ.const_pool)
+        b.finalize(keep_all_values=False)
+        v = b.evaluate(None, w, n_batch)
+        slots[reuse] = b.stats()["n_slots"]
+        for j in range(n_batch):
+            assert bool(v[j]["ok"]) == (int(ref[j]["status"]) == flat.EV_TRUE)
+            if not v[j]["ok"]:
+                assert int(v[j]["first_fail_seq"]) == int(ref[j]["fail_assert_seq"])
+        # live (not freed) wires stay readable and exact
+        _, dump = flat.eval_dump(gates, circ.const_pool, p.to_bytes(32, "little"), None, w[0], circ.n_wires)
+        live = list(range(circ.n_wires - 299, circ.n_wires))
+        vals = b.read_values(0, [b.scope_lookup(i) for i in live], 32)
+        assert vals == [int.from_bytes(dump[i].tobytes(), "little") for i in live]
+        if reuse == "1":   # a freed wire's value is no longer kept on device
+            with pytest.raises(z.ZkbError):
+                b.read_values(0, [circ.n_inputs + 50], 32)
+        b.close()
+    assert slots["1"] < slots["0"] / 10, slots

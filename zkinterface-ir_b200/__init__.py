@@ -271,8 +271,9 @@ class GpuBackend:
         self._chk(_lib.zkb_push_gates(self._c, _buf(gates), len(gates), _buf(const_pool), const_pool.shape[1],
                                       const_pool.shape[0]))
 
-    def finalize(self, keep_all_values: bool = False):
-        self._chk(_lib.zkb_finalize(self._c, int(keep_all_values)))
+    def finalize(self, keep_all_values: bool = False, verdicts_only: bool = False):
+        """keep_all_values: every value readable (no slot re-use); verdicts_only: nothing readable"""
+        self._chk(_lib.zkb_finalize(self._c, 1 if keep_all_values else (2 if verdicts_only else 0)))
 
     @staticmethod
     def _pack_inputs(x):

@@ -44,11 +44,16 @@ static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
     return ZKB_OK;
 }
 
-int ctx_finalize(zkb_ctx* c, bool keep_all) {
+int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
+    const bool keep_all = keep_values == 1;
     // observable values: whatever is still bound in the flat scope, plus the Evaluator's live wires
-    std::vector<uint32_t> live = c->live_values;
-    c->flat_scope.for_each([&](uint64_t, uint32_t v) { live.push_back(v); });
+    std::vector<uint32_t> live;
+    if (keep_values != 2) {
+        live = c->live_values;
+        c->flat_scope.for_each([&](uint64_t, uint32_t v) { live.push_back(v); });
+    }
+    if (const char* e = getenv("ZKB_SLOT_REUSE")) c->plan.slot_reuse = atoi(e) != 0;
     c->plan.build(c->prog, keep_all, &live);
     c->keep_all = keep_all;
     c->finalized = true;
@@ -321,9 +326,10 @@ extern "C" int zkb_scope_lookup(zkb_ctx* c, uint64_t wire, zkb_wire* out) {
     return ZKB_OK;
 }
 
-extern "C" int zkb_finalize(zkb_ctx* c, int keep_all_values) {
+extern "C" int zkb_finalize(zkb_ctx* c, int keep_values) {
     if (c->finalized) return c->fail(ZKB_E_ARG, "program already finalized");
-    return ctx_finalize(c, keep_all_values != 0);
+    if (keep_values < 0 || keep_values > 2) return c->fail(ZKB_E_ARG, "keep_values must be 0, 1 or 2");
+    return ctx_finalize(c, keep_values);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -621,7 +627,7 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
     for (uint64_t i = 0; i < n; i++) {
         if (values[i] >= p.n_values()) return c->fail(ZKB_E_ARG, "unknown wire handle");
         uint32_t s = c->plan.slot_of_value[values[i]];
-        if (s == kNoSlot)
+        if (s == kNoSlot || !c->plan.readable[values[i]])
             return c->fail(ZKB_E_ARG, "value was not kept on device (finalize with keep_all_values = 1 to read every value)");
         slots[i] = s;
     }

@@ -128,7 +128,7 @@ struct zkb_ctx {
 
 namespace zkb {
 // shared helpers implemented in backend.cu
-int ctx_finalize(zkb_ctx* c, bool keep_all);
+int ctx_finalize(zkb_ctx* c, int keep_values);  // 0 live wires, 1 all values, 2 verdicts only
 bool ctx_record_ok(zkb_ctx* c);  // false when a recording error is latched
 void ctx_latch(zkb_ctx* c, const std::string& msg);
 void r1cs_free(zkb_ctx* c);

@@ -490,7 +490,7 @@ struct zkb_evaluator {
             if (!c->finalized) {
                 c->live_values.clear();
                 values.for_each([&](uint64_t, uint32_t v) { c->live_values.push_back(v); });
-                int rc = ctx_finalize(c, false);
+                int rc = ctx_finalize(c, 0);
                 if (rc != ZKB_OK) return fail(rc, c->err);
             }
             // pack the queued streams: one statement = batch of 1

@@ -173,6 +173,30 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     for (uint32_t l = 0; l < n_levels; l++)
         max_level_ops = (uint32_t)std::max<uint64_t>(max_level_ops, level_off[l + 1] - level_off[l]);
 
+    // last wavefront that reads each value (kForever: must stay readable after the run)
+    constexpr uint32_t kForever = 0xFFFFFFFFu;
+    const bool reuse = !keep_all && slot_reuse;
+    std::vector<uint32_t> last_use;
+    if (reuse) {
+        last_use.assign(n, 0);
+        for (uint32_t v = 0; v < n; v++) {
+            uint8_t k = kind[v];
+            if (k <= V_WITNESS) continue;
+            if (level[v] > last_use[opa[v]]) last_use[opa[v]] = level[v];
+            if (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR)
+                if (level[v] > last_use[opb[v]]) last_use[opb[v]] = level[v];
+        }
+        for (uint32_t v : input_assert_value)
+            if (last_use[v] < 1) last_use[v] = 1;
+        for (uint32_t v = 0; v < n; v++)
+            if (observable[v]) last_use[v] = kForever;
+    }
+    // slots released once wavefront l has run (re-usable from wavefront l + 1 on: inside one launch a slot is
+    // never both read and written)
+    std::vector<std::vector<uint32_t>> release_after(reuse ? (size_t)n_levels + 1 : 0);
+    std::vector<uint32_t> free_slots;  // kept sorted descending: pop_back hands out the lowest slot first
+    readable.assign(n, 0);
+
     // pass 1: place values (order index) and assign slots in placement order
     slot_of_value.assign(n, kNoSlot);
     loads.clear();
@@ -181,6 +205,8 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         if (kind[v] <= V_WITNESS) {
             slot_of_value[v] = next_slot;
             loads.push_back(InputLoad{next_slot, kind[v], opb[v], 0});
+            readable[v] = 1;  // inputs are read back from the raw streams / constant pool
+            if (reuse && last_use[v] != kForever) release_after[last_use[v]].push_back(next_slot);
             next_slot++;
         }
     std::vector<uint64_t> pos_of_value(n, 0);
@@ -197,16 +223,42 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     op_assert_seq.assign(n_ops, kNoSeq);
     for (int i = 0; i < D_OPS; i++) n_dev_ops[i] = 0;
     std::vector<uint32_t> meta_of(n_ops, 0);
-    for (uint64_t i = 0; i < n_ops; i++) {
-        uint32_t v = value_at[i];
-        if (v == kNoSlot) continue;  // standalone assert position
-        uint32_t meta = dev_op_of(kind[v]);
-        bool has_assert = aseq[v] != kNoSeq;
-        if (has_assert) meta |= F_ASSERT;
-        bool store = keep_all || used[v] || observable[v] || !has_assert;
-        if (!store) meta |= F_NOSTORE;
-        else slot_of_value[v] = next_slot++;
-        meta_of[i] = meta;
+    n_reused_slots = 0;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        if (reuse) {  // wavefront l+1 may overwrite everything whose last reader ran in wavefront <= l
+            auto& rel = release_after[l];
+            if (!rel.empty()) {
+                free_slots.insert(free_slots.end(), rel.begin(), rel.end());
+                std::sort(free_slots.begin(), free_slots.end(), std::greater<uint32_t>());
+                std::vector<uint32_t>().swap(rel);
+            }
+        }
+        for (uint64_t i = level_off[l]; i < level_off[l + 1]; i++) {
+            uint32_t v = value_at[i];
+            if (v == kNoSlot) continue;  // standalone assert position
+            uint32_t meta = dev_op_of(kind[v]);
+            bool has_assert = aseq[v] != kNoSeq;
+            if (has_assert) meta |= F_ASSERT;
+            // stored unless nothing will ever read it: a value only tested by its own fused assertion, or
+            // (with slot re-use on) a dead value — it is still computed
+            bool store = keep_all || used[v] || observable[v] || (!has_assert && !reuse);
+            if (!store) {
+                meta |= F_NOSTORE;
+            } else {
+                uint32_t slot;
+                if (!free_slots.empty()) {
+                    slot = free_slots.back();
+                    free_slots.pop_back();
+                    n_reused_slots++;
+                } else {
+                    slot = next_slot++;
+                }
+                slot_of_value[v] = slot;
+                readable[v] = keep_all || observable[v];
+                if (reuse && last_use[v] != kForever) release_after[std::max(last_use[v], l + 1)].push_back(slot);
+            }
+            meta_of[i] = meta;
+        }
     }
     n_slots = next_slot;
     // pass 2: emit ops with operand slots

@@ -128,6 +128,9 @@ struct Plan {
     uint32_t n_slots = 0;
     uint32_t n_levels = 0;
     std::vector<uint32_t> slot_of_value;  // SSA value -> slot (kNoSlot if never stored)
+    std::vector<uint8_t> readable;        // value can be read back after the run (its slot is not re-used)
+    bool slot_reuse = true;               // liveness-based slot re-use (off: one slot per stored value)
+    uint64_t n_reused_slots = 0;
     std::vector<GateOp> ops;              // level-major, opcode-sorted inside a level
     std::vector<uint32_t> op_assert_seq;  // parallel to ops
     std::vector<uint64_t> level_off;      // n_levels + 1 offsets into ops
