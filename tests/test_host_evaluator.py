@@ -206,3 +206,55 @@ def test_levelizer_invariants():
     assert st["n_device_ops"] == circ.hist["add"] + circ.hist["mul"]
     assert st["algo_bytes_per_witness"] == c.algorithmic_bytes_per_witness(circ)
     assert 1 <= st["n_levels"] < 200
+
+
+def test_relation_split_over_several_messages():
+    # builder.rs:72,90-95: a producer flushes a Relation message every 100 000 gates; functions defined in an
+    # earlier message stay known, the wire namespace and the value queues continue (evaluator.rs:158-170, 273-300)
+    msgs = STATEMENTS["example"]()
+    inst, wit, rel = msgs
+    parts = [ir.Relation(rel.header, rel.gate_mask, rel.feat_mask, rel.functions, rel.gates[:3]),
+             ir.Relation(rel.header, rel.gate_mask, rel.feat_mask, [], rel.gates[3:8]),
+             ir.Relation(rel.header, rel.gate_mask, rel.feat_mask, [], rel.gates[8:])]
+    split = [inst, wit] + parts
+    assert ev.evaluate(split) == []
+    z, b, e = record(F.write_messages(split))
+    compare_with_oracle_trace(b, split)
+    z2, b2, e2 = record(F.write_messages(msgs))
+    k1, k2 = b.program(), b2.program()
+    assert all((x == y).all() for x, y in zip(k1, k2))
+    # values arriving AFTER the first relation message are still consumed by later ones
+    late = [inst, parts[0]]
+    tb = ev.TracingBackend()
+    with pytest.raises(ir.OraclePanic):          # ... but a witness that is not there yet is a panic in the reference
+        ev.Evaluator.from_messages(late, tb)
+
+
+def test_reader_survives_corrupted_buffers():
+    """bounds-checked FlatBuffers walker: random corruption must end in ZKB_E_FORMAT / a latched error / success,
+    never in a crash"""
+    z = zkb()
+    rng = np.random.default_rng(11)
+    base = bytearray(F.write_message(fx.example_relation()))
+    outcomes = {"ok": 0, "format": 0, "fatal": 0}
+    for trial in range(400):
+        buf = bytearray(base)
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(4, len(buf)))
+            buf[pos] = int(rng.integers(0, 256))
+        e = z.Evaluator(z.GpuBackend(-1))
+        # the witness the (possibly still valid) relation needs
+        e.ingest_message(F.write_message(fx.example_instance()))
+        e.ingest_message(F.write_message(fx.example_witness()))
+        try:
+            e.ingest_message(bytes(buf))
+            outcomes["ok"] += 1
+        except z.ZkbError as err:
+            assert err.code in (z.ZKB_E_FORMAT, z.ZKB_E_FATAL, z.ZKB_E_UNSUPPORTED, z.ZKB_E_SEMANTIC), err.code
+            outcomes["format" if err.code == z.ZKB_E_FORMAT else "fatal"] += 1
+    assert outcomes["format"] > 0 and outcomes["ok"] > 0, outcomes
+    # truncations
+    for cut in range(8, len(base), 97):
+        e = z.Evaluator(z.GpuBackend(-1))
+        with pytest.raises(z.ZkbError):
+            e.ingest_message(bytes(base[:cut]))

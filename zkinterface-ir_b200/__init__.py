@@ -171,7 +171,7 @@ class GpuBackend:
     def __init__(self, device: int = 0):
         self._c = _lib.zkb_create(device)
         self.device = device
-        err = _lib.zkb_last_error(self._c).decode()
+        err = _lib.zkb_last_error(self._c).decode("utf-8", "replace")
         if device >= 0 and err:
             _lib.zkb_destroy(self._c)
             self._c = None
@@ -191,7 +191,7 @@ class GpuBackend:
 
     def _chk(self, rc):
         if rc != ZKB_OK:
-            raise ZkbError(rc, _lib.zkb_last_error(self._c).decode())
+            raise ZkbError(rc, _lib.zkb_last_error(self._c).decode("utf-8", "replace"))
 
     # ---- ZKBackend methods -------------------------------------------------
     @staticmethod
@@ -317,7 +317,7 @@ class GpuBackend:
 
     def pending_error(self) -> Optional[str]:
         e = _lib.zkb_pending_error(self._c)
-        return e.decode() if e else None
+        return e.decode("utf-8", "replace") if e else None
 
     def read_values(self, batch_idx: int, values: Sequence[int], stride: int = 32) -> List[int]:
         vals = np.ascontiguousarray(values, dtype=np.uint64)
@@ -442,7 +442,7 @@ class Evaluator:
 
     def _chk(self, rc):
         if rc != ZKB_OK:
-            raise ZkbError(rc, _lib.zkb_evaluator_last_error(self._e).decode())
+            raise ZkbError(rc, _lib.zkb_evaluator_last_error(self._e).decode("utf-8", "replace"))
 
     @classmethod
     def from_messages(cls, source: Source, backend: Optional[GpuBackend] = None, device: int = 0):
@@ -464,7 +464,7 @@ class Evaluator:
     def get_violations(self) -> List[str]:
         n = C.c_size_t()
         self._chk(_lib.zkb_evaluator_get_violations(self._e, C.byref(n)))
-        return [_lib.zkb_evaluator_violation(self._e, i).decode() for i in range(n.value)]
+        return [_lib.zkb_evaluator_violation(self._e, i).decode("utf-8", "replace") for i in range(n.value)]
 
     def value_handle(self, wire_id: int) -> int:
         """SSA handle bound to a live top-scope wire (for GpuBackend.read_values on any batch element)"""
