@@ -132,10 +132,10 @@ def main():
     n_gates = 1 << args.log2_gates
 
     import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
     import zkb_loader
     import importlib
+    if args.impl == "reference" or world == 1:
+        ge.build()
 
     if args.impl == "reference":
         if rank != 0:
@@ -170,6 +170,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if rank == 0:          # one rank (re)builds if needed; the others load the library only afterwards
+            ge.build()
+        dist.barrier()
     z = zkb_loader.load()
     circ_mod = importlib.import_module("zkir_b200.circuits")
 

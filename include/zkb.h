@@ -250,6 +250,13 @@ int zkb_r1cs_check(zkb_ctx* ctx, const uint8_t* z_le, uint64_t z_set_stride, uin
 int zkb_r1cs_upload(zkb_ctx* ctx, const uint8_t* z_le, uint64_t z_set_stride, uint32_t value_stride, uint32_t n_batch);
 int zkb_r1cs_run(zkb_ctx* ctx, zkb_verdict* out);
 
+/* ------------------------------------------------------------------ 6. debug / measurement
+ * Not part of the drop-in surface.  field_ops: r[i] = a[i] op b[i] on the device for n elements of nlimb 32-bit
+ * limbs (op 0: modular add; 1: Montgomery product as the kernels compute it; 2: portable CIOS product).
+ * field_throughput: register-resident dependent chains of `iters` operations per thread -> operations/s. */
+int zkb_debug_field_ops(zkb_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint64_t n);
+int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops_per_second);
+
 #ifdef __cplusplus
 }
 #endif

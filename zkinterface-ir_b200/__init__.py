@@ -72,7 +72,7 @@ EXPORTED = [
     "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_level_info", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
     "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
     "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
-    "zkb_r1cs_upload", "zkb_r1cs_run",
+    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput",
 ]
 
 _vp, _u8p, _sz, _u64, _u32, _i = C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
@@ -131,6 +131,8 @@ _sig("zkb_r1cs_load", _i, _vp, C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), C.POINTER(Z
 _sig("zkb_r1cs_check", _i, _vp, _u8p, _u64, _u32, _u32, _vp)
 _sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
 _sig("zkb_r1cs_run", _i, _vp, _vp)
+_sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
+_sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
 
 
 class ZkbError(Exception):
@@ -366,6 +368,19 @@ class GpuBackend:
         t = ZkbTiming()
         self._chk(_lib.zkb_get_timing(self._c, C.byref(t)))
         return {k: getattr(t, k) for k, _ in ZkbTiming._fields_}
+
+    # ---- debug / measurement ---------------------------------------------------
+    def debug_field_ops(self, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        r = np.zeros_like(a)
+        self._chk(_lib.zkb_debug_field_ops(self._c, op, _buf(a), _buf(b), _buf(r), a.shape[0]))
+        return r
+
+    def debug_field_throughput(self, op: int, iters: int = 2000) -> float:
+        out = C.c_double()
+        self._chk(_lib.zkb_debug_field_throughput(self._c, op, iters, C.byref(out)))
+        return out.value
 
     # ---- R1CS -----------------------------------------------------------------
     def r1cs_load(self, A, B, Cm, coef_table: np.ndarray, n_vars: int):
