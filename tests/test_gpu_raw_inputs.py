@@ -1,0 +1,85 @@
+"""SURVEY.md section 8a trap 1: instance / witness / constant values >= p stay RAW in the reference
+(evaluator.rs:862-864, 896-898): AssertZero and Not test the raw integer, Add/Mul reduce.  The device resolves
+this itself (raw flags written by the input kernel); every case is compared with the oracle."""
+import numpy as np
+import pytest
+
+from oracle import evaluator as ev
+from oracle import ir
+from oracle import sieve_fbs as F
+from tests.util import zkb
+
+pytestmark = pytest.mark.gpu
+
+
+def both(msgs):
+    z = zkb()
+    e = z.Evaluator.from_messages(z.Source.from_buffers([F.write_messages(msgs)]), device=0)
+    return e.get_violations(), ev.evaluate(msgs), e
+
+
+@pytest.mark.parametrize("p", [101, (1 << 64) - (1 << 32) + 1, 2])
+def test_assert_and_not_on_unreduced_inputs(p):
+    h = ir.Header(ir.le_bytes(p))
+    boolean = p == 2
+    mask = ir.BOOL if boolean else ir.ARITH
+    addz = (lambda o, a: ("Xor", o, a, a)) if boolean else (lambda o, a: ("AddConstant", o, a, b"\x00"))
+    cases = []
+    for raw in (0, 1, p, 2 * p, p + 1, 3 * p):
+        w = ir.le_bytes(raw)
+        # assert directly on the witness: fails iff the RAW integer is non-zero
+        cases.append(([("Witness", 0), ("AssertZero", 0)], [w], []))
+        # assert after an arithmetic gate: reduced first
+        cases.append(([("Witness", 0), addz(1, 0), ("AssertZero", 1)] if not boolean else
+                      [("Witness", 0), ("Witness", 1), ("Xor", 2, 0, 1), ("AssertZero", 2)],
+                      [w] if not boolean else [w, b"\x00"], []))
+        # not(witness): 1 iff the RAW integer is zero; assert(not) fails iff raw == 0
+        cases.append(([("Witness", 0), ("Not", 1, 0), ("AssertZero", 1)], [w], []))
+        # through copies and as an instance
+        cases.append(([("Instance", 0), ("Copy", 1, 0), ("Copy", 2, 1), ("Not", 3, 2), ("AssertZero", 3), ("AssertZero", 2)], [], [w]))
+        # a constant >= p
+        cases.append(([("Constant", 0, w), ("Not", 1, 0), ("AssertZero", 1)], [], []))
+        cases.append(([("Constant", 0, w), ("AssertZero", 0)], [], []))
+    for gates, wit, inst in cases:
+        rel = ir.Relation(h, mask if not boolean else ir.BOOL, ir.SIMPLE, [], gates)
+        msgs = [ir.Instance(h, inst), ir.Witness(h, wit), rel]
+        got, want, e = both(msgs)
+        assert got == want, (p, gates, wit, inst)
+
+
+def test_batch_with_some_unreduced_witnesses():
+    z = zkb()
+    p = 101
+    h = ir.Header(ir.le_bytes(p))
+    gates = [("Witness", 0), ("Witness", 1), ("Add", 2, 0, 1), ("AssertZero", 2), ("Not", 3, 1), ("Mul", 4, 3, 0), ("AssertZero", 4),
+             ("AssertZero", 1)]
+    rel = ir.Relation(h, ir.ARITH | ir.NOT, ir.SIMPLE, [], gates)
+    rows = [(0, 0), (101, 0), (0, 101), (5, 96), (202, 0), (0, 202), (3, 98), (101, 101)]
+    b = z.GpuBackend(0)
+    e = z.Evaluator(b)
+    e.ingest_source(z.Source.from_buffers([F.write_messages([ir.Witness(h, [ir.le_bytes(rows[0][0]), ir.le_bytes(rows[0][1])]), rel])]))
+    assert e.get_violations() == []
+    W = np.zeros((len(rows), 2, 4), dtype=np.uint8)
+    for j, (x, y) in enumerate(rows):
+        W[j, 0, 0], W[j, 1, 0] = x, y
+    v = b.evaluate(None, W, len(rows))
+    for j, (x, y) in enumerate(rows):
+        want = ev.evaluate([ir.Witness(h, [ir.le_bytes(x), ir.le_bytes(y)]), rel])
+        got = [] if v[j]["ok"] else [f"Wire_{b.assert_wire(int(v[j]['first_fail_seq']))} (may be weighted) should be 0, while it is not"]
+        assert got == want, (j, x, y)
+
+
+def test_bitwise_gate_on_unreduced_input_is_refused_loudly():
+    z = zkb()
+    p = 101
+    h = ir.Header(ir.le_bytes(p))
+    rel = ir.Relation(h, ir.ARITH | ir.BOOL, ir.SIMPLE, [], [("Witness", 0), ("Witness", 1), ("And", 2, 0, 1), ("AssertZero", 2)])
+    for w0, ok in ((3, True), (101 + 3, False)):
+        e = z.Evaluator.from_messages(z.Source.from_buffers([F.write_messages([ir.Witness(h, [ir.le_bytes(w0), b"\x04"]), rel])]),
+                                      device=0)
+        if ok:
+            assert e.get_violations() == ev.evaluate([ir.Witness(h, [ir.le_bytes(w0), b"\x04"]), rel])
+        else:
+            with pytest.raises(z.ZkbError) as err:
+                e.get_violations()
+            assert err.value.code == z.ZKB_E_UNSUPPORTED

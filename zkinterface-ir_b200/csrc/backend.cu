@@ -47,6 +47,14 @@ static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
 int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
     const bool keep_all = keep_values == 1;
+    // a bitwise gate on a constant >= p would need the unreduced integer (evaluator.rs:924-930): refuse up front
+    for (uint32_t v = 0; v < c->prog.n_values(); v++) {
+        uint8_t k = c->prog.kind[v];
+        if (k != V_AND && k != V_XOR) continue;
+        for (uint32_t o : {c->prog.opa[v], c->prog.opb[v]})
+            if (c->prog.kind[o] == V_CONST && c->prog.const_unreduced[c->prog.opb[o]])
+                return c->fail(ZKB_E_UNSUPPORTED, "zkb: a constant >= p feeds a bitwise gate directly (unreduced-integer semantics)");
+    }
     // observable values: whatever is still bound in the flat scope, plus the Evaluator's live wires
     std::vector<uint32_t> live;
     if (keep_values != 2) {
@@ -66,6 +74,7 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     if ((rc = upload_vec(c, c->d_loads, c->plan.loads)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_consts, c->prog.const_limbs)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_level_off, c->plan.level_off)) != ZKB_OK) return rc;
+    if (c->plan.n_raw_ops > 0 && (rc = upload_vec(c, c->d_const_flags, c->prog.const_unreduced)) != ZKB_OK) return rc;
     if (!c->prog.binary) launch_to_mont(c->prog.nlimb, c->d_consts, c->prog.n_consts(), c->prog.fp, c->stream);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ZKB_OK;
@@ -114,6 +123,8 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_loads);
         cudaFree(c->d_consts);
         cudaFree(c->d_level_off);
+        cudaFree(c->d_const_flags);
+        cudaFree(c->d_rawflag);
         cudaFree(c->d_store);
         cudaFree(c->d_inst);
         cudaFree(c->d_wit);
@@ -371,6 +382,15 @@ static int choose_tile(zkb_ctx* c, uint32_t n_batch) {
     }
     c->log2_wt = l2;
     c->resident_tile = -1;
+    // per (input, lane) "raw integer >= p" flags, only when some gate tests an input value directly (trap 1)
+    size_t flag_bytes = c->plan.n_raw_ops > 0 ? (c->plan.loads.size() << l2) : 0;
+    if (flag_bytes > c->rawflag_bytes) {
+        if (c->d_rawflag) cudaFree(c->d_rawflag);
+        c->d_rawflag = nullptr;
+        c->rawflag_bytes = 0;
+        CUDA_TRY(c, cudaMalloc((void**)&c->d_rawflag, flag_bytes));
+        c->rawflag_bytes = flag_bytes;
+    }
     return ZKB_OK;
 }
 
@@ -440,11 +460,13 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     uint32_t wt = 1u << c->log2_wt;
     g.n_valid = std::min<uint32_t>(wt, c->n_batch - g.batch0);
     g.pad = 0;
+    uint8_t* rawflag = pl.n_raw_ops > 0 ? c->d_rawflag : nullptr;
     if (p.binary)
-        launch_bool_load_inputs(c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, c->stream);
+        launch_bool_load_inputs(c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, rawflag,
+                                c->d_const_flags, c->stream);
     else
-        launch_load_inputs(p.nlimb, c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, p.fp,
-                           c->stream);
+        launch_load_inputs(p.nlimb, c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, rawflag,
+                           c->d_const_flags, p.fp, c->stream);
     (*launches)++;
     const bool timed = level_launches != nullptr && d_fail == c->d_first_fail;
     if (timed) {
@@ -459,8 +481,8 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     bool coop = !p.binary && pl.n_levels > 1 && ((uint64_t)pl.max_level_ops << c->log2_wt) <= (uint64_t)c->sm_count * 8192;
     if (const char* e = getenv("ZKB_COOP")) coop = coop && atoi(e) != 0;
     if (coop && c->coop_supported) {
-        cudaError_t e = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, g,
-                                           p.fp, c->sm_count, (uint64_t)pl.max_level_ops << c->log2_wt, c->stream);
+        cudaError_t e = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, rawflag,
+                                           g, p.fp, c->sm_count, (uint64_t)pl.max_level_ops << c->log2_wt, c->stream);
         if (e == cudaSuccess) {
             (*launches)++;
             if (level_launches) (*level_launches)++;
@@ -476,20 +498,20 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         uint64_t lo = pl.level_off[l], mid = pl.level_rare[l], hi = pl.level_off[l + 1];
         if (p.binary) {
             if (hi > lo) {
-                launch_bool_level(c->d_ops + lo, c->d_aseq + lo, hi - lo, c->d_store, c->d_consts, d_fail, g, c->sm_count, c->stream);
+                launch_bool_level(c->d_ops + lo, c->d_aseq + lo, hi - lo, c->d_store, c->d_consts, d_fail, rawflag, g, c->sm_count, c->stream);
                 (*launches)++;
                 (*level_launches)++;
             }
             continue;
         }
         if (mid > lo) {
-            launch_level(p.nlimb, c->d_ops + lo, c->d_aseq + lo, mid - lo, c->d_store, c->d_consts, d_fail, g, p.fp, c->sm_count, false,
+            launch_level(p.nlimb, c->d_ops + lo, c->d_aseq + lo, mid - lo, c->d_store, c->d_consts, d_fail, rawflag, g, p.fp, c->sm_count, false,
                          c->stream);
             (*launches)++;
             (*level_launches)++;
         }
         if (hi > mid) {
-            launch_level(p.nlimb, c->d_ops + mid, c->d_aseq + mid, hi - mid, c->d_store, c->d_consts, d_fail, g, p.fp, c->sm_count, true,
+            launch_level(p.nlimb, c->d_ops + mid, c->d_aseq + mid, hi - mid, c->d_store, c->d_consts, d_fail, rawflag, g, p.fp, c->sm_count, true,
                          c->stream);
             (*launches)++;
             (*level_launches)++;
@@ -499,38 +521,22 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     c->resident_tile = tile;
 }
 
-// SURVEY.md §8a trap 1: values >= p stay RAW in the reference.  The device works on residues, which
-// is exact for add/mul; the raw-sensitive consumers of an input value are resolved here, on the
-// (rare) path where the load kernel counted at least one unreduced input.
-static int resolve_unreduced(zkb_ctx* c, std::vector<uint32_t>& first_fail) {
+// SURVEY.md §8a trap 1: values >= p stay RAW in the reference.  The device works on residues, which is exact
+// for add/mul (the reference reduces their results).  The raw-sensitive consumers of an input value are
+// resolved ON THE DEVICE: k_load_inputs writes a per-(input, witness) "raw integer >= p" flag, and the
+// assert / not gates that read an input directly (F_RAW) treat a flagged operand as the non-zero integer it
+// is.  What the device cannot reproduce is a bitwise gate on the unreduced integer itself: refused loudly.
+static int check_unreduced_supported(zkb_ctx* c) {
     const Program& p = c->prog;
-    const Plan& pl = c->plan;
-    // and / xor / not reading an input value directly would need the raw integer on device
     for (uint32_t v = 0; v < p.n_values(); v++) {
         uint8_t k = p.kind[v];
-        if (k == V_AND || k == V_XOR || k == V_NOT) {
-            bool direct = p.kind[p.opa[v]] <= V_WITNESS && p.kind[p.opa[v]] != V_CONST;
-            if (k != V_NOT) direct = direct || (p.kind[p.opb[v]] <= V_WITNESS && p.kind[p.opb[v]] != V_CONST);
+        if (k == V_AND || k == V_XOR) {
+            bool direct = p.kind[p.opa[v]] == V_INSTANCE || p.kind[p.opa[v]] == V_WITNESS || p.kind[p.opb[v]] == V_INSTANCE ||
+                          p.kind[p.opb[v]] == V_WITNESS;
             if (direct)
                 return c->fail(ZKB_E_UNSUPPORTED,
                                "zkb: an instance/witness value >= p feeds a bitwise gate directly; the reference evaluates that on the "
                                "unreduced integer, which the device path does not hold");
-        }
-    }
-    if (pl.input_assert_value.empty()) return ZKB_OK;
-    // bring the raw inputs back and test them
-    std::vector<uint8_t> hi(c->inst_bytes ? c->inst_bytes : 1), hw(c->wit_bytes ? c->wit_bytes : 1);
-    CUDA_TRY(c, cudaMemcpy(hi.data(), c->d_inst, c->inst_bytes, cudaMemcpyDeviceToHost));
-    CUDA_TRY(c, cudaMemcpy(hw.data(), c->d_wit, c->wit_bytes, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < pl.input_assert_value.size(); i++) {
-        uint32_t v = pl.input_assert_value[i], seq = pl.input_assert_seq[i];
-        if (p.kind[v] == V_CONST) continue;  // handled statically in zkb_run
-        for (uint32_t j = 0; j < c->n_batch; j++) {
-            const uint8_t* src = p.kind[v] == V_INSTANCE ? hi.data() + (size_t)j * c->in.inst_set_stride
-                                                         : hw.data() + (size_t)j * c->in.wit_set_stride;
-            src += (size_t)p.opb[v] * c->in.stride;
-            BigU raw = BigU::from_bytes_le(src, c->in.stride);
-            if (raw >= p.modulus && seq < first_fail[j]) first_fail[j] = seq;  // raw != 0: the assertion fails
         }
     }
     return ZKB_OK;
@@ -570,14 +576,8 @@ extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
     c->timing.load_ms = ms - lv;    // input conversion, verdict fill/copy, gaps
     c->timing.level_launches = level_launches;
     c->timing.kernel_launches = launches;
-    // constants >= p that are asserted directly fail for every witness (raw integer != 0)
-    for (size_t i = 0; i < c->plan.input_assert_value.size(); i++) {
-        uint32_t v = c->plan.input_assert_value[i];
-        if (c->prog.kind[v] == V_CONST && c->prog.const_unreduced[c->prog.opb[v]])
-            for (auto& f : c->h_first_fail) f = std::min(f, c->plan.input_assert_seq[i]);
-    }
     if (unreduced) {
-        int rc = resolve_unreduced(c, c->h_first_fail);
+        int rc = check_unreduced_supported(c);
         if (rc != ZKB_OK) return rc;
     }
     if (out)

@@ -98,6 +98,9 @@ struct zkb_ctx {
     zkb::InputLoad* d_loads = nullptr;
     uint32_t* d_consts = nullptr;
     uint64_t* d_level_off = nullptr;
+    uint8_t* d_const_flags = nullptr;   // per constant: raw value >= p
+    uint8_t* d_rawflag = nullptr;       // per (input load, lane): raw value >= p (only when plan.n_raw_ops > 0)
+    size_t rawflag_bytes = 0;
     bool coop_supported = false;
     uint32_t* d_store = nullptr;
     size_t store_bytes = 0;

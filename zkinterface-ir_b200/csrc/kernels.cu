@@ -45,7 +45,8 @@ __global__ void k_to_mont(uint32_t* consts, uint32_t n, FieldParams fp) {
 template <int N>
 __global__ void __launch_bounds__(256)
 k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* __restrict__ store,
-              const uint32_t* __restrict__ consts_mont, InputDesc in, TileGeom g, uint32_t* unreduced_count, FieldParams fp) {
+              const uint32_t* __restrict__ consts_mont, InputDesc in, TileGeom g, uint32_t* unreduced_count,
+              uint8_t* __restrict__ rawflag, const uint8_t* __restrict__ const_flags, FieldParams fp) {
     const uint64_t total = (uint64_t)n_loads << g.log2_wt;
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
@@ -53,12 +54,14 @@ k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* _
         uint32_t lane = (uint32_t)tid & wt_mask;
         InputLoad ld = loads[tid >> g.log2_wt];
         uint32_t v[N];
+        bool raw_ge_p = false;  // the reference would hold this input unreduced (raw integer >= p)
 #pragma unroll
         for (int k = 0; k < N; k++) v[k] = 0;
         if (lane < g.n_valid) {
             if (ld.kind == V_CONST) {
 #pragma unroll
                 for (int k = 0; k < N; k++) v[k] = consts_mont[(size_t)ld.index * N + k];
+                raw_ge_p = const_flags != nullptr && const_flags[ld.index] != 0;
             } else {
                 const uint8_t* src = (ld.kind == V_INSTANCE)
                                          ? in.inst + (uint64_t)(g.batch0 + lane) * in.inst_set_stride
@@ -87,7 +90,8 @@ k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* _
                     borrow = (uint32_t)(t >> 63);
                 }
                 (void)d;
-                if (wide || borrow == 0) atomicAdd(unreduced_count, 1u);
+                raw_ge_p = wide || borrow == 0;
+                if (raw_ge_p) atomicAdd(unreduced_count, 1u);
                 uint32_t m[N];
                 fe_mont_mul<N>(m, v, fp.r2, fp.p, fp.n0inv);  // also reduces v in [p, 2^(32N)) mod p
 #pragma unroll
@@ -95,6 +99,7 @@ k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* _
             }
         }
         store_elem<N>(store, ld.slot, lane, g.log2_wt, v);
+        if (rawflag) rawflag[((tid >> g.log2_wt) << g.log2_wt) + lane] = raw_ge_p;
     }
 }
 
@@ -104,7 +109,8 @@ k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* _
 //   NOT is (a == 0) ? 1 : 0 (evaluator.rs:932-938); zero is zero in Montgomery form too.
 //   ASSERT passes the operand through so the caller tests it.
 template <int N>
-__device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t opc, const FieldParams& fp) {
+__device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t opc, const FieldParams& fp,
+                                          bool raw_nonzero) {
     if (opc == D_AND || opc == D_XOR) {
         uint32_t one[N], ca[N], cb[N], x[N];
 #pragma unroll
@@ -115,12 +121,13 @@ __device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const 
         else fe_xor_canon<N>(x, ca, cb, fp.p);
         fe_mont_mul<N>(r, x, fp.r2, fp.p, fp.n0inv);
     } else if (opc == D_NOT) {
-        bool z = fe_is_zero<N>(a);
+        bool z = fe_is_zero<N>(a) && !raw_nonzero;  // an input >= p is a non-zero integer even when it is 0 mod p
 #pragma unroll
         for (int k = 0; k < N; k++) r[k] = z ? fp.one[k] : 0u;
-    } else {
+    } else {  // standalone assertion on an input: report non-zero when the raw integer is (evaluator.rs:900-906)
 #pragma unroll
         for (int k = 0; k < N; k++) r[k] = a[k];
+        if (raw_nonzero) r[0] |= 1u;
     }
 }
 
@@ -132,7 +139,8 @@ __device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const 
 template <int N, bool RARE>
 __global__ void __launch_bounds__(256)
 k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
-        const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
+        const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag,
+        TileGeom g, FieldParams fp) {
     const uint64_t total = n_ops << g.log2_wt;
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
@@ -161,7 +169,8 @@ k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint6
 #pragma unroll
                 for (int k = 0; k < N; k++) b[k] = 0;
             }
-            rare_gate<N>(r, a, b, opc, fp);
+            const bool raw_nonzero = (raw.w & F_RAW) && rawflag != nullptr && rawflag[((size_t)raw.x << g.log2_wt) + lane] != 0;
+            rare_gate<N>(r, a, b, opc, fp, raw_nonzero);
         }
         if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
         if (raw.w & F_ASSERT) {
@@ -242,7 +251,7 @@ template <int N>
 __global__ void __launch_bounds__(256)
 k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
               uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
-              TileGeom g, FieldParams fp) {
+              const uint8_t* __restrict__ rawflag, TileGeom g, FieldParams fp) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
@@ -280,7 +289,10 @@ k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq,
             }
             if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
             else if (opc == D_MUL || opc == D_MULC) fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
-            else rare_gate<N>(r, a, b, opc, fp);
+            else {
+                const bool raw_nonzero = (raw.w & F_RAW) && rawflag != nullptr && rawflag[((size_t)raw.x << g.log2_wt) + lane] != 0;
+                rare_gate<N>(r, a, b, opc, fp, raw_nonzero);
+            }
             if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
             if (raw.w & F_ASSERT) {
                 bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
@@ -313,7 +325,8 @@ __global__ void k_read_values(const uint32_t* __restrict__ slots, uint32_t n, co
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_bool_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* __restrict__ store,
-                   const uint32_t* __restrict__ const_bits, InputDesc in, TileGeom g, uint32_t* unreduced_count) {
+                   const uint32_t* __restrict__ const_bits, InputDesc in, TileGeom g, uint32_t* unreduced_count,
+                   uint8_t* __restrict__ rawflag, const uint8_t* __restrict__ const_flags) {
     const uint32_t log2_words = g.log2_wt - 5;
     const uint64_t total = ((uint64_t)n_loads << g.log2_wt);  // one thread per (load, lane), ballot packs
     for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
@@ -321,9 +334,11 @@ k_bool_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32
         uint32_t lane = (uint32_t)tid & ((1u << g.log2_wt) - 1);
         InputLoad ld = loads[tid >> g.log2_wt];
         uint32_t bit = 0;
+        bool raw_ge_p = false;
         if (lane < g.n_valid) {
             if (ld.kind == V_CONST) {
                 bit = const_bits[ld.index] & 1;
+                raw_ge_p = const_flags != nullptr && const_flags[ld.index] != 0;
             } else {
                 const uint8_t* src = (ld.kind == V_INSTANCE)
                                          ? in.inst + (uint64_t)(g.batch0 + lane) * in.inst_set_stride
@@ -332,18 +347,21 @@ k_bool_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32
                 uint32_t hi = 0;
                 for (uint32_t b = 0; b < in.stride; b++) hi |= (b == 0) ? (uint32_t)(src[0] >> 1) : (uint32_t)src[b];
                 bit = src[0] & 1;
+                raw_ge_p = hi != 0;
                 if (hi) atomicAdd(unreduced_count, 1u);
             }
         }
         // blockDim is a multiple of 32 and total a multiple of 32: full warps only
         uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
         if ((lane & 31) == 0) store[((size_t)ld.slot << log2_words) + (lane >> 5)] = word;
+        if (rawflag) rawflag[((tid >> g.log2_wt) << g.log2_wt) + lane] = raw_ge_p;
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
-             const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail, TileGeom g) {
+             const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag,
+             TileGeom g) {
     const uint32_t log2_words = g.log2_wt - 5;
     const uint64_t total = n_ops << log2_words;
     const uint32_t wmask = (1u << log2_words) - 1;
@@ -364,6 +382,13 @@ k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
             case D_MULC: r = a & (0u - (__ldg(const_bits + raw.y) & 1)); break;
             case D_NOT: r = ~a; break;
             default: r = a; break;
+        }
+        if ((raw.w & F_RAW) && rawflag != nullptr) {  // input values >= 2 are non-zero integers (trap 1)
+            uint32_t nz = 0;
+            const uint8_t* f = rawflag + ((size_t)raw.x << g.log2_wt) + ((size_t)w << 5);
+            for (int bq = 0; bq < 32; bq++) nz |= (uint32_t)(f[bq] != 0) << bq;
+            if (opc == D_NOT) r &= ~nz;
+            else r |= nz;
         }
         if (!(raw.w & F_NOSTORE)) store[((size_t)raw.z << log2_words) + w] = r;
         if (raw.w & F_ASSERT) {
@@ -438,15 +463,17 @@ void launch_to_mont(int nlimb, uint32_t* consts, uint32_t n, const FieldParams& 
 }
 
 void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* consts_mont,
-                        InputDesc in, TileGeom g, uint32_t* unreduced_count, const FieldParams& fp, cudaStream_t s) {
+                        InputDesc in, TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags,
+                        const FieldParams& fp, cudaStream_t s) {
     if (n_loads == 0) return;
-    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 16);
-    ZKB_DISPATCH_N(nlimb, (k_load_inputs<N><<<grid, 256, 0, s>>>(loads, n_loads, store, consts_mont, in, g, unreduced_count, fp)));
+    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 256);
+    ZKB_DISPATCH_N(nlimb, (k_load_inputs<N><<<grid, 256, 0, s>>>(loads, n_loads, store, consts_mont, in, g, unreduced_count, rawflag,
+                                                                 const_flags, fp)));
 }
 
 void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
-                  const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp, int sm_count,
-                  bool rare, cudaStream_t s) {
+                  const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, const FieldParams& fp,
+                  int sm_count, bool rare, cudaStream_t s) {
     if (n_ops == 0) return;
     // grid: a whole number of CTAs per SM (multiple of the SM count), grid-stride inside.  Measured on B200
     // (scripts/ab_level.sh, C3): 8 CTAs/SM (exactly resident, static partition) 87 % of the HBM roofline,
@@ -457,23 +484,23 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
         if (level_pipe_enabled()) {
             ZKB_DISPATCH_N(nlimb, (k_level_pipe<N><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
         } else {
-            ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+            ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rawflag, g, fp)));
         }
     } else {
-        ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+        ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rawflag, g, fp)));
     }
 }
 
 template <int N>
 static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
-                                 const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, FieldParams fp, int sm_count,
-                                 uint64_t max_level_items, cudaStream_t s) {
+                                 const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, FieldParams fp,
+                                 int sm_count, uint64_t max_level_items, cudaStream_t s) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels_coop<N>, 256, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
-                    (void*)&first_fail, (void*)&g, (void*)&fp};
+                    (void*)&first_fail, (void*)&rawflag, (void*)&g, (void*)&fp};
     // the grid barrier costs more the more CTAs take part: use only as many CTAs (a multiple of the SM count)
     // as the widest level can occupy
     uint64_t want = (max_level_items + 255) / 256;
@@ -485,10 +512,10 @@ static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const 
 }
 
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
-                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp,
-                               int sm_count, uint64_t max_level_items, cudaStream_t s) {
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g,
+                               const FieldParams& fp, int sm_count, uint64_t max_level_items, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
-    ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, g, fp, sm_count,
+    ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rawflag, g, fp, sm_count,
                                                 max_level_items, s)));
     return e;
 }
@@ -500,17 +527,17 @@ void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint
 }
 
 void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* const_bits, InputDesc in,
-                             TileGeom g, uint32_t* unreduced_count, cudaStream_t s) {
+                             TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags, cudaStream_t s) {
     if (n_loads == 0) return;
-    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 16);
-    k_bool_load_inputs<<<grid, 256, 0, s>>>(loads, n_loads, store, const_bits, in, g, unreduced_count);
+    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 256);
+    k_bool_load_inputs<<<grid, 256, 0, s>>>(loads, n_loads, store, const_bits, in, g, unreduced_count, rawflag, const_flags);
 }
 
 void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
-                       uint32_t* first_fail, TileGeom g, int sm_count, cudaStream_t s) {
+                       uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, int sm_count, cudaStream_t s) {
     if (n_ops == 0) return;
-    unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, 8);
-    k_bool_level<<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, g);
+    unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, grid_per_sm(256));
+    k_bool_level<<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g);
 }
 
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,

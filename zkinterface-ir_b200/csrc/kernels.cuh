@@ -32,22 +32,23 @@ struct InputDesc {
 // arithmetic fields (odd p, Montgomery form)
 void launch_to_mont(int nlimb, uint32_t* consts, uint32_t n, const FieldParams& fp, cudaStream_t s);
 void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* consts_mont,
-                        InputDesc in, TileGeom g, uint32_t* unreduced_count, const FieldParams& fp, cudaStream_t s);
+                        InputDesc in, TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags,
+                        const FieldParams& fp, cudaStream_t s);
 void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
-                  const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp, int sm_count,
-                  bool rare, cudaStream_t s);
+                  const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, const FieldParams& fp,
+                  int sm_count, bool rare, cudaStream_t s);
 // every wavefront in one cooperative launch (grid barrier between levels); for launch-bound programs
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
-                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, TileGeom g, const FieldParams& fp,
-                               int sm_count, uint64_t max_level_items, cudaStream_t s);
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g,
+                               const FieldParams& fp, int sm_count, uint64_t max_level_items, cudaStream_t s);
 void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                         uint32_t* out, const FieldParams& fp, cudaStream_t s);
 
 // p = 2: bit-sliced, one uint32 word = 32 witnesses
 void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* const_bits, InputDesc in,
-                             TileGeom g, uint32_t* unreduced_count, cudaStream_t s);
+                             TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags, cudaStream_t s);
 void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
-                       uint32_t* first_fail, TileGeom g, int sm_count, cudaStream_t s);
+                       uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, int sm_count, cudaStream_t s);
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                              uint32_t* out, cudaStream_t s);
 

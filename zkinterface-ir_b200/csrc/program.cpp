@@ -224,6 +224,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     for (int i = 0; i < D_OPS; i++) n_dev_ops[i] = 0;
     std::vector<uint32_t> meta_of(n_ops, 0);
     n_reused_slots = 0;
+    n_raw_ops = 0;
     for (uint32_t l = 0; l < n_levels; l++) {
         if (reuse) {  // wavefront l+1 may overwrite everything whose last reader ran in wavefront <= l
             auto& rel = release_after[l];
@@ -272,6 +273,10 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
         g.b = two ? slot_of_value[opb[v]] : opb[v];
         g.out = slot_of_value[v];
+        if (k == V_NOT && kind[opa[v]] <= V_WITNESS) {  // not(input): the reference tests the RAW integer
+            g.meta |= F_RAW;
+            n_raw_ops++;
+        }
         ops[i] = g;
         op_assert_seq[i] = aseq[v];
         n_dev_ops[g.meta & 0xff]++;
@@ -280,7 +285,8 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         uint64_t p = cnt[(size_t)0 * D_OPS + D_ASSERT];
         for (size_t i = 0; i < input_assert_seq.size(); i++, p++) {
             GateOp g;
-            g.meta = D_ASSERT | F_ASSERT | F_NOSTORE;
+            g.meta = D_ASSERT | F_ASSERT | F_NOSTORE | F_RAW;
+            n_raw_ops++;
             g.a = slot_of_value[input_assert_value[i]];
             g.b = 0;
             g.out = kNoSlot;

@@ -45,6 +45,7 @@ enum CbKind { CB_CONSTANT = 0, CB_INSTANCE, CB_WITNESS, CB_ADD, CB_MUL, CB_ADDC,
 enum DevOp : uint32_t { D_ADD = 0, D_MUL, D_ADDC, D_MULC, D_AND, D_XOR, D_NOT, D_ASSERT, D_OPS };
 constexpr uint32_t F_ASSERT = 1u << 8;    // result must be zero; assert seq in Plan::op_assert_seq
 constexpr uint32_t F_NOSTORE = 1u << 9;   // value is consumed by nothing but the fused assert
+constexpr uint32_t F_RAW = 1u << 10;      // operand a is an input value: consult its "raw value >= p" flag (trap 1)
 constexpr uint32_t kNoSeq = 0xFFFFFFFFu;
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 
@@ -131,6 +132,7 @@ struct Plan {
     std::vector<uint8_t> readable;        // value can be read back after the run (its slot is not re-used)
     bool slot_reuse = true;               // liveness-based slot re-use (off: one slot per stored value)
     uint64_t n_reused_slots = 0;
+    uint64_t n_raw_ops = 0;               // ops that need the raw-input flags (assert / not directly on an input)
     std::vector<GateOp> ops;              // level-major, opcode-sorted inside a level
     std::vector<uint32_t> op_assert_seq;  // parallel to ops
     std::vector<uint64_t> level_off;      // n_levels + 1 offsets into ops

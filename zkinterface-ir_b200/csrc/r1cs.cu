@@ -33,6 +33,7 @@ struct R1csDev {
     uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};
     uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
     uint32_t* d_cidx[3] = {nullptr, nullptr, nullptr};
+    uint32_t* d_row_order = nullptr;  // rows sorted by total term count (uniform trip counts inside a warp)
     uint32_t* d_coefs = nullptr;  // Montgomery form, nlimb limbs each
     uint32_t n_coefs = 0;
     uint32_t one_idx = 0xFFFFFFFFu;  // coefficient-table entry equal to 1 (multiplication skipped)
@@ -55,6 +56,7 @@ void r1cs_free(zkb_ctx* c) {
         cudaFree(r->d_col[m]);
         cudaFree(r->d_cidx[m]);
     }
+    cudaFree(r->d_row_order);
     cudaFree(r->d_coefs);
     cudaFree(r->d_z);
     cudaFree(r->d_zraw);
@@ -138,13 +140,15 @@ k_r1cs_check(const uint32_t* __restrict__ rpA, const uint32_t* __restrict__ colA
              const uint32_t* __restrict__ rpB, const uint32_t* __restrict__ colB, const uint32_t* __restrict__ ciB,
              const uint32_t* __restrict__ rpC, const uint32_t* __restrict__ colC, const uint32_t* __restrict__ ciC,
              const uint32_t* __restrict__ coefs, uint32_t one_idx, const uint32_t* __restrict__ z, uint64_t n_rows,
-             uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
+             const uint32_t* __restrict__ row_order, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
     const uint64_t total = n_rows << g.log2_wt;
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
     for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total; tid += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t lane = (uint32_t)tid & wt_mask;
-        const uint64_t row = tid >> g.log2_wt;
+        // rows are visited in order of decreasing term count, so the 32 rows of a warp (single-assignment mode)
+        // run the same number of gather/multiply iterations; the verdict still names the original row
+        const uint64_t row = __ldg(row_order + (tid >> g.log2_wt));
         uint32_t a[N], b[N], cc[N], ab[N];
         row_dot<N>(a, rpA, colA, ciA, coefs, one_idx, z, row, lane, g.log2_wt, fp);
         row_dot<N>(b, rpB, colB, ciB, coefs, one_idx, z, row, lane, g.log2_wt, fp);
@@ -209,6 +213,24 @@ extern "C" int zkb_r1cs_load(zkb_ctx* c, const zkb_csr* A, const zkb_csr* B, con
         CUDA_TRY(c, cudaMemcpy(r->d_rowptr[m], rp.data(), rp.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(c, cudaMemcpy(r->d_col[m], M[m]->col, nnz * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(c, cudaMemcpy(r->d_cidx[m], M[m]->coef_idx, nnz * 4, cudaMemcpyHostToDevice));
+    }
+    {   // row order: counting sort by total number of terms, heaviest first
+        const uint64_t nr = r->n_rows;
+        std::vector<uint32_t> terms(nr);
+        uint32_t max_terms = 0;
+        for (uint64_t i = 0; i < nr; i++) {
+            uint64_t t = 0;
+            for (int m = 0; m < 3; m++) t += M[m]->row_ptr[i + 1] - M[m]->row_ptr[i];
+            terms[i] = (uint32_t)std::min<uint64_t>(t, 4095);
+            max_terms = std::max(max_terms, terms[i]);
+        }
+        std::vector<uint64_t> start((size_t)max_terms + 2, 0);
+        for (uint64_t i = 0; i < nr; i++) start[max_terms - terms[i] + 1]++;
+        for (size_t k = 0; k + 1 < start.size(); k++) start[k + 1] += start[k];
+        std::vector<uint32_t> order(std::max<uint64_t>(nr, 1));
+        for (uint64_t i = 0; i < nr; i++) order[start[max_terms - terms[i]]++] = (uint32_t)i;
+        CUDA_TRY(c, cudaMalloc((void**)&r->d_row_order, order.size() * 4));
+        CUDA_TRY(c, cudaMemcpy(r->d_row_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
     }
     // coefficient table: reduce mod p on the host (empty coefficient = 0, from_r1cs.rs:72-77), Montgomery on device
     const int N = c->prog.nlimb;
@@ -309,14 +331,14 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
         g.batch0 = t << r->log2_wt;
         g.n_valid = std::min<uint32_t>(wt, r->n_batch - g.batch0);
         g.pad = 0;
-        unsigned grid = grid_for(r->n_vars << r->log2_wt, c->sm_count, 16);
+        unsigned grid = grid_for(r->n_vars << r->log2_wt, c->sm_count, 256);
         DISPATCH_N(N, (k_r1cs_load_z<N><<<grid, 256, 0, c->stream>>>(r->d_zraw, r->z_set_stride, r->stride, r->n_vars, r->d_z, g,
                                                                      c->d_unreduced, fp)));
         cudaEventRecord(c->tile_ev[2 * t], c->stream);
-        grid = grid_for(r->n_rows << r->log2_wt, c->sm_count, 8);
+        grid = grid_for(r->n_rows << r->log2_wt, c->sm_count, 256);
         DISPATCH_N(N, (k_r1cs_check<N><<<grid, 256, 0, c->stream>>>(r->d_rowptr[0], r->d_col[0], r->d_cidx[0], r->d_rowptr[1], r->d_col[1],
                                                                     r->d_cidx[1], r->d_rowptr[2], r->d_col[2], r->d_cidx[2], r->d_coefs,
-                                                                    r->one_idx, r->d_z, r->n_rows, r->d_first_fail, g, fp)));
+                                                                    r->one_idx, r->d_z, r->n_rows, r->d_row_order, r->d_first_fail, g, fp)));
         cudaEventRecord(c->tile_ev[2 * t + 1], c->stream);
         launches += 2;
     }
