@@ -83,3 +83,38 @@ def test_bitwise_gate_on_unreduced_input_is_refused_loudly():
             with pytest.raises(z.ZkbError) as err:
                 e.get_violations()
             assert err.value.code == z.ZKB_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("p,stride", [(101, 8), ((1 << 64) - (1 << 32) + 1, 20), (0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 48)])
+def test_witness_values_wider_than_the_field_element(p, stride):
+    """`Value`s are byte strings of any length; the reference reduces them at the first Add/Mul.  The input
+    kernel reduces arbitrarily wide raw values (Horner over element-sized chunks)."""
+    z = zkb()
+    h = ir.Header(ir.le_bytes(p))
+    rng = np.random.default_rng(9)
+    gates = [("Witness", 0), ("Witness", 1), ("Mul", 2, 0, 1), ("Add", 3, 2, 0), ("MulConstant", 4, 3, ir.le_bytes(p - 1)),
+             ("Add", 5, 4, 3), ("AssertZero", 5), ("AssertZero", 1)]
+    rel = ir.Relation(h, ir.ARITH, ir.SIMPLE, [], gates)
+    n = 12
+    W = rng.integers(0, 256, size=(n, 2, stride), dtype=np.uint8)
+    W[3, 1] = 0                      # raw zero: the direct assertion holds
+    W[5, 1, :] = np.frombuffer((p * 7).to_bytes(stride, "little"), dtype=np.uint8)   # 0 mod p but non-zero: fails
+    b = z.GpuBackend(0)
+    e = z.Evaluator(b)
+    e.ingest_source(z.Source.from_buffers([F.write_messages([ir.Witness(h, [W[0, 0].tobytes(), W[0, 1].tobytes()]), rel])]))
+    b.finalize(True)
+    e.get_violations()
+    v = b.evaluate(None, W, n)
+    for j in range(n):
+        msgs = [ir.Witness(h, [W[j, 0].tobytes(), W[j, 1].tobytes()]), rel]
+        tb = ev.TracingBackend()
+        o = ev.Evaluator.from_messages(msgs, tb)
+        want = o.get_violations()
+        got = [] if v[j]["ok"] else [f"Wire_{b.assert_wire(int(v[j]['first_fail_seq']))} (may be weighted) should be 0, while it is not"]
+        assert got == want, j
+        # computed values (reduced by the first gate) and the raw inputs themselves
+        vals = b.read_values(j, [2, 3, 4, 5], 64)
+        x, y = int.from_bytes(W[j, 0].tobytes(), "little"), int.from_bytes(W[j, 1].tobytes(), "little")
+        m = x * y % p
+        assert vals == [m, (m + x) % p, (m + x) * (p - 1) % p, 0]
+        assert b.read_values(j, [0, 1], 64) == [x, y]

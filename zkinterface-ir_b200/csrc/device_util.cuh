@@ -86,6 +86,67 @@ __device__ __forceinline__ void store_elem(uint32_t* store, uint32_t slot, uint3
 }
 
 // ---------------------------------------------------------------------------------------------
+// A raw little-endian value of `stride` bytes (any length: `Value`s are arbitrary byte strings,
+// rust/src/structs/value.rs:11) -> its residue in Montgomery form.  Wider than one element: Horner over
+// N-limb chunks, M <- M*R + chunk (in Montgomery form: mont_mul(M, R^2) + mont_mul(chunk, R^2)).
+// ge_p: the raw integer is >= p, i.e. the reference would hold it unreduced (evaluator.rs:862-864).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void load_raw_value(uint32_t* out, bool& ge_p, const uint8_t* src, uint32_t stride, const FieldParams& fp) {
+    uint32_t v[N];
+    if (stride == 4 * N && ((uintptr_t)src & 3) == 0) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = s32[k];
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            uint64_t t = (uint64_t)v[k] - fp.p[k] - borrow;
+            borrow = (uint32_t)(t >> 63);
+        }
+        ge_p = borrow == 0;
+        fe_mont_mul<N>(out, v, fp.r2, fp.p, fp.n0inv);  // also reduces v in [p, 2^(32N)) mod p
+        return;
+    }
+    const uint32_t n_chunks = (stride + 4 * N - 1) / (4 * N);
+    uint32_t acc[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) acc[k] = 0;
+    bool high_nonzero = false;
+    for (uint32_t c = n_chunks; c-- > 0;) {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = 0;
+        const uint32_t b0 = c * 4 * N;
+        for (uint32_t b = 0; b < 4 * N && b0 + b < stride; b++) v[b >> 2] |= (uint32_t)src[b0 + b] << (8 * (b & 3));
+        uint32_t m[N], t[N];
+        fe_mont_mul<N>(m, v, fp.r2, fp.p, fp.n0inv);
+        if (c + 1 < n_chunks) {
+            fe_mont_mul<N>(t, acc, fp.r2, fp.p, fp.n0inv);
+            fe_add<N>(acc, t, m, fp.p);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; k++) acc[k] = m[k];
+        }
+        if (c > 0) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) any |= v[k];
+            high_nonzero = high_nonzero || any != 0;
+        } else {
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                uint64_t t2 = (uint64_t)v[k] - fp.p[k] - borrow;
+                borrow = (uint32_t)(t2 >> 63);
+            }
+            ge_p = high_nonzero || borrow == 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) out[k] = acc[k];
+}
+
+// ---------------------------------------------------------------------------------------------
 // AssertZero reporting: first failing assertion (program order) per witness.
 // Failures are found with one warp ballot; only failing lanes touch memory.  When all lanes of a
 // warp belong to the same witness (single-witness, gate-parallel tiles) the warp first reduces its

@@ -67,35 +67,8 @@ k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* _
                                          ? in.inst + (uint64_t)(g.batch0 + lane) * in.inst_set_stride
                                          : in.wit + (uint64_t)(g.batch0 + lane) * in.wit_set_stride;
                 src += (uint64_t)ld.index * in.stride;
-                bool wide = false;
-                if (in.stride == 4 * N && ((uintptr_t)src & 3) == 0) {
-                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-#pragma unroll
-                    for (int k = 0; k < N; k++) v[k] = s32[k];
-                } else {
-                    for (uint32_t b = 0; b < in.stride; b++) {
-                        uint32_t byte = src[b];
-                        if (b < 4 * N) v[b >> 2] |= byte << (8 * (b & 3));
-                        else if (byte) wide = true;
-                    }
-                }
-                // raw value >= p (or wider than the element): the reference keeps it unreduced
-                // (evaluator.rs:862-864, 896-898); the host resolves raw semantics, see backend.cu
-                uint32_t d[N];
-                uint32_t borrow = 0;
-#pragma unroll
-                for (int k = 0; k < N; k++) {
-                    uint64_t t = (uint64_t)v[k] - fp.p[k] - borrow;
-                    d[k] = (uint32_t)t;
-                    borrow = (uint32_t)(t >> 63);
-                }
-                (void)d;
-                raw_ge_p = wide || borrow == 0;
+                load_raw_value<N>(v, raw_ge_p, src, in.stride, fp);
                 if (raw_ge_p) atomicAdd(unreduced_count, 1u);
-                uint32_t m[N];
-                fe_mont_mul<N>(m, v, fp.r2, fp.p, fp.n0inv);  // also reduces v in [p, 2^(32N)) mod p
-#pragma unroll
-                for (int k = 0; k < N; k++) v[k] = m[k];
             }
         }
         store_elem<N>(store, ld.slot, lane, g.log2_wt, v);

@@ -80,29 +80,9 @@ k_r1cs_load_z(const uint8_t* __restrict__ zraw, uint64_t set_stride, uint32_t st
         for (int k = 0; k < N; k++) v[k] = 0;
         if (lane < g.n_valid) {
             const uint8_t* src = zraw + (uint64_t)(g.batch0 + lane) * set_stride + var * stride;
-            bool wide = false;
-            if (stride == 4 * N && ((uintptr_t)src & 3) == 0) {
-                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-#pragma unroll
-                for (int k = 0; k < N; k++) v[k] = s32[k];
-            } else {
-                for (uint32_t b = 0; b < stride; b++) {
-                    uint32_t byte = src[b];
-                    if (b < 4 * N) v[b >> 2] |= byte << (8 * (b & 3));
-                    else if (byte) wide = true;
-                }
-            }
-            uint32_t borrow = 0;
-#pragma unroll
-            for (int k = 0; k < N; k++) {
-                uint64_t t = (uint64_t)v[k] - fp.p[k] - borrow;
-                borrow = (uint32_t)(t >> 63);
-            }
-            if (wide || borrow == 0) atomicAdd(unreduced_count, 1u);
-            uint32_t m[N];
-            fe_mont_mul<N>(m, v, fp.r2, fp.p, fp.n0inv);
-#pragma unroll
-            for (int k = 0; k < N; k++) v[k] = m[k];
+            bool ge_p = false;
+            load_raw_value<N>(v, ge_p, src, stride, fp);
+            if (ge_p) atomicAdd(unreduced_count, 1u);
         }
         store_elem<N>(z, (uint32_t)var, lane, g.log2_wt, v);
     }
