@@ -48,7 +48,7 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
     const bool keep_all = keep_values == 1;
     // a bitwise gate on a constant >= p would need the unreduced integer (evaluator.rs:924-930): refuse up front
-    for (uint32_t v = 0; v < c->prog.n_values(); v++) {
+    for (uint32_t v = 0; v < c->prog.n_values() && !c->prog.binary; v++) {
         uint8_t k = c->prog.kind[v];
         if (k != V_AND && k != V_XOR) continue;
         for (uint32_t o : {c->prog.opa[v], c->prog.opb[v]})
@@ -528,6 +528,7 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
 // is.  What the device cannot reproduce is a bitwise gate on the unreduced integer itself: refused loudly.
 static int check_unreduced_supported(zkb_ctx* c) {
     const Program& p = c->prog;
+    if (p.binary) return ZKB_OK;  // mod 2 the bitwise gates only see the low bit: residues are exact
     for (uint32_t v = 0; v < p.n_values(); v++) {
         uint8_t k = p.kind[v];
         if (k == V_AND || k == V_XOR) {
