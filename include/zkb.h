@@ -52,6 +52,12 @@ typedef uint64_t zkb_wire;
 zkb_ctx* zkb_create(int device);
 void zkb_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(zkb_ctx* ctx);
+/* Resource limits of the host pass (0 keeps the current value).  The reference unrolls whatever the statement
+ * says until the host runs out of memory; here a For over 2^60 iterations or a 2^32-wire range in a malformed /
+ * hostile message ends in "zkb: resource limit exceeded (...)" (a latched evaluation error).
+ *   max_values : SSA values recorded (default and maximum 2^32 - 256, handles are 32-bit)
+ *   max_steps  : gates ingested + loop iterations + wires expanded by the Evaluator mirror (default 2^40) */
+int zkb_set_limits(zkb_ctx* ctx, uint64_t max_values, uint64_t max_steps);
 
 /* ------------------------------------------------------------------ 2. ZKBackend seam
  * One function per method of `trait ZKBackend` (evaluator.rs:17-76).  The backend is

@@ -242,7 +242,9 @@ def test_reader_survives_corrupted_buffers():
         for _ in range(int(rng.integers(1, 6))):
             pos = int(rng.integers(4, len(buf)))
             buf[pos] = int(rng.integers(0, 256))
-        e = z.Evaluator(z.GpuBackend(-1))
+        b = z.GpuBackend(-1)
+        b.set_limits(max_values=1 << 20, max_steps=1 << 22)  # a corrupted For bound must not unroll for ever
+        e = z.Evaluator(b)
         # the witness the (possibly still valid) relation needs
         e.ingest_message(F.write_message(fx.example_instance()))
         e.ingest_message(F.write_message(fx.example_witness()))
@@ -258,3 +260,28 @@ def test_reader_survives_corrupted_buffers():
         e = z.Evaluator(z.GpuBackend(-1))
         with pytest.raises(z.ZkbError):
             e.ingest_message(bytes(base[:cut]))
+
+
+def test_resource_limits_stop_hostile_loops():
+    """zkb_set_limits: a For over 2^60 iterations / a 2^31-wire range ends in a latched error, not in an exhausted host"""
+    z = zkb()
+    h = fx.example_header()
+    loop = ("For", "i", 0, (1 << 60), [], ("IterExprAnonCall", [], [], 0, 0, []))
+    wide = ("AnonCall", [ir.WireRange(0, 1 << 31)], [], 0, 0, [])
+    for gate, limits in [(loop, dict(max_steps=1 << 16)), (wide, dict(max_steps=1 << 16))]:
+        rel = ir.Relation(h, ir.ARITH, ir.FOR_FUNCTION_SWITCH, [], [gate])
+        b = z.GpuBackend(-1)
+        b.set_limits(**limits)
+        e = z.Evaluator(b)
+        e.ingest_source(z.Source.from_buffers([F.write_messages([rel])]))
+        assert b.pending_error() == "zkb: resource limit exceeded (max_steps)"
+    body = [("Constant", 0, b"\x01")]
+    loop = ("For", "i", 0, 999, [ir.WireRange(0, 999)], ("IterExprAnonCall", [("Single", ("Name", "i"))], [], 0, 0, body))
+    rel = ir.Relation(h, ir.ARITH, ir.FOR_FUNCTION_SWITCH, [], [loop])
+    b = z.GpuBackend(-1)
+    b.set_limits(max_values=100)
+    e = z.Evaluator(b)
+    e.ingest_source(z.Source.from_buffers([F.write_messages([rel])]))
+    assert b.pending_error() == "zkb: resource limit exceeded (max_values)"
+    with pytest.raises(z.ZkbError):
+        b.set_limits(max_values=1 << 33)

@@ -65,7 +65,7 @@ CALLBACK_NAMES = ["constant", "instance", "witness", "add", "mul", "addc", "mulc
 
 # every symbol include/zkb.h declares (tests check the library exports all of them)
 EXPORTED = [
-    "zkb_create", "zkb_destroy", "zkb_last_error", "zkb_set_field", "zkb_one", "zkb_minus_one", "zkb_zero", "zkb_copy",
+    "zkb_create", "zkb_destroy", "zkb_last_error", "zkb_set_limits", "zkb_set_field", "zkb_one", "zkb_minus_one", "zkb_zero", "zkb_copy",
     "zkb_constant", "zkb_assert_zero", "zkb_add", "zkb_multiply", "zkb_add_constant", "zkb_mul_constant", "zkb_and",
     "zkb_xor", "zkb_not", "zkb_instance", "zkb_witness", "zkb_push_gates", "zkb_finalize", "zkb_evaluate",
     "zkb_upload_inputs", "zkb_run", "zkb_assert_info", "zkb_pending_error", "zkb_read_values", "zkb_scope_lookup",
@@ -90,6 +90,7 @@ _sig("zkb_create", _vp, _i)
 _sig("zkb_destroy", None, _vp)
 _sig("zkb_last_error", C.c_char_p, _vp)
 _sig("zkb_pending_error", C.c_char_p, _vp)
+_sig("zkb_set_limits", _i, _vp, _u64, _u64)
 _sig("zkb_set_field", _i, _vp, _u8p, _sz, _u32, _i)
 for _n in ("zkb_one", "zkb_minus_one", "zkb_zero"):
     _sig(_n, _i, _vp, _u8p, _sz, C.POINTER(C.c_size_t))
@@ -199,6 +200,10 @@ class GpuBackend:
     @staticmethod
     def from_bytes_le(val: bytes) -> bytes:
         return bytes(val)
+
+    def set_limits(self, max_values: int = 0, max_steps: int = 0):
+        """resource limits of the host pass (0 keeps the current value), zkb.h section 1"""
+        self._chk(_lib.zkb_set_limits(self._c, max_values, max_steps))
 
     def set_field(self, modulus, degree: int = 1, is_boolean: bool = False):
         m = _le(modulus)

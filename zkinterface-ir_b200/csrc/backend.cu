@@ -174,7 +174,7 @@ extern "C" int zkb_minus_one(zkb_ctx* c, uint8_t* out, size_t cap, size_t* len) 
 #define REC_PROLOGUE(c)                                                                         \
     if (!(c)->prog.field_set) return (c)->fail(ZKB_E_ARG, "set_field must be called before recording"); \
     if ((c)->finalized) return (c)->fail(ZKB_E_ARG, "program already finalized");               \
-    if ((c)->prog.n_values() >= 0xFFFFFFF0u) return (c)->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 values")
+    if ((c)->prog.n_values() >= (c)->max_values) return (c)->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)")
 #define CHECK_WIRE(c, w) \
     if ((w) >= (c)->prog.n_values()) return (c)->fail(ZKB_E_ARG, "unknown wire handle")
 
@@ -264,7 +264,7 @@ extern "C" int zkb_push_gates(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gate
     p.opb.reserve(p.opb.size() + n_gates);
     for (uint64_t i = 0; i < n_gates; i++) {
         const zkb_gate& g = gates[i];
-        if (p.n_values() >= 0xFFFFFFF0u) return c->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 values");
+        if (p.n_values() >= c->max_values) return c->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)");
         uint32_t va = 0, vb = 0, res = 0;
         switch (g.op) {
             case ZKB_G_CONSTANT:
@@ -669,6 +669,13 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
         if (nb > stride) return c->fail(ZKB_E_ARG, "output stride too small for the value");
         memcpy(dst, src, nb);
     }
+    return ZKB_OK;
+}
+
+extern "C" int zkb_set_limits(zkb_ctx* c, uint64_t max_values, uint64_t max_steps) {
+    if (max_values > 0xFFFFFF00ull) return c->fail(ZKB_E_ARG, "max_values above the 32-bit handle space");
+    if (max_values) c->max_values = max_values;
+    if (max_steps) c->max_steps = max_steps;
     return ZKB_OK;
 }
 

@@ -90,6 +90,10 @@ struct zkb_ctx {
     std::vector<uint32_t> live_values;  // observable values supplied by the Evaluator at finalize
     bool has_pending = false;
     std::string pending_error;       // first recording error (latched)
+    // resource limits of the host pass (zkb_set_limits): a malformed or hostile statement (a For over 2^60
+    // iterations, a 2^32-wire range) must end in an error, not in an exhausted host
+    uint64_t max_values = 0xFFFFFF00ull;  // SSA values (handles are 32-bit)
+    uint64_t max_steps = 1ull << 40;      // gates ingested + loop iterations + wires expanded
 
     // device state
     cudaStream_t stream = nullptr;

@@ -68,6 +68,13 @@ struct zkb_evaluator {
 
     Program& prog() { return c->prog; }
 
+    // work accounting against zkb_set_limits (not in the reference, which would run until memory is exhausted)
+    uint64_t steps = 0;
+    void step(uint64_t n = 1) {
+        steps += n;
+        if (steps > c->max_steps || steps < n) throw EvalErr{"zkb: resource limit exceeded (max_steps)"};
+    }
+
     Scope* new_scope() {
         if (scope_pool.empty()) return new Scope();
         Scope* s = scope_pool.back();
@@ -93,7 +100,7 @@ struct zkb_evaluator {
     }
 
     // ---- structs/wire.rs:179-203 ---------------------------------------------------------------
-    static void expand_wirelist(const ir::WireList& wl, std::vector<uint64_t>& out) {
+    void expand_wirelist(const ir::WireList& wl, std::vector<uint64_t>& out) {
         out.clear();
         for (const auto& e : wl) {
             if (!e.is_range) {
@@ -103,6 +110,7 @@ struct zkb_evaluator {
                     throw EvalErr{"In WireRange, last WireId (" + u64s(e.last) + ") must be strictly greater than first WireId (" +
                                   u64s(e.first) + ")."};
                 if (e.last - e.first > (1ull << 32)) throw EvalErr{"zkb: wire range too large"};
+                step(e.last - e.first);
                 for (uint64_t w = e.first; w <= e.last; w++) out.push_back(w);
             }
         }
@@ -126,7 +134,7 @@ struct zkb_evaluator {
         }
         throw Fatal{"Unknown Iterator Expression type"};
     }
-    static void eval_iterexpr_list(const ir::IterExprList& l, const Iters& known, std::vector<uint64_t>& out) {
+    void eval_iterexpr_list(const ir::IterExprList& l, const Iters& known, std::vector<uint64_t>& out) {
         out.clear();
         for (const auto& el : l) {
             uint64_t a = eval_iterexpr(el.first, known);
@@ -135,6 +143,7 @@ struct zkb_evaluator {
             } else {
                 uint64_t b = eval_iterexpr(el.last, known);
                 if (b >= a && b - a > (1ull << 32)) throw EvalErr{"zkb: iterator range too large"};
+                if (b >= a) step(b - a);
                 for (uint64_t w = a; w <= b && b >= a; w++) {
                     out.push_back(w);
                     if (w == UINT64_MAX) break;
@@ -223,7 +232,8 @@ struct zkb_evaluator {
     void ingest_gate(const ir::Gate& g, const std::vector<std::vector<uint8_t>>& consts, Scope& scope, Iters& iters,
                      Queue& instances, Queue& witnesses, const uint32_t* weight) {
         Program& p = prog();
-        if (p.n_values() >= 0xFFFFFF00u) throw EvalErr{"zkb: more than 2^32 values"};
+        if (p.n_values() >= c->max_values) throw EvalErr{"zkb: resource limit exceeded (max_values)"};
+        step();
         switch (g.type) {
             case ir::G_CONSTANT: {  // :345-348
                 const auto& v = consts[g.const_idx];
@@ -275,6 +285,7 @@ struct zkb_evaluator {
             } break;
             case ir::G_FREE: {  // :434-439
                 uint64_t last = g.has_last ? g.w1 : g.w0;
+                if (last > g.w0) step(last - g.w0);
                 for (uint64_t w = g.w0; w <= last; w++) {
                     remove(scope, w);
                     if (w == UINT64_MAX) break;
@@ -303,6 +314,7 @@ struct zkb_evaluator {
                 const ir::Complex& cx = *g.cx;
                 std::vector<uint64_t> eo, ei;
                 for (uint64_t i = cx.first; i <= cx.last; i++) {
+                    step();
                     iters_set(iters, cx.name, i);
                     if (!cx.body_is_anon) {
                         auto it = known_functions.find(cx.fn_name);
