@@ -262,6 +262,10 @@ int zkb_r1cs_run(zkb_ctx* ctx, zkb_verdict* out);
  * field_throughput: register-resident dependent chains of `iters` operations per thread -> operations/s. */
 int zkb_debug_field_ops(zkb_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint64_t n);
 int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops_per_second);
+/* Device layout zkb_r1cs_load built (host-only contexts): counts = {slices, term groups, rows}; slices: 4 x uint32 per slice
+ * {first group, KA, KB, KC}; terms: 32 x {col, coefficient tag} per group (tag 0xFFFFFFFF: padding / zero coefficient,
+ * 0xFFFFFFFE: coefficient one, else the table index); row_ids: sorted position -> row.  NULL pointers are skipped. */
+int zkb_debug_r1cs_layout(zkb_ctx* ctx, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ EXPORTED = [
     "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_level_info", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
     "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
     "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
-    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput",
+    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout",
 ]
 
 _vp, _u8p, _sz, _u64, _u32, _i = C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
@@ -134,6 +134,7 @@ _sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
 _sig("zkb_r1cs_run", _i, _vp, _vp)
 _sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
 _sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
+_sig("zkb_debug_r1cs_layout", _i, _vp, _u64p, _vp, _vp, _vp)
 
 
 class ZkbError(Exception):
@@ -403,6 +404,16 @@ class GpuBackend:
         coef_table = np.ascontiguousarray(coef_table, dtype=np.uint8)
         self._chk(_lib.zkb_r1cs_load(self._c, C.byref(a), C.byref(b), C.byref(c), _buf(coef_table),
                                      coef_table.shape[1], coef_table.shape[0], n_vars))
+
+    def r1cs_layout(self):
+        """(slices uint32[n,4], terms uint32[groups,32,2], row_ids uint32[rows]) of a host-only context"""
+        cnt = (C.c_uint64 * 3)()
+        self._chk(_lib.zkb_debug_r1cs_layout(self._c, cnt, None, None, None))
+        slices = np.zeros((cnt[0], 4), dtype=np.uint32)
+        terms = np.zeros((cnt[1], 32, 2), dtype=np.uint32)
+        rows = np.zeros(cnt[2], dtype=np.uint32)
+        self._chk(_lib.zkb_debug_r1cs_layout(self._c, cnt, slices.ctypes.data, terms.ctypes.data, rows.ctypes.data))
+        return slices, terms, rows
 
     def r1cs_check(self, z: np.ndarray) -> np.ndarray:
         """z: uint8 [n_batch, n_vars, stride]"""

@@ -45,7 +45,7 @@ ZKB_HD bool fe_is_zero(const uint32_t* a) {
 
 // r = a - p if (carry || a >= p) else a.   a has an extra carry bit `carry`.
 template <int N>
-ZKB_HD void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
+ZKB_HD void fe_cond_sub_p_portable(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
     uint32_t d[N];
     uint32_t borrow = 0;
 #pragma unroll
@@ -61,7 +61,7 @@ ZKB_HD void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const 
 
 // r = (a + b) mod p, inputs in [0, p)
 template <int N>
-ZKB_HD void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p) {
+ZKB_HD void fe_add_portable(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p) {
     uint32_t s[N];
     uint64_t c = 0;
 #pragma unroll
@@ -70,7 +70,7 @@ ZKB_HD void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint
         s[i] = (uint32_t)c;
         c >>= 32;
     }
-    fe_cond_sub_p<N>(r, s, (uint32_t)c, p);
+    fe_cond_sub_p_portable<N>(r, s, (uint32_t)c, p);
 }
 
 // Montgomery product r = a*b/R mod p (CIOS).  a*b < p*R is enough (so one operand
@@ -106,15 +106,27 @@ ZKB_HD void fe_mont_mul_portable(uint32_t* r, const uint32_t* a, const uint32_t*
         t[N - 1] = (uint32_t)c;
         t[N] = t[N + 1] + (uint32_t)(c >> 32);
     }
-    fe_cond_sub_p<N>(r, t, t[N], p);
+    fe_cond_sub_p_portable<N>(r, t, t[N], p);
 }
 
-// the device pass gets fe_mont_mul from field_ptx.cuh (PTX carry chains); host code and -DZKB_NO_PTX_FIELD use the portable one
+// the device pass gets fe_mont_mul / fe_add / fe_cond_sub_p from field_ptx.cuh (PTX carry chains); host code and
+// -DZKB_NO_PTX_FIELD use the portable ones
 #if !(defined(__CUDA_ARCH__) && !defined(ZKB_NO_PTX_FIELD))
 template <int N>
 ZKB_HD void fe_mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t n0inv) {
     fe_mont_mul_portable<N>(r, a, b, p, n0inv);
 }
+template <int N>
+ZKB_HD void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p) {
+    fe_add_portable<N>(r, a, b, p);
+}
+template <int N>
+ZKB_HD void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
+    fe_cond_sub_p_portable<N>(r, a, carry, p);
+}
+#else
+template <int N>
+__device__ __forceinline__ void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p);
 #endif
 
 // Bitwise gates on canonical (non-Montgomery) residues, as PlaintextBackend::and / ::xor

@@ -106,6 +106,91 @@ __device__ __forceinline__ uint32_t mad_chain2_fold(uint32_t& e0, uint32_t f0, u
     return c;
 }
 
+// ---- additions / conditional subtraction as single carry chains -------------------------------------
+// d = (carry:a) - p over N+1 limbs; the top limb is 0 when the difference is non-negative (then r = d), all ones otherwise
+__device__ __forceinline__ void cond_sub_chain8(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
+    uint32_t d[8], top;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, %25, 0;"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(top)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(p[0]), "r"(p[1]), "r"(p[2]),
+          "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(carry));
+    const bool use_d = top == 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = use_d ? d[i] : a[i];
+}
+__device__ __forceinline__ void cond_sub_chain4(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
+    uint32_t d[4], top;
+    asm("sub.cc.u32 %0, %5, %9;\n\t"
+        "subc.cc.u32 %1, %6, %10;\n\t"
+        "subc.cc.u32 %2, %7, %11;\n\t"
+        "subc.cc.u32 %3, %8, %12;\n\t"
+        "subc.u32 %4, %13, 0;"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(top)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(carry));
+    const bool use_d = top == 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r[i] = use_d ? d[i] : a[i];
+}
+// s = a + b, returns the carry out
+__device__ __forceinline__ uint32_t add_chain8(uint32_t* s, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]),
+          "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+}
+__device__ __forceinline__ uint32_t add_chain4(uint32_t* s, const uint32_t* a, const uint32_t* b) {
+    uint32_t c;
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    return c;
+}
+
+template <int N>
+__device__ __forceinline__ void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
+    if constexpr (N == 8) cond_sub_chain8(r, a, carry, p);
+    else if constexpr (N == 4) cond_sub_chain4(r, a, carry, p);
+    else fe_cond_sub_p_portable<N>(r, a, carry, p);
+}
+
+// r = (a + b) mod p, inputs in [0, p)
+template <int N>
+__device__ __forceinline__ void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p) {
+    if constexpr (N == 8) {
+        uint32_t s[8];
+        uint32_t c = add_chain8(s, a, b);
+        cond_sub_chain8(r, s, c, p);
+    } else if constexpr (N == 4) {
+        uint32_t s[4];
+        uint32_t c = add_chain4(s, a, b);
+        cond_sub_chain4(r, s, c, p);
+    } else {
+        fe_add_portable<N>(r, a, b, p);
+    }
+}
+
 template <int N>
 struct PtxChains;
 template <>
@@ -160,19 +245,13 @@ __device__ __forceinline__ void fe_mont_mul_chain(uint32_t* r, const uint32_t* a
         }
     }
     // final shift + merge of the two accumulators: limb j = E[j+1] + O[j], limb N-1 = cE + O[N-1], top = cO
-    uint32_t t[N];
-    uint64_t c = (uint64_t)E[1] + O[0];
-    t[0] = (uint32_t)c;
-    c >>= 32;
+    uint32_t t[N], up[N];
 #pragma unroll
-    for (int j = 1; j < N - 1; j++) {
-        c += (uint64_t)E[j + 1] + O[j];
-        t[j] = (uint32_t)c;
-        c >>= 32;
-    }
-    c += (uint64_t)cE + O[N - 1];
-    t[N - 1] = (uint32_t)c;
-    uint32_t top = (uint32_t)(c >> 32) + cO;
+    for (int j = 0; j < N - 1; j++) up[j] = E[j + 1];
+    up[N - 1] = cE;
+    uint32_t top;
+    if constexpr (N == 8) top = add_chain8(t, up, O) + cO;
+    else top = add_chain4(t, up, O) + cO;
     fe_cond_sub_p<N>(r, t, top, p);
 }
 

@@ -28,16 +28,28 @@ using namespace zkb;
 
 namespace zkb {
 
+// Device layout of the three matrices: SELL-32-sigma (sliced ELLPACK).  Rows are sorted by (|A_r|, |B_r|, |C_r|),
+// heaviest first, inside windows of `sigma` consecutive rows (locality of the variables a window touches is kept,
+// e.g. the slack variables of neighbouring rows stay in the same L2-resident region) and cut into slices of 32
+// sorted rows.  A slice stores KA + KB + KC term groups (K* = the slice's largest LC of that matrix); a group is
+// 32 x {col, coef} with the row of the slice as the fast index, so
+//   - with ONE assignment a warp works on the 32 rows of a slice: every group is one coalesced 256-byte load
+//     and all lanes run the same trip counts;
+//   - with a batch of assignments a warp works on one row for 32 assignments: the term is a broadcast load and
+//     the z gathers are coalesced 512-byte rows.
+// Rows shorter than their slice are padded with {0, T_PAD}.
+constexpr uint32_t T_PAD = 0xFFFFFFFFu;  // no term
+constexpr uint32_t T_ONE = 0xFFFFFFFEu;  // coefficient 1: the multiplication is skipped
+
 struct R1csDev {
     uint64_t n_rows = 0, n_vars = 0, nnz[3] = {0, 0, 0};
-    uint32_t* d_rowptr[3] = {nullptr, nullptr, nullptr};
-    uint32_t* d_col[3] = {nullptr, nullptr, nullptr};
-    uint32_t* d_cidx[3] = {nullptr, nullptr, nullptr};
-    uint32_t* d_row_order = nullptr;  // rows sorted by total term count (uniform trip counts inside a warp)
-    uint32_t* d_coefs = nullptr;  // Montgomery form, nlimb limbs each
+    uint64_t n_slices = 0, n_groups = 0;
+    uint4* d_slices = nullptr;     // {first group, KA, KB, KC}
+    uint2* d_terms = nullptr;      // [group][32] {col, coefficient index | T_ONE | T_PAD}
+    uint32_t* d_row_ids = nullptr; // sorted position -> original row (the verdict names the original row)
+    uint32_t* d_coefs = nullptr;   // Montgomery form, nlimb limbs each
     uint32_t n_coefs = 0;
-    uint32_t one_idx = 0xFFFFFFFFu;  // coefficient-table entry equal to 1 (multiplication skipped)
-    uint32_t* d_z = nullptr;         // [var][chunk][lane][CW] Montgomery
+    uint32_t* d_z = nullptr;       // [var][chunk][lane][CW] Montgomery
     size_t z_bytes = 0;
     uint8_t* d_zraw = nullptr;
     size_t zraw_bytes = 0;
@@ -46,17 +58,18 @@ struct R1csDev {
     uint32_t* d_first_fail = nullptr;
     size_t first_fail_cap = 0;
     bool uploaded = false;
+    // host copies of the layout (inspection: zkb_debug_r1cs_layout)
+    std::vector<uint4> h_slices;
+    std::vector<uint2> h_terms;
+    std::vector<uint32_t> h_row_ids;
 };
 
 void r1cs_free(zkb_ctx* c) {
     R1csDev* r = c->r1cs;
     if (!r) return;
-    for (int m = 0; m < 3; m++) {
-        cudaFree(r->d_rowptr[m]);
-        cudaFree(r->d_col[m]);
-        cudaFree(r->d_cidx[m]);
-    }
-    cudaFree(r->d_row_order);
+    cudaFree(r->d_slices);
+    cudaFree(r->d_terms);
+    cudaFree(r->d_row_ids);
     cudaFree(r->d_coefs);
     cudaFree(r->d_z);
     cudaFree(r->d_zraw);
@@ -88,57 +101,106 @@ k_r1cs_load_z(const uint8_t* __restrict__ zraw, uint64_t set_stride, uint32_t st
     }
 }
 
-// one sparse row . z  (Montgomery residues)
 template <int N>
-__device__ __forceinline__ void row_dot(uint32_t* acc, const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col,
-                                        const uint32_t* __restrict__ cidx, const uint32_t* __restrict__ coefs, uint32_t one_idx,
-                                        const uint32_t* __restrict__ z, uint64_t row, uint32_t lane, uint32_t log2_wt,
-                                        const FieldParams& fp) {
+__device__ __forceinline__ void prefetch_elem_l2(const uint32_t* z, uint32_t var, uint32_t lane, uint32_t log2_wt) {
 #pragma unroll
-    for (int k = 0; k < N; k++) acc[k] = 0;
-    const uint32_t lo = __ldg(rowptr + row), hi = __ldg(rowptr + row + 1);
-    for (uint32_t e = lo; e < hi; e++) {
-        const uint32_t var = __ldg(col + e), ci = __ldg(cidx + e);
-        uint32_t zv[N], t[N];
-        load_elem<N>(zv, z, var, lane, log2_wt);
-        if (ci != one_idx) {
-            uint32_t cf[N];
-#pragma unroll
-            for (int k = 0; k < N; k++) cf[k] = __ldg(coefs + (size_t)ci * N + k);
-            fe_mont_mul<N>(t, zv, cf, fp.p, fp.n0inv);
-        } else {
-#pragma unroll
-            for (int k = 0; k < N; k++) t[k] = zv[k];
-        }
-        fe_add<N>(acc, acc, t, fp.p);
+    for (int c = 0; c < Elem<N>::NC; c++) {
+        const uint32_t* p = z + ((((size_t)var * Elem<N>::NC + c) << log2_wt) + lane) * Elem<N>::CW;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
 }
 
+// The term stream of one (row, assignment lane): terms are consumed in order A_r, B_r, C_r.  Four terms are in
+// flight per thread: the {col, coef} pair three terms ahead, an L2 prefetch of z two terms ahead, and the z limbs
+// of the next term in registers while the current term's integer chain runs.
 template <int N>
-__global__ void __launch_bounds__(256)
-k_r1cs_check(const uint32_t* __restrict__ rpA, const uint32_t* __restrict__ colA, const uint32_t* __restrict__ ciA,
-             const uint32_t* __restrict__ rpB, const uint32_t* __restrict__ colB, const uint32_t* __restrict__ ciB,
-             const uint32_t* __restrict__ rpC, const uint32_t* __restrict__ colC, const uint32_t* __restrict__ ciC,
-             const uint32_t* __restrict__ coefs, uint32_t one_idx, const uint32_t* __restrict__ z, uint64_t n_rows,
-             const uint32_t* __restrict__ row_order, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
-    const uint64_t total = n_rows << g.log2_wt;
+struct TermStream {
+    const uint2* tp;  // this row's column of the slice: term k at tp[32 * k]
+    const uint32_t* z;
+    uint32_t lane, log2_wt, k, K;
+    uint2 t0, t1, t2;
+    uint32_t z0[N], z1[N];
+
+    __device__ __forceinline__ uint2 fetch(uint32_t i) const { return i < K ? __ldg(tp + (size_t)32 * i) : make_uint2(0, T_PAD); }
+    __device__ __forceinline__ void start(const uint2* tp_, const uint32_t* z_, uint32_t lane_, uint32_t log2_wt_, uint32_t K_) {
+        tp = tp_; z = z_; lane = lane_; log2_wt = log2_wt_; k = 0; K = K_;
+        t0 = fetch(0);
+        t1 = fetch(1);
+        t2 = fetch(2);
+#pragma unroll
+        for (int i = 0; i < N; i++) z0[i] = 0;
+        if (t0.y != T_PAD) load_elem<N>(z0, z, t0.x, lane, log2_wt);
+        if (t1.y != T_PAD) prefetch_elem_l2<N>(z, t1.x, lane, log2_wt);
+    }
+    // issue the loads of the following terms; call before the current term's arithmetic
+    __device__ __forceinline__ void prefetch(uint2& t3) {
+        t3 = fetch(k + 3);
+        if (t2.y != T_PAD) prefetch_elem_l2<N>(z, t2.x, lane, log2_wt);
+#pragma unroll
+        for (int i = 0; i < N; i++) z1[i] = 0;
+        if (t1.y != T_PAD) load_elem<N>(z1, z, t1.x, lane, log2_wt);
+    }
+    __device__ __forceinline__ void advance(const uint2& t3) {
+#pragma unroll
+        for (int i = 0; i < N; i++) z0[i] = z1[i];
+        t0 = t1; t1 = t2; t2 = t3;
+        k++;
+    }
+};
+
+// acc = sum of the next `n` terms of the stream (Montgomery residues)
+template <int N>
+__device__ __forceinline__ void lc_dot(uint32_t* acc, TermStream<N>& st, uint32_t n, const uint32_t* __restrict__ coefs,
+                                       const FieldParams& fp) {
+#pragma unroll
+    for (int i = 0; i < N; i++) acc[i] = 0;
+    for (uint32_t j = 0; j < n; j++) {
+        uint2 t3;
+        st.prefetch(t3);
+        const uint32_t ci = st.t0.y;
+        if (ci != T_PAD) {
+            uint32_t t[N];
+            if (ci != T_ONE) {
+                uint32_t cf[N];
+#pragma unroll
+                for (int i = 0; i < N; i++) cf[i] = __ldg(coefs + (size_t)ci * N + i);
+                fe_mont_mul<N>(t, st.z0, cf, fp.p, fp.n0inv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) t[i] = st.z0[i];
+            }
+            fe_add<N>(acc, acc, t, fp.p);
+        }
+        st.advance(t3);
+    }
+}
+
+// thread <-> (sorted row, assignment lane), lane fastest
+template <int N>
+__global__ void __launch_bounds__(256, 3)
+k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, const uint32_t* __restrict__ row_ids,
+             const uint32_t* __restrict__ coefs, const uint32_t* __restrict__ z, uint64_t n_rows, uint64_t n_slices,
+             uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
+    const uint64_t total = (n_slices * 32) << g.log2_wt;
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
     for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total; tid += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t lane = (uint32_t)tid & wt_mask;
-        // rows are visited in order of decreasing term count, so the 32 rows of a warp (single-assignment mode)
-        // run the same number of gather/multiply iterations; the verdict still names the original row
-        const uint64_t row = __ldg(row_order + (tid >> g.log2_wt));
+        const uint64_t srow = tid >> g.log2_wt;
+        const uint4 sl = __ldg(slices + (srow >> 5));
+        TermStream<N> st;
+        st.start(terms + (size_t)sl.x * 32 + (srow & 31), z, lane, g.log2_wt, sl.y + sl.z + sl.w);
         uint32_t a[N], b[N], cc[N], ab[N];
-        row_dot<N>(a, rpA, colA, ciA, coefs, one_idx, z, row, lane, g.log2_wt, fp);
-        row_dot<N>(b, rpB, colB, ciB, coefs, one_idx, z, row, lane, g.log2_wt, fp);
-        row_dot<N>(cc, rpC, colC, ciC, coefs, one_idx, z, row, lane, g.log2_wt, fp);
+        lc_dot<N>(a, st, sl.y, coefs, fp);
+        lc_dot<N>(b, st, sl.z, coefs, fp);
+        lc_dot<N>(cc, st, sl.w, coefs, fp);
         fe_mont_mul<N>(ab, a, b, fp.p, fp.n0inv);  // (aR)(bR)/R = abR, compared with cR
         uint32_t diff = 0;
 #pragma unroll
         for (int k = 0; k < N; k++) diff |= ab[k] ^ cc[k];
-        bool fail = diff != 0 && lane < g.n_valid;
-        report_fail(fail, (uint32_t)row, first_fail, g.batch0 + lane, single);
+        const bool real = srow < n_rows;  // the last slice may hold padding rows
+        bool fail = diff != 0 && real && lane < g.n_valid;
+        report_fail(fail, real ? __ldg(row_ids + srow) : 0u, first_fail, g.batch0 + lane, single);
     }
 }
 
@@ -164,74 +226,126 @@ extern "C" int zkb_r1cs_load(zkb_ctx* c, const zkb_csr* A, const zkb_csr* B, con
                              size_t coef_stride, uint64_t n_coefs, uint64_t n_vars) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "set_field must be called before zkb_r1cs_load");
     if (c->prog.binary) return c->fail(ZKB_E_UNSUPPORTED, "zkb: R1CS over p = 2 is not supported");
-    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
     if (A->n_rows != B->n_rows || A->n_rows != C->n_rows) return c->fail(ZKB_E_ARG, "A, B, C must have the same number of rows");
+    if (A->n_rows >= 0xFFFFFFE0ull) return c->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 rows");
     if (n_vars == 0 || n_vars >= 0xFFFFFFFFull) return c->fail(ZKB_E_ARG, "n_vars out of range");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (n_coefs >= T_ONE) return c->fail(ZKB_E_ARG, "coefficient table too large");
+    if (c->has_gpu) CUDA_TRY(c, cudaSetDevice(c->device));
     r1cs_free(c);
     R1csDev* r = new R1csDev();
     c->r1cs = r;
-    r->n_rows = A->n_rows;
+    const uint64_t nr = A->n_rows;
+    r->n_rows = nr;
     r->n_vars = n_vars;
     const zkb_csr* M[3] = {A, B, C};
     for (int m = 0; m < 3; m++) {
-        uint64_t nnz = M[m]->row_ptr[M[m]->n_rows];
+        uint64_t nnz = M[m]->row_ptr[nr];
         if (nnz >= 0xFFFFFFFFull) return c->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 non-zeros per matrix");
         r->nnz[m] = nnz;
-        std::vector<uint32_t> rp(r->n_rows + 1);
-        for (uint64_t i = 0; i <= r->n_rows; i++) {
+        for (uint64_t i = 0; i <= nr; i++)
             if (M[m]->row_ptr[i] > nnz || (i && M[m]->row_ptr[i] < M[m]->row_ptr[i - 1])) return c->fail(ZKB_E_ARG, "row_ptr is not monotone");
-            rp[i] = (uint32_t)M[m]->row_ptr[i];
-        }
         for (uint64_t e = 0; e < nnz; e++) {
             if (M[m]->col[e] >= n_vars) return c->fail(ZKB_E_SEMANTIC, "The WireId " + std::to_string(M[m]->col[e]) + " has not been defined yet.");  // from_r1cs.rs:90
             if (M[m]->coef_idx[e] >= n_coefs) return c->fail(ZKB_E_ARG, "coefficient index out of range");
         }
-        CUDA_TRY(c, cudaMalloc((void**)&r->d_rowptr[m], rp.size() * 4));
-        CUDA_TRY(c, cudaMalloc((void**)&r->d_col[m], std::max<uint64_t>(nnz, 1) * 4));
-        CUDA_TRY(c, cudaMalloc((void**)&r->d_cidx[m], std::max<uint64_t>(nnz, 1) * 4));
-        CUDA_TRY(c, cudaMemcpy(r->d_rowptr[m], rp.data(), rp.size() * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(c, cudaMemcpy(r->d_col[m], M[m]->col, nnz * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(c, cudaMemcpy(r->d_cidx[m], M[m]->coef_idx, nnz * 4, cudaMemcpyHostToDevice));
-    }
-    {   // row order: counting sort by total number of terms, heaviest first
-        const uint64_t nr = r->n_rows;
-        std::vector<uint32_t> terms(nr);
-        uint32_t max_terms = 0;
-        for (uint64_t i = 0; i < nr; i++) {
-            uint64_t t = 0;
-            for (int m = 0; m < 3; m++) t += M[m]->row_ptr[i + 1] - M[m]->row_ptr[i];
-            terms[i] = (uint32_t)std::min<uint64_t>(t, 4095);
-            max_terms = std::max(max_terms, terms[i]);
-        }
-        std::vector<uint64_t> start((size_t)max_terms + 2, 0);
-        for (uint64_t i = 0; i < nr; i++) start[max_terms - terms[i] + 1]++;
-        for (size_t k = 0; k + 1 < start.size(); k++) start[k + 1] += start[k];
-        std::vector<uint32_t> order(std::max<uint64_t>(nr, 1));
-        for (uint64_t i = 0; i < nr; i++) order[start[max_terms - terms[i]]++] = (uint32_t)i;
-        CUDA_TRY(c, cudaMalloc((void**)&r->d_row_order, order.size() * 4));
-        CUDA_TRY(c, cudaMemcpy(r->d_row_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
     }
     // coefficient table: reduce mod p on the host (empty coefficient = 0, from_r1cs.rs:72-77), Montgomery on device
     const int N = c->prog.nlimb;
     std::vector<uint32_t> limbs((size_t)std::max<uint64_t>(n_coefs, 1) * N, 0);
+    std::vector<uint8_t> coef_class(n_coefs, 2);  // 0: zero (term dropped), 1: one, 2: general
     for (uint64_t i = 0; i < n_coefs; i++) {
         BigU v = BigU::from_bytes_le(coef_table_le + i * coef_stride, coef_stride);
         if (v >= c->prog.modulus) v = v.mod(c->prog.modulus);
         v.to_limbs(&limbs[i * N], N);
-        if (v.is_one() && r->one_idx == 0xFFFFFFFFu) r->one_idx = (uint32_t)i;
+        coef_class[i] = v.is_zero() ? 0 : v.is_one() ? 1 : 2;
     }
     r->n_coefs = (uint32_t)n_coefs;
-    CUDA_TRY(c, cudaMalloc((void**)&r->d_coefs, limbs.size() * 4));
-    CUDA_TRY(c, cudaMemcpyAsync(r->d_coefs, limbs.data(), limbs.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    launch_to_mont(N, r->d_coefs, (uint32_t)n_coefs, c->prog.fp, c->stream);
+    if (c->has_gpu) {
+        CUDA_TRY(c, cudaMalloc((void**)&r->d_coefs, limbs.size() * 4));
+        CUDA_TRY(c, cudaMemcpyAsync(r->d_coefs, limbs.data(), limbs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        launch_to_mont(N, r->d_coefs, (uint32_t)n_coefs, c->prog.fp, c->stream);
+    }
+
+    // ---- SELL-32-sigma ----
+    uint64_t sigma = 16384;
+    if (const char* e = getenv("ZKB_R1CS_SIGMA")) sigma = std::max<uint64_t>(32, (uint64_t)atoll(e) / 32 * 32);
+    auto cnt = [&](int m, uint64_t row) { return (uint64_t)(M[m]->row_ptr[row + 1] - M[m]->row_ptr[row]); };
+    std::vector<uint32_t> order(std::max<uint64_t>(nr, 1));
+    for (uint64_t i = 0; i < nr; i++) order[i] = (uint32_t)i;
+    for (uint64_t w0 = 0; w0 < nr; w0 += sigma) {
+        uint64_t w1 = std::min(nr, w0 + sigma);
+        std::stable_sort(order.begin() + w0, order.begin() + w1, [&](uint32_t x, uint32_t y) {
+            for (int m = 0; m < 3; m++) {
+                uint64_t cx = cnt(m, x), cy = cnt(m, y);
+                if (cx != cy) return cx > cy;
+            }
+            return false;
+        });
+    }
+    const uint64_t n_slices = (nr + 31) / 32;
+    std::vector<uint4> slices(std::max<uint64_t>(n_slices, 1));
+    uint64_t n_groups = 0;
+    for (uint64_t s = 0; s < n_slices; s++) {
+        uint64_t k[3] = {0, 0, 0};
+        for (uint64_t i = s * 32; i < std::min(nr, s * 32 + 32); i++)
+            for (int m = 0; m < 3; m++) k[m] = std::max(k[m], cnt(m, order[i]));
+        slices[s] = make_uint4((uint32_t)n_groups, (uint32_t)k[0], (uint32_t)k[1], (uint32_t)k[2]);
+        n_groups += k[0] + k[1] + k[2];
+        if (n_groups >= (1ull << 32) / 32) return c->fail(ZKB_E_UNSUPPORTED, "zkb: R1CS too large for the sliced layout");
+    }
+    std::vector<uint2> terms(std::max<uint64_t>(n_groups, 1) * 32, make_uint2(0, T_PAD));
+    for (uint64_t s = 0; s < n_slices; s++) {
+        uint64_t g0 = slices[s].x;
+        const uint32_t kk[3] = {slices[s].y, slices[s].z, slices[s].w};
+        for (uint64_t i = s * 32; i < std::min(nr, s * 32 + 32); i++) {
+            const uint64_t row = order[i];
+            uint64_t gm = g0;
+            for (int m = 0; m < 3; m++) {
+                const uint64_t lo = M[m]->row_ptr[row], n = cnt(m, row);
+                for (uint64_t e = 0; e < n; e++) {
+                    const uint32_t ci = M[m]->coef_idx[lo + e];
+                    const uint32_t tag = coef_class[ci] == 0 ? T_PAD : coef_class[ci] == 1 ? T_ONE : ci;
+                    terms[(gm + e) * 32 + (i & 31)] = make_uint2(tag == T_PAD ? 0u : M[m]->col[lo + e], tag);
+                }
+                gm += kk[m];
+            }
+        }
+    }
+    r->n_slices = n_slices;
+    r->n_groups = n_groups;
+    if (!c->has_gpu) {  // host-only context: the layout can be inspected, every evaluation call fails with ZKB_E_CUDA
+        r->h_slices = std::move(slices);
+        r->h_terms = std::move(terms);
+        r->h_row_ids = std::move(order);
+        return ZKB_OK;
+    }
+    CUDA_TRY(c, cudaMalloc((void**)&r->d_slices, slices.size() * sizeof(uint4)));
+    CUDA_TRY(c, cudaMalloc((void**)&r->d_terms, terms.size() * sizeof(uint2)));
+    CUDA_TRY(c, cudaMalloc((void**)&r->d_row_ids, order.size() * 4));
+    CUDA_TRY(c, cudaMemcpy(r->d_slices, slices.data(), slices.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(r->d_terms, terms.data(), terms.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(r->d_row_ids, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ZKB_OK;
+}
+
+extern "C" int zkb_debug_r1cs_layout(zkb_ctx* c, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids) {
+    R1csDev* r = c->r1cs;
+    if (!r) return c->fail(ZKB_E_ARG, "zkb_r1cs_load must be called first");
+    if (c->has_gpu) return c->fail(ZKB_E_ARG, "zkb_debug_r1cs_layout needs a host-only context (device < 0)");
+    counts[0] = r->n_slices;
+    counts[1] = r->n_groups;
+    counts[2] = r->n_rows;
+    if (slices) memcpy(slices, r->h_slices.data(), r->n_slices * sizeof(uint4));
+    if (terms) memcpy(terms, r->h_terms.data(), r->n_groups * 32 * sizeof(uint2));
+    if (row_ids) memcpy(row_ids, r->h_row_ids.data(), r->n_rows * 4);
     return ZKB_OK;
 }
 
 extern "C" int zkb_r1cs_upload(zkb_ctx* c, const uint8_t* z_le, uint64_t z_set_stride, uint32_t value_stride, uint32_t n_batch) {
     R1csDev* r = c->r1cs;
     if (!r) return c->fail(ZKB_E_ARG, "zkb_r1cs_load must be called first");
+    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
     if (n_batch == 0 || value_stride == 0) return c->fail(ZKB_E_ARG, "n_batch and value_stride must be > 0");
     if (n_batch > 1 && z_set_stride < r->n_vars * value_stride) return c->fail(ZKB_E_ARG, "z_set_stride smaller than one assignment vector");
     // variable 0 is the constant one (from_r1cs.rs:40-42, 52-56)
@@ -315,10 +429,9 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
         DISPATCH_N(N, (k_r1cs_load_z<N><<<grid, 256, 0, c->stream>>>(r->d_zraw, r->z_set_stride, r->stride, r->n_vars, r->d_z, g,
                                                                      c->d_unreduced, fp)));
         cudaEventRecord(c->tile_ev[2 * t], c->stream);
-        grid = grid_for(r->n_rows << r->log2_wt, c->sm_count, 256);
-        DISPATCH_N(N, (k_r1cs_check<N><<<grid, 256, 0, c->stream>>>(r->d_rowptr[0], r->d_col[0], r->d_cidx[0], r->d_rowptr[1], r->d_col[1],
-                                                                    r->d_cidx[1], r->d_rowptr[2], r->d_col[2], r->d_cidx[2], r->d_coefs,
-                                                                    r->one_idx, r->d_z, r->n_rows, r->d_row_order, r->d_first_fail, g, fp)));
+        grid = grid_for((r->n_slices * 32) << r->log2_wt, c->sm_count, 256);
+        DISPATCH_N(N, (k_r1cs_check<N><<<grid, 256, 0, c->stream>>>(r->d_slices, r->d_terms, r->d_row_ids, r->d_coefs, r->d_z, r->n_rows,
+                                                                    r->n_slices, r->d_first_fail, g, fp)));
         cudaEventRecord(c->tile_ev[2 * t + 1], c->stream);
         launches += 2;
     }
