@@ -237,6 +237,40 @@ int zkb_evaluator_get_wire(zkb_evaluator* ev, uint64_t wire_id, uint8_t* out_le,
 int zkb_evaluator_lookup(zkb_evaluator* ev, uint64_t wire_id, zkb_wire* out);
 const char* zkb_evaluator_last_error(zkb_evaluator* ev);
 
+/* `zki_sieve flatten` (cli.rs:442-472): the Evaluator driving the reference's IRFlattener backend
+ * (consumers/flattening.rs:42-191) instead of an evaluating one.  Call set_flatten(ev, 1) BEFORE ingesting; the
+ * statement is then recorded gate for gate as the IRFlattener's GateBuilder would emit it (one SIMPLE gate per
+ * ZKBackend callback incl. copies, wire ids 0, 1, 2, ..., messages of at most 100 000 gates / values) and can be
+ * written out, not evaluated (host only, no device needed).
+ *   zkb_evaluator_flatten        : MemorySink — three buffers of size-prefixed messages, owned by ev
+ *   zkb_evaluator_flatten_to_dir : FilesSink::new_clean — 000_instance / 001_witness / 002_relation .sieve */
+int zkb_evaluator_set_flatten(zkb_evaluator* ev, int on);
+int zkb_evaluator_flatten(zkb_evaluator* ev, const uint8_t** instance, size_t* instance_len, const uint8_t** witness,
+                          size_t* witness_len, const uint8_t** relation, size_t* relation_len);
+int zkb_evaluator_flatten_to_dir(zkb_evaluator* ev, const char* out_dir);
+
+/* ------------------------------------------------------------------ 4b. Validator
+ * Mirror of `Validator` (rust/src/consumers/validator.rs:68-829): the semantic / syntactic checks of
+ * `zki_sieve validate` and `valid-eval-metrics` (cli.rs:302-313, 333-363), with the reference's violation texts.
+ * Host only.  as_prover 1: Validator::new_as_prover, 0: new_as_verifier (:108-117). */
+typedef struct zkb_validator zkb_validator;
+zkb_validator* zkb_validator_create(int as_prover);
+void zkb_validator_destroy(zkb_validator* v);
+/* Validator::ingest_message on one size-prefixed message / a concatenation of messages / Source paths */
+int zkb_validator_ingest_message(zkb_validator* v, const uint8_t* buf, size_t len);
+int zkb_validator_ingest_buffer(zkb_validator* v, const uint8_t* buf, size_t len);
+int zkb_validator_ingest_paths(zkb_validator* v, const char* const* paths, size_t n_paths);
+/* Validator::get_violations (:136-144): runs the end-of-statement checks once, returns the number of violations */
+int zkb_validator_get_violations(zkb_validator* v, size_t* n_violations);
+const char* zkb_validator_violation(zkb_validator* v, size_t i);
+/* Validator::how_many_violations (:150-152): violations so far, without the end-of-statement checks */
+size_t zkb_validator_how_many_violations(zkb_validator* v);
+/* wires still live (the reference prints "WARNING: few variables were not freed." when non-zero, :139-141) */
+uint64_t zkb_validator_live_wires(zkb_validator* v);
+/* loop / expansion budget (gates + loop iterations + wires expanded); default 2^40, 0 keeps the current value */
+int zkb_validator_set_limits(zkb_validator* v, uint64_t max_steps);
+const char* zkb_validator_last_error(zkb_validator* v);
+
 /* ------------------------------------------------------------------ 5. R1CS (Az o Bz = Cz)
  * The satisfiability check that `zkif-to-ir` + `evaluate` performs gate by gate on an R1CS
  * (rust/src/producers/from_r1cs.rs:110-125), done as three CSR sparse mod-p mat-vecs and a
@@ -265,6 +299,14 @@ int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops
 /* Device layout zkb_r1cs_load built (host-only contexts): counts = {slices, term groups, rows}; slices: 4 x uint32 per slice
  * {first group, KA, KB, KC}; terms: 32 x {col, coefficient tag} per group (tag 0xFFFFFFFF: padding / zero coefficient,
  * 0xFFFFFFFE: coefficient one, else the table index); row_ids: sorted position -> row.  NULL pointers are skipped. */
+/* FlatBuffers reader -> owned structs -> writer on one size-prefixed message (round-trip tests); *out is valid until
+ * the next call on this thread. */
+int zkb_debug_rewrite_message(zkb_ctx* ctx, const uint8_t* buf, size_t len, const uint8_t** out, size_t* out_len);
+/* zkb_gate[] -> a SIMPLE relation as size-prefixed messages of at most 100 000 gates (GateBuilder + MemorySink,
+ * builder.rs:93-98): generator of large `.sieve` inputs for the reader / Evaluator path. */
+int zkb_debug_write_flat_relation(zkb_ctx* ctx, const uint8_t* modulus_le, size_t modulus_len, int is_boolean,
+                                  const zkb_gate* gates, uint64_t n_gates, const uint8_t* const_pool_le, size_t const_stride,
+                                  uint64_t n_consts, const uint8_t** out, size_t* out_len);
 int zkb_debug_r1cs_layout(zkb_ctx* ctx, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids);
 
 #ifdef __cplusplus

@@ -71,8 +71,11 @@ EXPORTED = [
     "zkb_upload_inputs", "zkb_run", "zkb_assert_info", "zkb_pending_error", "zkb_read_values", "zkb_scope_lookup",
     "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_level_info", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
     "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
-    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
-    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout",
+    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_evaluator_set_flatten", "zkb_evaluator_flatten",
+    "zkb_evaluator_flatten_to_dir", "zkb_validator_create", "zkb_validator_destroy", "zkb_validator_ingest_message",
+    "zkb_validator_ingest_buffer", "zkb_validator_ingest_paths", "zkb_validator_get_violations", "zkb_validator_violation",
+    "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
+    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_write_flat_relation",
 ]
 
 _vp, _u8p, _sz, _u64, _u32, _i = C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
@@ -128,6 +131,21 @@ _sig("zkb_evaluator_violation", C.c_char_p, _vp, _sz)
 _sig("zkb_evaluator_get_wire", _i, _vp, _u64, _u8p, _sz, C.POINTER(C.c_size_t))
 _sig("zkb_evaluator_lookup", _i, _vp, _u64, _u64p)
 _sig("zkb_evaluator_last_error", C.c_char_p, _vp)
+_sig("zkb_evaluator_set_flatten", _i, _vp, _i)
+_sig("zkb_evaluator_flatten", _i, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+     C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+_sig("zkb_evaluator_flatten_to_dir", _i, _vp, C.c_char_p)
+_sig("zkb_validator_create", _vp, _i)
+_sig("zkb_validator_destroy", None, _vp)
+_sig("zkb_validator_ingest_message", _i, _vp, _u8p, _sz)
+_sig("zkb_validator_ingest_buffer", _i, _vp, _u8p, _sz)
+_sig("zkb_validator_ingest_paths", _i, _vp, C.POINTER(C.c_char_p), _sz)
+_sig("zkb_validator_get_violations", _i, _vp, C.POINTER(C.c_size_t))
+_sig("zkb_validator_violation", C.c_char_p, _vp, _sz)
+_sig("zkb_validator_how_many_violations", C.c_size_t, _vp)
+_sig("zkb_validator_live_wires", _u64, _vp)
+_sig("zkb_validator_set_limits", _i, _vp, _u64)
+_sig("zkb_validator_last_error", C.c_char_p, _vp)
 _sig("zkb_r1cs_load", _i, _vp, C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), _u8p, _sz, _u64, _u64)
 _sig("zkb_r1cs_check", _i, _vp, _u8p, _u64, _u32, _u32, _vp)
 _sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
@@ -135,6 +153,9 @@ _sig("zkb_r1cs_run", _i, _vp, _vp)
 _sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
 _sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
 _sig("zkb_debug_r1cs_layout", _i, _vp, _u64p, _vp, _vp, _vp)
+_sig("zkb_debug_rewrite_message", _i, _vp, _u8p, _sz, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+_sig("zkb_debug_write_flat_relation", _i, _vp, _u8p, _sz, _i, _vp, _u64, _u8p, _sz, _u64, C.POINTER(C.c_void_p),
+     C.POINTER(C.c_size_t))
 
 
 class ZkbError(Exception):
@@ -405,6 +426,23 @@ class GpuBackend:
         self._chk(_lib.zkb_r1cs_load(self._c, C.byref(a), C.byref(b), C.byref(c), _buf(coef_table),
                                      coef_table.shape[1], coef_table.shape[0], n_vars))
 
+    def write_flat_relation(self, modulus: int, gates: np.ndarray, const_pool: Optional[np.ndarray] = None,
+                            is_boolean: bool = False) -> bytes:
+        """zkb_gate[] -> SIMPLE relation messages (100 000 gates each), as a GateBuilder over a MemorySink would emit"""
+        gates = np.ascontiguousarray(gates)
+        pool = np.ascontiguousarray(const_pool, dtype=np.uint8) if const_pool is not None else np.zeros((0, 1), np.uint8)
+        m = _le(modulus)
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._chk(_lib.zkb_debug_write_flat_relation(self._c, _buf(m), len(m), int(is_boolean), gates.ctypes.data, len(gates),
+                                                     _buf(pool), pool.shape[1], pool.shape[0], C.byref(ptr), C.byref(n)))
+        return C.string_at(ptr.value, n.value)
+
+    def rewrite_message(self, buf: bytes) -> bytes:
+        """C++ reader -> owned structs -> C++ writer (round-trip tests)"""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._chk(_lib.zkb_debug_rewrite_message(self._c, _buf(buf), len(buf), C.byref(ptr), C.byref(n)))
+        return C.string_at(ptr.value, n.value)
+
     def r1cs_layout(self):
         """(slices uint32[n,4], terms uint32[groups,32,2], row_ids uint32[rows]) of a host-only context"""
         cnt = (C.c_uint64 * 3)()
@@ -456,9 +494,13 @@ class Source:
 class Evaluator:
     """`Evaluator<GpuBackend>` (evaluator.rs:158-753) over `.sieve` bytes."""
 
-    def __init__(self, backend: Optional[GpuBackend] = None, device: int = 0):
-        self.backend = backend or GpuBackend(device)
+    def __init__(self, backend: Optional[GpuBackend] = None, device: int = 0, flatten: bool = False):
+        """flatten=True: the Evaluator drives the IRFlattener instead of an evaluating backend
+        (consumers/flattening.rs); the statement can then be written out with flatten() / flatten_to_dir()."""
+        self.backend = backend or GpuBackend(-1 if flatten else device)
         self._e = _lib.zkb_evaluator_create(self.backend._c)
+        if flatten:
+            self._chk(_lib.zkb_evaluator_set_flatten(self._e, 1))
 
     def close(self):
         if getattr(self, "_e", None):
@@ -497,6 +539,18 @@ class Evaluator:
         self._chk(_lib.zkb_evaluator_get_violations(self._e, C.byref(n)))
         return [_lib.zkb_evaluator_violation(self._e, i).decode("utf-8", "replace") for i in range(n.value)]
 
+    def flatten(self):
+        """(instance, witness, relation) buffers of size-prefixed messages — IRFlattener over a MemorySink"""
+        ptr = [C.c_void_p() for _ in range(3)]
+        ln = [C.c_size_t() for _ in range(3)]
+        self._chk(_lib.zkb_evaluator_flatten(self._e, C.byref(ptr[0]), C.byref(ln[0]), C.byref(ptr[1]), C.byref(ln[1]),
+                                             C.byref(ptr[2]), C.byref(ln[2])))
+        return tuple(C.string_at(p.value, n.value) if n.value else b"" for p, n in zip(ptr, ln))
+
+    def flatten_to_dir(self, out_dir):
+        """IRFlattener over FilesSink::new_clean: 000_instance / 001_witness / 002_relation .sieve"""
+        self._chk(_lib.zkb_evaluator_flatten_to_dir(self._e, str(out_dir).encode()))
+
     def value_handle(self, wire_id: int) -> int:
         """SSA handle bound to a live top-scope wire (for GpuBackend.read_values on any batch element)"""
         out = C.c_uint64()
@@ -508,3 +562,58 @@ class Evaluator:
         n = C.c_size_t()
         self._chk(_lib.zkb_evaluator_get_wire(self._e, wire_id, C.cast(out, C.c_void_p), 64, C.byref(n)))
         return int.from_bytes(out.raw[:n.value], "little")
+
+
+class Validator:
+    """`Validator` (rust/src/consumers/validator.rs:68-829) over `.sieve` bytes; host only."""
+
+    def __init__(self, as_prover: bool = False):
+        self._v = _lib.zkb_validator_create(int(as_prover))
+
+    @classmethod
+    def new_as_prover(cls):
+        return cls(True)
+
+    @classmethod
+    def new_as_verifier(cls):
+        return cls(False)
+
+    def close(self):
+        if getattr(self, "_v", None):
+            _lib.zkb_validator_destroy(self._v)
+            self._v = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != ZKB_OK:
+            raise ZkbError(rc, _lib.zkb_validator_last_error(self._v).decode("utf-8", "replace"))
+
+    def set_limits(self, max_steps: int):
+        self._chk(_lib.zkb_validator_set_limits(self._v, max_steps))
+
+    def ingest_message(self, buf: bytes):
+        self._chk(_lib.zkb_validator_ingest_message(self._v, _buf(buf), len(buf)))
+
+    def ingest_source(self, source: Source):
+        if source.buffers is not None:
+            for b in source.buffers:
+                self._chk(_lib.zkb_validator_ingest_buffer(self._v, _buf(b), len(b)))
+        else:
+            arr = (C.c_char_p * len(source.paths))(*[p.encode() for p in source.paths])
+            self._chk(_lib.zkb_validator_ingest_paths(self._v, arr, len(source.paths)))
+
+    def how_many_violations(self) -> int:
+        return int(_lib.zkb_validator_how_many_violations(self._v))
+
+    def live_wires(self) -> int:
+        return int(_lib.zkb_validator_live_wires(self._v))
+
+    def get_violations(self) -> List[str]:
+        n = C.c_size_t()
+        self._chk(_lib.zkb_validator_get_violations(self._v, C.byref(n)))
+        return [_lib.zkb_validator_violation(self._v, i).decode("utf-8", "replace") for i in range(n.value)]

@@ -46,6 +46,7 @@ static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
 
 int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
+    if (c->prog.keep_copies) return c->fail(ZKB_E_ARG, "this context records in flatten mode: the program can be written out, not evaluated");
     const bool keep_all = keep_values == 1;
     // a bitwise gate on a constant >= p would need the unreduced integer (evaluator.rs:924-930): refuse up front
     for (uint32_t v = 0; v < c->prog.n_values() && !c->prog.binary; v++) {

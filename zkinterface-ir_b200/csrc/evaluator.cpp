@@ -11,7 +11,10 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <deque>
+#include <thread>
 #include <unordered_map>
 
 #include "context.h"
@@ -59,6 +62,7 @@ struct zkb_evaluator {
 
     bool evaluated = false;
     std::vector<std::string> violations;
+    std::vector<uint8_t> flat_out[3];  // flatten output (instance, witness, relation), owned here
     std::vector<Scope*> scope_pool;
 
     explicit zkb_evaluator(zkb_ctx* ctx) : c(ctx) {}
@@ -545,6 +549,245 @@ struct zkb_evaluator {
     }
 };
 
+static bool has_sieve_ext(const std::string& p);
+
+// --------------------------------------------------------------------------------------------------
+// flatten: the statement `zki_sieve flatten` writes (cli.rs:442-472) — what the reference's IRFlattener backend
+// (consumers/flattening.rs:42-191) emits through a GateBuilder when it sits behind the Evaluator: one SIMPLE gate per
+// ZKBackend callback (copies included, no Free), output wire ids allocated 0, 1, 2, ... (builder.rs:229-233, 251-256),
+// the consumed instance / witness values re-emitted in consumption order, messages cut every 100 000 gates / values
+// (builder.rs:45-49, 79-100).  In flatten mode Program records copies as values, so a value handle IS that wire id.
+// --------------------------------------------------------------------------------------------------
+namespace {
+
+std::vector<uint8_t> minimal_le(const uint8_t* p, size_t n) {  // BigUint::to_bytes_le: no trailing zeros, zero is [0]
+    while (n > 0 && p[n - 1] == 0) n--;
+    if (n == 0) return std::vector<uint8_t>{0};
+    return std::vector<uint8_t>(p, p + n);
+}
+
+std::vector<uint8_t> const_bytes(const Program& p, uint32_t idx) {
+    if (p.const_unreduced[idx]) return minimal_le(p.const_raw[idx].data(), p.const_raw[idx].size());
+    const int N = std::max(p.nlimb, 1);
+    std::vector<uint8_t> b((size_t)N * 4);
+    for (int k = 0; k < N; k++) {
+        uint32_t w = p.const_limbs[(size_t)idx * N + k];
+        memcpy(&b[(size_t)k * 4], &w, 4);
+    }
+    return minimal_le(b.data(), b.size());
+}
+
+constexpr size_t kMaxLen = 100 * 1000;  // MessageBuilder::max_len
+
+}  // namespace
+
+static int flatten_statement(zkb_evaluator* ev, std::vector<uint8_t>& inst_out, std::vector<uint8_t>& wit_out,
+                             std::vector<uint8_t>& rel_out) {
+    Program& p = ev->prog();
+    if (!p.keep_copies) return ev->fail(ZKB_E_ARG, "zkb_evaluator_set_flatten(ev, 1) must be called before ingesting");
+    if (ev->fatal) return ev->fail(ZKB_E_FATAL, ev->err);
+    inst_out.clear();
+    wit_out.clear();
+    rel_out.clear();
+    if (!p.field_set) return ZKB_OK;  // no relation reached the backend: the builder was never created
+    ir::Header h;
+    h.version = "1.0.0";  // IR_VERSION, structs/mod.rs:36
+    h.field_characteristic = p.modulus_le;
+    h.field_degree = 1;
+    ir::Message inst, wit, rel;
+    inst.type = ir::MSG_INSTANCE;
+    wit.type = ir::MSG_WITNESS;
+    rel.type = ir::MSG_RELATION;
+    inst.header = wit.header = rel.header = h;
+    rel.gate_mask = ev->c->is_boolean ? ir::M_BOOL : ir::M_ARITH;
+    rel.feat_mask = ir::M_SIMPLE;
+    auto append = [](std::vector<uint8_t>& out, const ir::Message& m) {
+        std::vector<uint8_t> b = ir::write_message(m);
+        out.insert(out.end(), b.begin(), b.end());
+    };
+    auto push_gate = [&](const ir::Gate& g) {
+        rel.gates.push_back(g);
+        if (rel.gates.size() >= kMaxLen) {
+            append(rel_out, rel);
+            rel.gates.clear();
+            rel.consts.clear();
+        }
+    };
+    auto add_const = [&](std::vector<uint8_t>&& b) {
+        rel.consts.push_back(std::move(b));
+        return (uint32_t)rel.consts.size() - 1;
+    };
+    const uint32_t n = p.n_values();
+    size_t ai = 0;
+    for (uint32_t v = 0; v <= n; v++) {
+        for (; ai < p.asserts.size() && p.asserts[ai].pos == v; ai++) {
+            ir::Gate g;
+            g.type = ir::G_ASSERT_ZERO;
+            g.w0 = p.asserts[ai].value;
+            push_gate(g);
+        }
+        if (v == n) break;
+        ir::Gate g;
+        g.w0 = v;
+        const uint32_t a = p.opa[v], b = p.opb[v];
+        switch (p.kind[v]) {
+            case V_CONST: g.type = ir::G_CONSTANT; g.const_idx = add_const(const_bytes(p, b)); break;
+            case V_INSTANCE: {
+                g.type = ir::G_INSTANCE;
+                const auto& val = ev->instance_values[b];
+                inst.values.push_back(minimal_le(val.data(), val.size()));
+                if (inst.values.size() == kMaxLen) {
+                    append(inst_out, inst);
+                    inst.values.clear();
+                }
+            } break;
+            case V_WITNESS: {
+                g.type = ir::G_WITNESS;
+                const auto& val = ev->witness_values[b];
+                wit.values.push_back(minimal_le(val.data(), val.size()));
+                if (wit.values.size() == kMaxLen) {
+                    append(wit_out, wit);
+                    wit.values.clear();
+                }
+            } break;
+            case V_ADD: g.type = ir::G_ADD; g.w1 = a; g.w2 = b; break;
+            case V_MUL: g.type = ir::G_MUL; g.w1 = a; g.w2 = b; break;
+            case V_AND: g.type = ir::G_AND; g.w1 = a; g.w2 = b; break;
+            case V_XOR: g.type = ir::G_XOR; g.w1 = a; g.w2 = b; break;
+            case V_ADDC: g.type = ir::G_ADD_CONSTANT; g.w1 = a; g.const_idx = add_const(const_bytes(p, b)); break;
+            case V_MULC: g.type = ir::G_MUL_CONSTANT; g.w1 = a; g.const_idx = add_const(const_bytes(p, b)); break;
+            case V_NOT: g.type = ir::G_NOT; g.w1 = a; break;
+            case V_COPY: g.type = ir::G_COPY; g.w1 = a; break;
+            default: return ev->fail(ZKB_E_ARG, "corrupt program");
+        }
+        push_gate(g);
+    }
+    // MessageBuilder::finish, builder.rs:124-135
+    if (!inst.values.empty()) append(inst_out, inst);
+    if (!wit.values.empty()) append(wit_out, wit);
+    if (!rel.gates.empty()) append(rel_out, rel);
+    return ZKB_OK;
+}
+
+// reader -> owned structs -> writer, for round-trip tests of the two halves (any message kind, any gate)
+extern "C" int zkb_debug_rewrite_message(zkb_ctx* c, const uint8_t* buf, size_t len, const uint8_t** out, size_t* out_len) {
+    static thread_local std::vector<uint8_t> scratch;
+    ir::Message m;
+    std::string e;
+    if (!ir::read_message(buf, len, m, e)) return c->fail(ZKB_E_FORMAT, e);
+    scratch = ir::write_message(m);
+    *out = scratch.data();
+    *out_len = scratch.size();
+    return ZKB_OK;
+}
+
+// zkb_gate[] -> a SIMPLE relation as size-prefixed messages of at most 100 000 gates (what a GateBuilder over a
+// MemorySink produces for the same gate list, builder.rs:93-98); workload generator for large `.sieve` inputs
+extern "C" int zkb_debug_write_flat_relation(zkb_ctx* c, const uint8_t* modulus_le, size_t modulus_len, int is_boolean,
+                                             const zkb_gate* gates, uint64_t n_gates, const uint8_t* const_pool_le, size_t const_stride,
+                                             uint64_t n_consts, const uint8_t** out, size_t* out_len) {
+    static thread_local std::vector<uint8_t> scratch;
+    scratch.clear();
+    ir::Message rel;
+    rel.type = ir::MSG_RELATION;
+    rel.header.version = "1.0.0";
+    rel.header.field_characteristic.assign(modulus_le, modulus_le + modulus_len);
+    rel.header.field_degree = 1;
+    rel.gate_mask = is_boolean ? ir::M_BOOL : ir::M_ARITH;
+    rel.feat_mask = ir::M_SIMPLE;
+    auto flush = [&]() {
+        std::vector<uint8_t> b = ir::write_message(rel);
+        scratch.insert(scratch.end(), b.begin(), b.end());
+        rel.gates.clear();
+        rel.consts.clear();
+    };
+    for (uint64_t i = 0; i < n_gates; i++) {
+        const zkb_gate& g = gates[i];
+        ir::Gate o;
+        o.type = g.op;
+        switch (g.op) {
+            case ZKB_G_CONSTANT: case ZKB_G_ADD_CONSTANT: case ZKB_G_MUL_CONSTANT: {
+                if (g.b >= n_consts) return c->fail(ZKB_E_ARG, "constant index out of range");
+                const uint8_t* v = const_pool_le + (size_t)g.b * const_stride;
+                size_t n = const_stride;
+                while (n > 1 && v[n - 1] == 0) n--;
+                rel.consts.emplace_back(v, v + n);
+                o.const_idx = (uint32_t)rel.consts.size() - 1;
+                o.w0 = g.out;
+                o.w1 = g.a;
+            } break;
+            case ZKB_G_ASSERT_ZERO: o.w0 = g.a; break;
+            case ZKB_G_COPY: case ZKB_G_NOT: o.w0 = g.out; o.w1 = g.a; break;
+            case ZKB_G_ADD: case ZKB_G_MUL: case ZKB_G_AND: case ZKB_G_XOR: o.w0 = g.out; o.w1 = g.a; o.w2 = g.b; break;
+            case ZKB_G_INSTANCE: case ZKB_G_WITNESS: o.w0 = g.out; break;
+            case ZKB_G_FREE: o.w0 = g.a; o.w1 = g.b; o.has_last = g.b != g.a; break;
+            default: return c->fail(ZKB_E_ARG, "unknown gate opcode");
+        }
+        rel.gates.push_back(o);
+        if (rel.gates.size() >= kMaxLen) flush();
+    }
+    if (!rel.gates.empty() || n_gates == 0) flush();
+    *out = scratch.data();
+    *out_len = scratch.size();
+    return ZKB_OK;
+}
+
+extern "C" int zkb_evaluator_set_flatten(zkb_evaluator* ev, int on) {
+    if (ev->prog().n_values() > 0) return ev->fail(ZKB_E_ARG, "flatten mode must be chosen before anything is recorded");
+    ev->prog().keep_copies = on != 0;
+    return ZKB_OK;
+}
+
+extern "C" int zkb_evaluator_flatten(zkb_evaluator* ev, const uint8_t** instance, size_t* instance_len, const uint8_t** witness,
+                                     size_t* witness_len, const uint8_t** relation, size_t* relation_len) {
+    int rc = flatten_statement(ev, ev->flat_out[0], ev->flat_out[1], ev->flat_out[2]);
+    if (rc != ZKB_OK) return rc;
+    const uint8_t** ptr[3] = {instance, witness, relation};
+    size_t* len[3] = {instance_len, witness_len, relation_len};
+    for (int i = 0; i < 3; i++) {
+        if (ptr[i]) *ptr[i] = ev->flat_out[i].data();
+        if (len[i]) *len[i] = ev->flat_out[i].size();
+    }
+    return ZKB_OK;
+}
+
+// FilesSink::new_clean + the three conventional file names (producers/sink.rs:67-104, 139-153)
+extern "C" int zkb_evaluator_flatten_to_dir(zkb_evaluator* ev, const char* out_dir) {
+    std::string dir = out_dir;
+    if (has_sieve_ext(dir)) return ev->fail(ZKB_E_ARG, "IR flattening requires a directory as output value");  // cli.rs:459-460
+    int rc = flatten_statement(ev, ev->flat_out[0], ev->flat_out[1], ev->flat_out[2]);
+    if (rc != ZKB_OK) return rc;
+    std::string acc;
+    for (size_t i = 0; i <= dir.size(); i++) {  // create_dir_all
+        if (i == dir.size() || dir[i] == '/') {
+            if (!acc.empty()) mkdir(acc.c_str(), 0777);
+        }
+        if (i < dir.size()) acc.push_back(dir[i]);
+    }
+    if (DIR* d = opendir(dir.c_str())) {  // clean_workspace: remove existing *.sieve
+        while (dirent* e = readdir(d)) {
+            std::string full = dir + "/" + e->d_name;
+            if (has_sieve_ext(full)) remove(full.c_str());
+        }
+        closedir(d);
+    } else {
+        return ev->fail(ZKB_E_ARG, "cannot create directory " + dir);
+    }
+    const char* names[3] = {"000_instance.sieve", "001_witness.sieve", "002_relation.sieve"};
+    for (int i = 0; i < 3; i++) {
+        std::string path = dir + "/" + names[i];
+        FILE* fp = fopen(path.c_str(), "wb");
+        if (!fp) return ev->fail(ZKB_E_ARG, "cannot write " + path);
+        size_t n = ev->flat_out[i].size();
+        if (n && fwrite(ev->flat_out[i].data(), 1, n, fp) != n) {
+            fclose(fp);
+            return ev->fail(ZKB_E_ARG, "short write to " + path);
+        }
+        fclose(fp);
+    }
+    return ZKB_OK;
+}
+
 // --------------------------------------------------------------------------------------------------
 // Source: file discovery and ordering, rust/src/consumers/source.rs:64-89, 165-193
 // --------------------------------------------------------------------------------------------------
@@ -555,16 +798,24 @@ static bool has_sieve_ext(const std::string& p) {
     return dot != std::string::npos && dot > 0 && name.substr(dot + 1) == "sieve";
 }
 
-static int list_workspace_files(zkb_evaluator* ev, const char* const* paths, size_t n, std::vector<std::string>& out) {
+namespace zkb {
+int list_workspace_files(const char* const* paths, size_t n, std::vector<std::string>& out, std::string& err) {
     for (size_t i = 0; i < n; i++) {
         std::string p = paths[i];
         if (has_sieve_ext(p)) {
             out.push_back(p);
         } else if (p == "-") {
-            return ev->fail(ZKB_E_UNSUPPORTED, "zkb: reading the statement from stdin is not supported");
+            if (n > 1) {  // source.rs:170-173
+                err = "Cannot combine files and stdin";
+                return ZKB_E_ARG;
+            }
+            out.push_back(p);  // BufferSource::Stdin, source.rs:69-71
         } else {
             DIR* d = opendir(p.c_str());
-            if (!d) return ev->fail(ZKB_E_ARG, "cannot read directory " + p);
+            if (!d) {
+                err = "cannot read directory " + p;
+                return ZKB_E_ARG;
+            }
             while (dirent* e = readdir(d)) {
                 std::string name = e->d_name;
                 std::string full = p + (p.size() && p.back() == '/' ? "" : "/") + name;
@@ -587,37 +838,96 @@ static int list_workspace_files(zkb_evaluator* ev, const char* const* paths, siz
     return ZKB_OK;
 }
 
+bool read_whole_file(const std::string& path, std::vector<uint8_t>& data) {
+    FILE* fp = path == "-" ? stdin : fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    uint8_t chunk[1 << 16];
+    size_t got;
+    while ((got = fread(chunk, 1, sizeof chunk, fp)) > 0) data.insert(data.end(), chunk, chunk + got);
+    if (fp != stdin) fclose(fp);
+    return true;
+}
+}  // namespace zkb
+
 extern "C" zkb_evaluator* zkb_evaluator_create(zkb_ctx* backend) { return new zkb_evaluator(backend); }
 extern "C" void zkb_evaluator_destroy(zkb_evaluator* ev) { delete ev; }
 extern "C" const char* zkb_evaluator_last_error(zkb_evaluator* ev) { return ev->err.c_str(); }
 
 extern "C" int zkb_evaluator_ingest_message(zkb_evaluator* ev, const uint8_t* buf, size_t len) { return ev->ingest_bytes(buf, len); }
 
+// FlatBuffers -> owned structs is the expensive half of ingestion (about 80 % for flat relations) and messages
+// are independent of each other there, so a large buffer (a builder-produced relation arrives as one message per
+// 100 000 gates) is parsed by a small thread pool, one window of messages at a time; flattening / recording then
+// consumes the parsed messages strictly in order, so errors surface exactly where the serial loop would meet them
+// (a malformed message is fatal when it is reached: Evaluator::from_messages unwraps it, evaluator.rs:193).
+static unsigned parse_threads() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZKB_PARSE_THREADS");
+        unsigned hw = std::thread::hardware_concurrency();
+        v = e ? atoi(e) : (int)std::min(16u, hw ? hw : 1u);
+        if (v < 1) v = 1;
+    }
+    return (unsigned)v;
+}
+
 extern "C" int zkb_evaluator_ingest_buffer(zkb_evaluator* ev, const uint8_t* buf, size_t len) {
     std::vector<std::pair<size_t, size_t>> msgs;
     ir::split_messages(buf, len, msgs);
-    for (auto& m : msgs) {
-        int rc = ev->ingest_bytes(buf + m.first, m.second);
-        if (rc != ZKB_OK) return rc;
+    const unsigned T = parse_threads();
+    if (T < 2 || msgs.size() < 2 || len < ((size_t)1 << 20)) {
+        for (auto& m : msgs) {
+            int rc = ev->ingest_bytes(buf + m.first, m.second);
+            if (rc != ZKB_OK) return rc;
+        }
+        return ZKB_OK;
     }
+    const size_t window = (size_t)T * 2;
+    double t_parse = 0, t_ing = 0;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    for (size_t w0 = 0; w0 < msgs.size(); w0 += window) {
+        double ta = now();
+        const size_t w1 = std::min(msgs.size(), w0 + window);
+        std::vector<ir::Message> parsed(w1 - w0);
+        std::vector<std::string> errs(w1 - w0);
+        std::vector<char> ok(w1 - w0, 0);
+        std::atomic<size_t> next{w0};
+        auto work = [&]() {
+            for (size_t i; (i = next.fetch_add(1)) < w1;)
+                ok[i - w0] = ir::read_message(buf + msgs[i].first, msgs[i].second, parsed[i - w0], errs[i - w0]) ? 1 : 0;
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T && t < w1 - w0; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        double tb = now();
+        t_parse += tb - ta;
+        for (size_t i = w0; i < w1; i++) {
+            if (!ok[i - w0]) {
+                ev->fatal = true;
+                return ev->fail(ZKB_E_FORMAT, errs[i - w0]);
+            }
+            int rc = ev->ingest_parsed(parsed[i - w0]);
+            if (rc != ZKB_OK) return rc;
+            parsed[i - w0] = ir::Message();  // release the owned structs as soon as they are recorded
+        }
+        t_ing += now() - tb;
+    }
+    if (getenv("ZKB_TIMING")) fprintf(stderr, "parse %.3f s ingest %.3f s\n", t_parse, t_ing);
     return ZKB_OK;
 }
 
 extern "C" int zkb_evaluator_ingest_paths(zkb_evaluator* ev, const char* const* paths, size_t n_paths) {
     std::vector<std::string> files;
-    int rc = list_workspace_files(ev, paths, n_paths, files);
-    if (rc != ZKB_OK) return rc;
+    std::string e;
+    int rc = zkb::list_workspace_files(paths, n_paths, files, e);
+    if (rc != ZKB_OK) return ev->fail(rc, e);
     for (const auto& f : files) {
-        FILE* fp = fopen(f.c_str(), "rb");
-        if (!fp) {
+        std::vector<uint8_t> data;
+        if (!zkb::read_whole_file(f, data)) {
             fprintf(stderr, "Warning: failed to open file %s\n", f.c_str());  // source.rs:132
             continue;
         }
-        std::vector<uint8_t> data;
-        uint8_t chunk[1 << 16];
-        size_t got;
-        while ((got = fread(chunk, 1, sizeof chunk, fp)) > 0) data.insert(data.end(), chunk, chunk + got);
-        fclose(fp);
         rc = zkb_evaluator_ingest_buffer(ev, data.data(), data.size());
         if (rc != ZKB_OK) return rc;
     }

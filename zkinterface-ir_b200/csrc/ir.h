@@ -111,6 +111,9 @@ bool read_message(const uint8_t* buf, size_t len, Message& out, std::string& err
 // A message running past the end of the buffer stops the split (the reference's read_exact fails).
 void split_messages(const uint8_t* buf, size_t len, std::vector<std::pair<size_t, size_t>>& out);
 
+// One size-prefixed message from owned structs (Relation / Instance / Witness ::write_into, relation.rs:86-137).
+std::vector<uint8_t> write_message(const Message& m);
+
 bool parse_gate_set(const std::string& s, uint16_t& mask, std::string& err);        // relation.rs:144-167
 bool parse_feature_toggle(const std::string& s, uint16_t& mask, std::string& err);  // relation.rs:229-244
 

@@ -34,6 +34,7 @@ enum ValKind : uint8_t {
     V_AND,
     V_XOR,
     V_NOT,
+    V_COPY,  // only recorded in flatten mode (Program::keep_copies); otherwise a copy is an alias
     V_KINDS
 };
 
@@ -109,7 +110,13 @@ public:
     uint32_t constant(const uint8_t* le, size_t n) { cb_count[CB_CONSTANT]++; return push_value(V_CONST, 0, intern_const(le, n)); }
     uint32_t instance() { cb_count[CB_INSTANCE]++; return push_value(V_INSTANCE, 0, n_instance++); }
     uint32_t witness() { cb_count[CB_WITNESS]++; return push_value(V_WITNESS, 0, n_witness++); }
-    uint32_t copy(uint32_t a) { cb_count[CB_COPY]++; return a; }
+    // flatten mode (the reference's IRFlattener, flattening.rs:83-88): a copy is a gate with its own output wire, so
+    // value handles coincide with the wire ids GateBuilder would allocate.  Such a program is written out, not run.
+    bool keep_copies = false;
+    uint32_t copy(uint32_t a) {
+        cb_count[CB_COPY]++;
+        return keep_copies ? push_value(V_COPY, a, 0) : a;
+    }
     uint32_t add(uint32_t a, uint32_t b) { cb_count[CB_ADD]++; return push_value(V_ADD, a, b); }
     uint32_t multiply(uint32_t a, uint32_t b) { cb_count[CB_MUL]++; return push_value(V_MUL, a, b); }
     uint32_t add_constant(uint32_t a, const uint8_t* le, size_t n) { cb_count[CB_ADDC]++; return push_value(V_ADDC, a, intern_const(le, n)); }
