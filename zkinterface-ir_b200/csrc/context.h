@@ -21,6 +21,10 @@ public:
     std::unordered_map<uint64_t, uint32_t> sparse;
     uint64_t live = 0;
 
+    // operand ids of a gate a few iterations ahead: random circuits read the map all over, so the loads are started early
+    void prefetch(uint64_t id) const {
+        if (id < dense.size()) __builtin_prefetch(&dense[id]);
+    }
     uint32_t get(uint64_t id) const {
         if (id < dense.size()) return dense[id];
         if (id < kDenseLimit) return kNone;

@@ -18,6 +18,7 @@
 #include <unordered_map>
 
 #include "context.h"
+#include "file_bytes.h"
 #include "ir.h"
 
 using namespace zkb;
@@ -455,7 +456,15 @@ struct zkb_evaluator {
             known_functions[f.name] = std::move(d);
         }
         Iters iters;
-        for (const auto& g : m.gates) ingest_gate(g, *consts, values, iters, instance_queue, witness_queue, nullptr);
+        const size_t n_gates = m.gates.size();
+        for (size_t i = 0; i < n_gates; i++) {
+            if (i + 8 < n_gates) {
+                const ir::Gate& ahead = m.gates[i + 8];
+                values.prefetch(ahead.w1);
+                values.prefetch(ahead.w2);
+            }
+            ingest_gate(m.gates[i], *consts, values, iters, instance_queue, witness_queue, nullptr);
+        }
     }
 
     // Evaluator::ingest_message, :213-230: errors latch, later messages are skipped
@@ -838,15 +847,6 @@ int list_workspace_files(const char* const* paths, size_t n, std::vector<std::st
     return ZKB_OK;
 }
 
-bool read_whole_file(const std::string& path, std::vector<uint8_t>& data) {
-    FILE* fp = path == "-" ? stdin : fopen(path.c_str(), "rb");
-    if (!fp) return false;
-    uint8_t chunk[1 << 16];
-    size_t got;
-    while ((got = fread(chunk, 1, sizeof chunk, fp)) > 0) data.insert(data.end(), chunk, chunk + got);
-    if (fp != stdin) fclose(fp);
-    return true;
-}
 }  // namespace zkb
 
 extern "C" zkb_evaluator* zkb_evaluator_create(zkb_ctx* backend) { return new zkb_evaluator(backend); }
@@ -923,12 +923,12 @@ extern "C" int zkb_evaluator_ingest_paths(zkb_evaluator* ev, const char* const* 
     int rc = zkb::list_workspace_files(paths, n_paths, files, e);
     if (rc != ZKB_OK) return ev->fail(rc, e);
     for (const auto& f : files) {
-        std::vector<uint8_t> data;
-        if (!zkb::read_whole_file(f, data)) {
+        zkb::FileBytes data;
+        if (!data.open(f)) {
             fprintf(stderr, "Warning: failed to open file %s\n", f.c_str());  // source.rs:132
             continue;
         }
-        rc = zkb_evaluator_ingest_buffer(ev, data.data(), data.size());
+        rc = zkb_evaluator_ingest_buffer(ev, data.data, data.size);
         if (rc != ZKB_OK) return rc;
     }
     return ZKB_OK;

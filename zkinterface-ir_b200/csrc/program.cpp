@@ -2,7 +2,11 @@
 
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 
 namespace zkb {
 
@@ -108,6 +112,14 @@ static inline uint32_t dev_op_of(uint8_t k) {
 }
 
 void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>* live_values) {
+    const bool timing = getenv("ZKB_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  plan %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     const uint32_t n = prog.n_values();
     const uint8_t* kind = prog.kind.data();
     const uint32_t* opa = prog.opa.data();
@@ -116,7 +128,12 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint32_t> level(n);
     std::vector<uint8_t> used(n, 0);  // consumed by another value
     uint32_t max_level = 0;
+    constexpr uint32_t kAhead = 16;  // operands are random earlier values: start their loads a few iterations early
     for (uint32_t v = 0; v < n; v++) {
+        if (v + kAhead < n) {
+            __builtin_prefetch(&level[opa[v + kAhead]]);
+            __builtin_prefetch(&level[opb[v + kAhead] < n ? opb[v + kAhead] : 0]);
+        }
         uint8_t k = kind[v];
         if (k <= V_WITNESS) {
             level[v] = 0;
@@ -133,6 +150,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         level[v] = la + 1;
         if (la + 1 > max_level) max_level = la + 1;
     }
+    lap("levels");
     // earliest assert per value (a value that is non-zero fails at its first assert)
     std::vector<uint32_t> aseq(n, kNoSeq);
     for (size_t s = 0; s < prog.asserts.size(); s++) {
@@ -157,6 +175,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     if (!input_assert_seq.empty() && max_level < 1) max_level = 1;
     n_levels = max_level;
 
+    lap("asserts/observable");
     // counting sort of device ops by (level, opcode)
     const size_t n_keys = (size_t)n_levels * D_OPS;
     std::vector<uint64_t> cnt(n_keys + 1, 0);
@@ -173,6 +192,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     for (uint32_t l = 0; l < n_levels; l++)
         max_level_ops = (uint32_t)std::max<uint64_t>(max_level_ops, level_off[l + 1] - level_off[l]);
 
+    lap("histogram");
     // last wavefront that reads each value (kForever: must stay readable after the run)
     constexpr uint32_t kForever = 0xFFFFFFFFu;
     const bool reuse = !keep_all && slot_reuse;
@@ -180,6 +200,10 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     if (reuse) {
         last_use.assign(n, 0);
         for (uint32_t v = 0; v < n; v++) {
+            if (v + kAhead < n) {
+                __builtin_prefetch(&last_use[opa[v + kAhead]], 1);
+                __builtin_prefetch(&last_use[opb[v + kAhead] < n ? opb[v + kAhead] : 0], 1);
+            }
             uint8_t k = kind[v];
             if (k <= V_WITNESS) continue;
             if (level[v] > last_use[opa[v]]) last_use[opa[v]] = level[v];
@@ -197,6 +221,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint32_t> free_slots;  // kept sorted descending: pop_back hands out the lowest slot first
     readable.assign(n, 0);
 
+    lap("last use");
     // pass 1: place values (order index) and assign slots in placement order
     slot_of_value.assign(n, kNoSlot);
     loads.clear();
@@ -219,6 +244,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint32_t> value_at(n_ops, kNoSlot);
     for (uint32_t v = 0; v < n; v++)
         if (kind[v] > V_WITNESS) value_at[pos_of_value[v]] = v;
+    lap("placement");
     ops.assign(n_ops, GateOp{0, 0, 0, 0});
     op_assert_seq.assign(n_ops, kNoSeq);
     for (int i = 0; i < D_OPS; i++) n_dev_ops[i] = 0;
@@ -229,12 +255,27 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         if (reuse) {  // wavefront l+1 may overwrite everything whose last reader ran in wavefront <= l
             auto& rel = release_after[l];
             if (!rel.empty()) {
+                // free_slots stays sorted descending: sort only the newcomers, then one linear merge
+                std::sort(rel.begin(), rel.end(), std::greater<uint32_t>());
+                const size_t mid = free_slots.size();
                 free_slots.insert(free_slots.end(), rel.begin(), rel.end());
-                std::sort(free_slots.begin(), free_slots.end(), std::greater<uint32_t>());
+                std::inplace_merge(free_slots.begin(), free_slots.begin() + mid, free_slots.end(), std::greater<uint32_t>());
                 std::vector<uint32_t>().swap(rel);
             }
         }
         for (uint64_t i = level_off[l]; i < level_off[l + 1]; i++) {
+            if (i + kAhead < n_ops) {  // values arrive in sorted, i.e. random, order: start their loads early
+                uint32_t va = value_at[i + kAhead];
+                if (va != kNoSlot) {
+                    __builtin_prefetch(&kind[va]);
+                    __builtin_prefetch(&aseq[va]);
+                    __builtin_prefetch(&used[va]);
+                    if (!keep_all) __builtin_prefetch(&observable[va]);
+                    if (reuse) __builtin_prefetch(&last_use[va]);
+                    __builtin_prefetch(&slot_of_value[va], 1);
+                    __builtin_prefetch(&readable[va], 1);
+                }
+            }
             uint32_t v = value_at[i];
             if (v == kNoSlot) continue;  // standalone assert position
             uint32_t meta = dev_op_of(kind[v]);
@@ -262,8 +303,24 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         }
     }
     n_slots = next_slot;
+    lap("slot assignment");
     // pass 2: emit ops with operand slots
     for (uint64_t i = 0; i < n_ops; i++) {
+        if (i + 2 * kAhead < n_ops) {  // two-stage prefetch: the value's record, then its operands' slots
+            uint32_t v2 = value_at[i + 2 * kAhead];
+            if (v2 != kNoSlot) {
+                __builtin_prefetch(&opa[v2]);
+                __builtin_prefetch(&opb[v2]);
+                __builtin_prefetch(&kind[v2]);
+                __builtin_prefetch(&aseq[v2]);
+                __builtin_prefetch(&slot_of_value[v2]);
+            }
+            uint32_t v1 = value_at[i + kAhead];
+            if (v1 != kNoSlot) {
+                __builtin_prefetch(&slot_of_value[opa[v1]]);
+                if (opb[v1] < n) __builtin_prefetch(&slot_of_value[opb[v1]]);
+            }
+        }
         uint32_t v = value_at[i];
         if (v == kNoSlot) continue;
         uint8_t k = kind[v];
@@ -295,6 +352,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             n_dev_ops[D_ASSERT]++;
         }
     }
+    lap("emit");
     const uint64_t E = prog.binary ? 1 : (uint64_t)prog.nlimb * 4;
     const uint64_t* c = prog.cb_count;
     algo_bytes_per_witness = 3 * E * (c[CB_ADD] + c[CB_MUL] + c[CB_AND] + c[CB_XOR]) +

@@ -19,6 +19,7 @@
 
 #include "../../include/zkb.h"
 #include "bigu.h"
+#include "file_bytes.h"
 #include "ir.h"
 
 using namespace zkb;
@@ -630,7 +631,6 @@ extern "C" int zkb_validator_ingest_buffer(zkb_validator* v, const uint8_t* buf,
 namespace zkb {
 // shared with evaluator.cpp: Source::from_dirs_and_files ordering (source.rs:64-89, 165-193)
 int list_workspace_files(const char* const* paths, size_t n, std::vector<std::string>& out, std::string& err);
-bool read_whole_file(const std::string& path, std::vector<uint8_t>& data);
 }  // namespace zkb
 
 extern "C" int zkb_validator_ingest_paths(zkb_validator* v, const char* const* paths, size_t n_paths) {
@@ -639,12 +639,12 @@ extern "C" int zkb_validator_ingest_paths(zkb_validator* v, const char* const* p
     int rc = zkb::list_workspace_files(paths, n_paths, files, e);
     if (rc != ZKB_OK) return v->fail(rc, e);
     for (const auto& f : files) {
-        std::vector<uint8_t> data;
-        if (!zkb::read_whole_file(f, data)) {
+        zkb::FileBytes data;
+        if (!data.open(f)) {
             fprintf(stderr, "Warning: failed to open file %s\n", f.c_str());  // source.rs:132
             continue;
         }
-        rc = zkb_validator_ingest_buffer(v, data.data(), data.size());
+        rc = zkb_validator_ingest_buffer(v, data.data, data.size);
         if (rc != ZKB_OK) return rc;
     }
     return ZKB_OK;
