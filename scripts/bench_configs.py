@@ -150,14 +150,16 @@ def c3_sieve(log2_gates):
         open(os.path.join(d, "002_relation.sieve"), "wb").write(rel)
         best = None
         for _ in range(3):
+            tc = time.perf_counter()
+            be = z.GpuBackend(0)                 # CUDA context creation: paid once per process, reported apart
             t0 = time.perf_counter()
-            e = z.Evaluator(z.GpuBackend(0))
+            e = z.Evaluator(be)
             e.ingest_source(z.Source.from_directory(d))
             t1 = time.perf_counter()
             v = e.get_violations()
             t2 = time.perf_counter()
             assert v == []
-            cur = {"ingest_s": t1 - t0, "levelize_upload_evaluate_s": t2 - t1, "total_s": t2 - t0,
+            cur = {"cuda_context_s": t0 - tc, "ingest_s": t1 - t0, "levelize_upload_evaluate_s": t2 - t1, "total_s": t2 - t0,
                    "device_ms": e.backend.timing()["total_ms"]}
             if best is None or cur["total_s"] < best["total_s"]:
                 best = cur

@@ -511,6 +511,9 @@ struct zkb_evaluator {
         std::string first_error;
         bool have_error = false;
         Program& p = prog();
+        const bool timing = getenv("ZKB_TIMING") != nullptr;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_begin = now();
         if (p.field_set && p.n_values() > 0) {
             if (!c->finalized) {
                 c->live_values.clear();
@@ -518,6 +521,7 @@ struct zkb_evaluator {
                 int rc = ctx_finalize(c, 0);
                 if (rc != ZKB_OK) return fail(rc, c->err);
             }
+            if (timing) fprintf(stderr, "finish: live wires + levelize + program upload %.3f s\n", now() - t_begin);
             // pack the queued streams: one statement = batch of 1
             size_t stride = (size_t)p.nlimb * 4;
             auto widen = [&](const std::vector<std::vector<uint8_t>>& vals) {
@@ -540,8 +544,10 @@ struct zkb_evaluator {
             };
             std::vector<uint8_t> ib = pack(instance_values, p.n_instance), wb = pack(witness_values, p.n_witness);
             zkb_verdict v;
+            const double t_eval = now();
             int rc = zkb_evaluate(c, ib.data(), 0, wb.data(), 0, (uint32_t)stride, 1, &v);
             if (rc != ZKB_OK) return fail(rc, c->err);
+            if (timing) fprintf(stderr, "finish: zkb_evaluate (allocations, input upload, kernels, verdict) %.3f s\n", now() - t_eval);
             if (v.first_fail_seq != UINT64_MAX) {
                 uint64_t w = p.asserts[v.first_fail_seq].src_wire;
                 first_error = "Wire_" + u64s(w) + " (may be weighted) should be 0, while it is not";  // :357-362
