@@ -170,8 +170,11 @@ __device__ __forceinline__ void load_operands(uint32_t* a, uint32_t* b, const ui
     }
 }
 
+#ifndef ZKB_LEVEL_PIPE_MIN_CTAS
+#define ZKB_LEVEL_PIPE_MIN_CTAS 4  // 64 registers: 4 resident CTAs per SM measured 6 % faster than 3 (scripts/ab_min_ctas.sh)
+#endif
 template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, ZKB_LEVEL_PIPE_MIN_CTAS)
 k_level_pipe(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
              const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
     const uint64_t total = n_ops << g.log2_wt;

@@ -176,8 +176,11 @@ __device__ __forceinline__ void lc_dot(uint32_t* acc, TermStream<N>& st, uint32_
 }
 
 // thread <-> (sorted row, assignment lane), lane fastest
+#ifndef ZKB_R1CS_MIN_CTAS
+#define ZKB_R1CS_MIN_CTAS 3
+#endif
 template <int N>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, ZKB_R1CS_MIN_CTAS)
 k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, const uint32_t* __restrict__ row_ids,
              const uint32_t* __restrict__ coefs, const uint32_t* __restrict__ z, uint64_t n_rows, uint64_t n_slices,
              uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
