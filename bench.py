@@ -125,6 +125,17 @@ def workload_name(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON: anything a library prints on fd 1 while the job runs (NCCL's version
+    # banner, build chatter) is routed to stderr, and fd 1 is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -159,7 +170,7 @@ def main():
             "e2e": {"value": rate, "unit": "gate-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of zki_sieve 3.0.0 Evaluator<PlaintextBackend> (oracle/plaintext_flat.c), not the Rust binary",
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
@@ -331,7 +342,7 @@ def main():
             "wall_ms_per_step": wall_ms / args.steps,
             "verdicts": {"true": int((ff >= (1 << 40)).sum()), "false": int((ff < (1 << 40)).sum())},
         }
-        print(json.dumps(line))
+        emit(line)
     be.close()
     if world > 1:
         dist.destroy_process_group()
