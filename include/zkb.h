@@ -271,6 +271,19 @@ uint64_t zkb_validator_live_wires(zkb_validator* v);
 int zkb_validator_set_limits(zkb_validator* v, uint64_t max_steps);
 const char* zkb_validator_last_error(zkb_validator* v);
 
+/* ------------------------------------------------------------------ 4c. Stats
+ * Mirror of `Stats` (rust/src/consumers/stats.rs:11-287): what the `metrics` / `valid-eval-metrics` verbs print
+ * (cli.rs:322-363).  zkb_metrics_json: the JSON `serde_json::to_writer_pretty(&stats)` writes (fields in declaration
+ * order; `functions` is a HashMap in the reference, so its key order is unspecified there, sorted here).  Host only. */
+typedef struct zkb_metrics zkb_metrics;
+zkb_metrics* zkb_metrics_create(void);
+void zkb_metrics_destroy(zkb_metrics* m);
+int zkb_metrics_ingest_message(zkb_metrics* m, const uint8_t* buf, size_t len);
+int zkb_metrics_ingest_buffer(zkb_metrics* m, const uint8_t* buf, size_t len);
+int zkb_metrics_ingest_paths(zkb_metrics* m, const char* const* paths, size_t n_paths);
+const char* zkb_metrics_json(zkb_metrics* m);
+const char* zkb_metrics_last_error(zkb_metrics* m);
+
 /* ------------------------------------------------------------------ 5. R1CS (Az o Bz = Cz)
  * The satisfiability check that `zkif-to-ir` + `evaluate` performs gate by gate on an R1CS
  * (rust/src/producers/from_r1cs.rs:110-125), done as three CSR sparse mod-p mat-vecs and a

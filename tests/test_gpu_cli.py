@@ -53,3 +53,22 @@ def test_python_source_on_the_same_workspaces():
         files = [os.path.join(path, f) for f in sorted(os.listdir(path)) if f.endswith(".sieve")]
         e = z.Evaluator.from_messages(z.Source.from_dirs_and_files(files), device=0)
         assert e.get_violations() == want
+
+
+def test_cli_valid_eval_metrics_and_stdin():
+    """cli.rs:333-363: validator + evaluator + stats over the same messages; `-` reads the statement from stdin"""
+    import json
+    from oracle import stats as os_
+    ws = os.path.join(GOLDEN, "example_incorrect")
+    r = subprocess.run([CLI, "valid-eval-metrics", ws], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "The statement is COMPLIANT with the specification!" in r.stderr
+    assert "The statement is NOT TRUE!" in r.stderr and "- Wire_9 (may be weighted) should be 0, while it is not" in r.stderr
+    msgs = [m for n in sorted(os.listdir(ws)) for m in F.read_messages(open(os.path.join(ws, n), "rb").read())]
+    assert json.loads(r.stdout) == os_.stats(msgs).as_dict()
+    stream = b"".join(open(os.path.join(GOLDEN, "example", n), "rb").read() for n in sorted(os.listdir(os.path.join(GOLDEN, "example"))))
+    r = subprocess.run([CLI, "valid-eval-metrics", "-"], input=stream, capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert b"The statement is TRUE!" in r.stderr and b"COMPLIANT" in r.stderr
+    r = subprocess.run([CLI, "evaluate", "-"], input=stream, capture_output=True, timeout=120)
+    assert r.returncode == 0 and b"The statement is TRUE!" in r.stderr

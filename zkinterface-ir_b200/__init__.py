@@ -74,7 +74,8 @@ EXPORTED = [
     "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_evaluator_set_flatten", "zkb_evaluator_flatten",
     "zkb_evaluator_flatten_to_dir", "zkb_validator_create", "zkb_validator_destroy", "zkb_validator_ingest_message",
     "zkb_validator_ingest_buffer", "zkb_validator_ingest_paths", "zkb_validator_get_violations", "zkb_validator_violation",
-    "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
+    "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_metrics_create", "zkb_metrics_destroy", "zkb_metrics_ingest_message",
+    "zkb_metrics_ingest_buffer", "zkb_metrics_ingest_paths", "zkb_metrics_json", "zkb_metrics_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
     "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_write_flat_relation",
 ]
 
@@ -146,6 +147,13 @@ _sig("zkb_validator_how_many_violations", C.c_size_t, _vp)
 _sig("zkb_validator_live_wires", _u64, _vp)
 _sig("zkb_validator_set_limits", _i, _vp, _u64)
 _sig("zkb_validator_last_error", C.c_char_p, _vp)
+_sig("zkb_metrics_create", _vp)
+_sig("zkb_metrics_destroy", None, _vp)
+_sig("zkb_metrics_ingest_message", _i, _vp, _u8p, _sz)
+_sig("zkb_metrics_ingest_buffer", _i, _vp, _u8p, _sz)
+_sig("zkb_metrics_ingest_paths", _i, _vp, C.POINTER(C.c_char_p), _sz)
+_sig("zkb_metrics_json", C.c_char_p, _vp)
+_sig("zkb_metrics_last_error", C.c_char_p, _vp)
 _sig("zkb_r1cs_load", _i, _vp, C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), C.POINTER(ZkbCsr), _u8p, _sz, _u64, _u64)
 _sig("zkb_r1cs_check", _i, _vp, _u8p, _u64, _u32, _u32, _vp)
 _sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
@@ -617,3 +625,39 @@ class Validator:
         n = C.c_size_t()
         self._chk(_lib.zkb_validator_get_violations(self._v, C.byref(n)))
         return [_lib.zkb_validator_violation(self._v, i).decode("utf-8", "replace") for i in range(n.value)]
+
+
+class Stats:
+    """`Stats` (rust/src/consumers/stats.rs) over `.sieve` bytes; host only."""
+
+    def __init__(self):
+        self._m = _lib.zkb_metrics_create()
+
+    def close(self):
+        if getattr(self, "_m", None):
+            _lib.zkb_metrics_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != ZKB_OK:
+            raise ZkbError(rc, _lib.zkb_metrics_last_error(self._m).decode("utf-8", "replace"))
+
+    def ingest_message(self, buf: bytes):
+        self._chk(_lib.zkb_metrics_ingest_message(self._m, _buf(buf), len(buf)))
+
+    def ingest_source(self, source: Source):
+        if source.buffers is not None:
+            for b in source.buffers:
+                self._chk(_lib.zkb_metrics_ingest_buffer(self._m, _buf(b), len(b)))
+        else:
+            arr = (C.c_char_p * len(source.paths))(*[p.encode() for p in source.paths])
+            self._chk(_lib.zkb_metrics_ingest_paths(self._m, arr, len(source.paths)))
+
+    def to_json_pretty(self) -> str:
+        return _lib.zkb_metrics_json(self._m).decode("utf-8")

@@ -2,6 +2,8 @@
 //   zkb evaluate [--device N] <workspace dir | *.sieve ... | ->       cli.rs:130, 315-320, 557-571
 //   zkb flatten --out <dir | -> <workspace dir | *.sieve ... | ->     cli.rs:442-472 (host only)
 //   zkb validate <workspace dir | *.sieve ... | ->                    cli.rs:297-313 (host only)
+//   zkb metrics <workspace dir | *.sieve ... | ->                     cli.rs:322-330 (host only; JSON on stdout)
+//   zkb valid-eval-metrics [--device N] <paths...>                    cli.rs:333-363 (all three in one go)
 // `evaluate` / `validate` print exactly what the reference prints on stderr ("The statement is TRUE!" /
 // "The statement is COMPLIANT with the specification!" / the violation lists) and exit non-zero with
 // "Found N violations." when there are any.
@@ -18,8 +20,10 @@ static int usage(const char* argv0) {
     fprintf(stderr,
             "usage: %s evaluate [--device N] <paths...>\n"
             "       %s flatten --out <dir|-> <paths...>\n"
-            "       %s validate <paths...>\n",
-            argv0, argv0, argv0);
+            "       %s validate <paths...>\n"
+            "       %s metrics <paths...>\n"
+            "       %s valid-eval-metrics [--device N] <paths...>\n",
+            argv0, argv0, argv0, argv0, argv0);
     return 2;
 }
 
@@ -108,6 +112,67 @@ int main(int argc, char** argv) {
         int status = print_violations(n, v, "COMPLIANT with the specification");
         zkb_validator_destroy(val);
         return status;
+    }
+    if (verb == "metrics") {
+        zkb_metrics* m = zkb_metrics_create();
+        if (zkb_metrics_ingest_paths(m, paths.data(), paths.size()) != ZKB_OK) {
+            fprintf(stderr, "Error: %s\n", zkb_metrics_last_error(m));
+            return 1;
+        }
+        printf("%s\n", zkb_metrics_json(m));
+        zkb_metrics_destroy(m);
+        return 0;
+    }
+    if (verb == "valid-eval-metrics") {  // main_valid_eval_metrics: validator (as prover), evaluator and stats on the same messages
+        zkb_validator* val = zkb_validator_create(1);
+        zkb_metrics* m = zkb_metrics_create();
+        zkb_ctx* ctx = zkb_create(device);
+        if (zkb_last_error(ctx)[0]) {
+            fprintf(stderr, "Error: %s\n", zkb_last_error(ctx));
+            return 1;
+        }
+        zkb_evaluator* ev = zkb_evaluator_create(ctx);
+        const bool from_stdin = paths.size() == 1 && strcmp(paths[0], "-") == 0;
+        std::vector<uint8_t> piped;  // stdin can be read only once: the three consumers share the bytes
+        if (from_stdin) {
+            uint8_t chunk[1 << 16];
+            size_t got;
+            while ((got = fread(chunk, 1, sizeof chunk, stdin)) > 0) piped.insert(piped.end(), chunk, chunk + got);
+        }
+        int rc = from_stdin ? zkb_validator_ingest_buffer(val, piped.data(), piped.size())
+                            : zkb_validator_ingest_paths(val, paths.data(), paths.size());
+        if (rc != ZKB_OK) {
+            fprintf(stderr, "Error: %s\n", zkb_validator_last_error(val));
+            return 1;
+        }
+        rc = from_stdin ? zkb_evaluator_ingest_buffer(ev, piped.data(), piped.size())
+                        : zkb_evaluator_ingest_paths(ev, paths.data(), paths.size());
+        if (rc != ZKB_OK) {
+            fprintf(stderr, "Error: %s\n", zkb_evaluator_last_error(ev));
+            return 1;
+        }
+        rc = from_stdin ? zkb_metrics_ingest_buffer(m, piped.data(), piped.size())
+                        : zkb_metrics_ingest_paths(m, paths.data(), paths.size());
+        if (rc != ZKB_OK) {
+            fprintf(stderr, "Error: %s\n", zkb_metrics_last_error(m));
+            return 1;
+        }
+        size_t n1 = 0, n2 = 0;
+        if (zkb_validator_get_violations(val, &n1) != ZKB_OK) {
+            fprintf(stderr, "Error: %s\n", zkb_validator_last_error(val));
+            return 1;
+        }
+        if (zkb_evaluator_get_violations(ev, &n2) != ZKB_OK) {
+            fprintf(stderr, "Error: %s\n", zkb_evaluator_last_error(ev));
+            return 1;
+        }
+        std::vector<std::string> v1, v2;
+        for (size_t i = 0; i < n1; i++) v1.push_back(zkb_validator_violation(val, i));
+        for (size_t i = 0; i < n2; i++) v2.push_back(zkb_evaluator_violation(ev, i));
+        int res1 = print_violations(n1, v1, "COMPLIANT with the specification");
+        int res2 = print_violations(n2, v2, "TRUE");
+        printf("%s\n", zkb_metrics_json(m));
+        return res1 ? res1 : res2;
     }
     return usage(argv[0]);
 }
