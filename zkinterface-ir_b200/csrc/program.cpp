@@ -98,6 +98,34 @@ std::vector<uint8_t> Program::minus_one_le() const {
     return out;
 }
 
+// Slots released after one wavefront arrive as a few ASCENDING runs (one per wavefront that allocated them: a
+// wavefront hands out slots in increasing order), so ordering them is a handful of linear merges, not a sort.
+struct ReleaseList {
+    std::vector<uint32_t> slots;
+    std::vector<size_t> run_start;  // offsets where a new ascending run begins
+    uint32_t last_writer = 0xFFFFFFFFu;
+    void push(uint32_t slot, uint32_t writer) {
+        if (writer != last_writer) {
+            run_start.push_back(slots.size());
+            last_writer = writer;
+        }
+        slots.push_back(slot);
+    }
+    void merge_runs() {
+        while (run_start.size() > 1) {
+            std::vector<size_t> next;
+            for (size_t r = 0; r < run_start.size(); r += 2) {
+                next.push_back(run_start[r]);
+                if (r + 1 < run_start.size()) {
+                    size_t end = r + 2 < run_start.size() ? run_start[r + 2] : slots.size();
+                    std::inplace_merge(slots.begin() + run_start[r], slots.begin() + run_start[r + 1], slots.begin() + end);
+                }
+            }
+            run_start.swap(next);
+        }
+    }
+};
+
 static inline uint32_t dev_op_of(uint8_t k) {
     switch (k) {
         case V_ADD: return D_ADD;
@@ -217,8 +245,10 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     }
     // slots released once wavefront l has run (re-usable from wavefront l + 1 on: inside one launch a slot is
     // never both read and written)
-    std::vector<std::vector<uint32_t>> release_after(reuse ? (size_t)n_levels + 1 : 0);
-    std::vector<uint32_t> free_slots;  // kept sorted descending: pop_back hands out the lowest slot first
+    std::vector<ReleaseList> release_after(reuse ? (size_t)n_levels + 1 : 0);
+    std::vector<uint32_t> free_slots;  // ascending from free_head on: the lowest free slot is handed out first
+    size_t free_head = 0;
+    constexpr uint32_t kInputWriter = 0xFFFFFFFEu;
     readable.assign(n, 0);
 
     lap("last use");
@@ -231,7 +261,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             slot_of_value[v] = next_slot;
             loads.push_back(InputLoad{next_slot, kind[v], opb[v], 0});
             readable[v] = 1;  // inputs are read back from the raw streams / constant pool
-            if (reuse && last_use[v] != kForever) release_after[last_use[v]].push_back(next_slot);
+            if (reuse && last_use[v] != kForever) release_after[last_use[v]].push(next_slot, kInputWriter);
             next_slot++;
         }
     std::vector<uint64_t> pos_of_value(n, 0);
@@ -253,14 +283,15 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     n_raw_ops = 0;
     for (uint32_t l = 0; l < n_levels; l++) {
         if (reuse) {  // wavefront l+1 may overwrite everything whose last reader ran in wavefront <= l
-            auto& rel = release_after[l];
-            if (!rel.empty()) {
-                // free_slots stays sorted descending: sort only the newcomers, then one linear merge
-                std::sort(rel.begin(), rel.end(), std::greater<uint32_t>());
-                const size_t mid = free_slots.size();
-                free_slots.insert(free_slots.end(), rel.begin(), rel.end());
-                std::inplace_merge(free_slots.begin(), free_slots.begin() + mid, free_slots.end(), std::greater<uint32_t>());
-                std::vector<uint32_t>().swap(rel);
+            ReleaseList& rel = release_after[l];
+            if (!rel.slots.empty()) {
+                rel.merge_runs();
+                std::vector<uint32_t> merged;
+                merged.resize(rel.slots.size() + (free_slots.size() - free_head));
+                std::merge(free_slots.begin() + free_head, free_slots.end(), rel.slots.begin(), rel.slots.end(), merged.begin());
+                free_slots.swap(merged);
+                free_head = 0;
+                ReleaseList().slots.swap(rel.slots);
             }
         }
         for (uint64_t i = level_off[l]; i < level_off[l + 1]; i++) {
@@ -288,16 +319,15 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                 meta |= F_NOSTORE;
             } else {
                 uint32_t slot;
-                if (!free_slots.empty()) {
-                    slot = free_slots.back();
-                    free_slots.pop_back();
+                if (free_head < free_slots.size()) {
+                    slot = free_slots[free_head++];
                     n_reused_slots++;
                 } else {
                     slot = next_slot++;
                 }
                 slot_of_value[v] = slot;
                 readable[v] = keep_all || observable[v];
-                if (reuse && last_use[v] != kForever) release_after[std::max(last_use[v], l + 1)].push_back(slot);
+                if (reuse && last_use[v] != kForever) release_after[std::max(last_use[v], l + 1)].push(slot, l);
             }
             meta_of[i] = meta;
         }
