@@ -101,15 +101,6 @@ k_r1cs_load_z(const uint8_t* __restrict__ zraw, uint64_t set_stride, uint32_t st
     }
 }
 
-template <int N>
-__device__ __forceinline__ void prefetch_elem_l2(const uint32_t* z, uint32_t var, uint32_t lane, uint32_t log2_wt) {
-#pragma unroll
-    for (int c = 0; c < Elem<N>::NC; c++) {
-        const uint32_t* p = z + ((((size_t)var * Elem<N>::NC + c) << log2_wt) + lane) * Elem<N>::CW;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-}
-
 // The term stream of one (row, assignment lane): terms are consumed in order A_r, B_r, C_r.  Four terms are in
 // flight per thread: the {col, coef} pair three terms ahead, an L2 prefetch of z two terms ahead, and the z limbs
 // of the next term in registers while the current term's integer chain runs.
