@@ -309,9 +309,11 @@ int zkb_r1cs_run(zkb_ctx* ctx, zkb_verdict* out);
  * field_throughput: register-resident dependent chains of `iters` operations per thread -> operations/s. */
 int zkb_debug_field_ops(zkb_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint64_t n);
 int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops_per_second);
-/* Device layout zkb_r1cs_load built (host-only contexts): counts = {slices, term groups, rows}; slices: 4 x uint32 per slice
- * {first group, KA, KB, KC}; terms: 32 x {col, coefficient tag} per group (tag 0xFFFFFFFF: padding / zero coefficient,
- * 0xFFFFFFFE: coefficient one, else the table index); row_ids: sorted position -> row.  NULL pointers are skipped. */
+/* Device layout of kind 0 (tiles of fewer than 32 assignments: ones and general terms in separate classes) or 1 (wider
+ * tiles: one class per matrix, ones tagged inside it), host-only contexts: counts = {slices, term groups, rows}; slices: 4 x uint32 per slice
+ * {first group, A ones | A general << 16, B ones | B general << 16, C ones | C general << 16} (group counts per term
+ * class); terms: 32 x {col, coefficient tag} per group (tag 0xFFFFFFFF: padding, 0xFFFFFFFE: coefficient one, else the
+ * table index; zero coefficients are dropped); row_ids: sorted position -> row.  NULL pointers are skipped. */
 /* FlatBuffers reader -> owned structs -> writer on one size-prefixed message (round-trip tests); *out is valid until
  * the next call on this thread. */
 int zkb_debug_rewrite_message(zkb_ctx* ctx, const uint8_t* buf, size_t len, const uint8_t** out, size_t* out_len);
@@ -320,7 +322,7 @@ int zkb_debug_rewrite_message(zkb_ctx* ctx, const uint8_t* buf, size_t len, cons
 int zkb_debug_write_flat_relation(zkb_ctx* ctx, const uint8_t* modulus_le, size_t modulus_len, int is_boolean,
                                   const zkb_gate* gates, uint64_t n_gates, const uint8_t* const_pool_le, size_t const_stride,
                                   uint64_t n_consts, const uint8_t** out, size_t* out_len);
-int zkb_debug_r1cs_layout(zkb_ctx* ctx, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids);
+int zkb_debug_r1cs_layout(zkb_ctx* ctx, int kind, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids);
 
 #ifdef __cplusplus
 }

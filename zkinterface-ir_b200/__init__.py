@@ -160,7 +160,7 @@ _sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
 _sig("zkb_r1cs_run", _i, _vp, _vp)
 _sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
 _sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
-_sig("zkb_debug_r1cs_layout", _i, _vp, _u64p, _vp, _vp, _vp)
+_sig("zkb_debug_r1cs_layout", _i, _vp, _i, _u64p, _vp, _vp, _vp)
 _sig("zkb_debug_rewrite_message", _i, _vp, _u8p, _sz, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
 _sig("zkb_debug_write_flat_relation", _i, _vp, _u8p, _sz, _i, _vp, _u64, _u8p, _sz, _u64, C.POINTER(C.c_void_p),
      C.POINTER(C.c_size_t))
@@ -451,14 +451,14 @@ class GpuBackend:
         self._chk(_lib.zkb_debug_rewrite_message(self._c, _buf(buf), len(buf), C.byref(ptr), C.byref(n)))
         return C.string_at(ptr.value, n.value)
 
-    def r1cs_layout(self):
+    def r1cs_layout(self, kind: int = 0):
         """(slices uint32[n,4], terms uint32[groups,32,2], row_ids uint32[rows]) of a host-only context"""
         cnt = (C.c_uint64 * 3)()
-        self._chk(_lib.zkb_debug_r1cs_layout(self._c, cnt, None, None, None))
+        self._chk(_lib.zkb_debug_r1cs_layout(self._c, kind, cnt, None, None, None))
         slices = np.zeros((cnt[0], 4), dtype=np.uint32)
         terms = np.zeros((cnt[1], 32, 2), dtype=np.uint32)
         rows = np.zeros(cnt[2], dtype=np.uint32)
-        self._chk(_lib.zkb_debug_r1cs_layout(self._c, cnt, slices.ctypes.data, terms.ctypes.data, rows.ctypes.data))
+        self._chk(_lib.zkb_debug_r1cs_layout(self._c, kind, cnt, slices.ctypes.data, terms.ctypes.data, rows.ctypes.data))
         return slices, terms, rows
 
     def r1cs_check(self, z: np.ndarray) -> np.ndarray:

@@ -72,16 +72,6 @@ __device__ __forceinline__ void load_elem_coherent(uint32_t* r, const uint32_t* 
     }
 }
 
-// L2 prefetch of an element that will be loaded a few iterations later (no destination registers)
-template <int N>
-__device__ __forceinline__ void prefetch_elem_l2(const uint32_t* z, uint32_t var, uint32_t lane, uint32_t log2_wt) {
-#pragma unroll
-    for (int c = 0; c < Elem<N>::NC; c++) {
-        const uint32_t* p = z + ((((size_t)var * Elem<N>::NC + c) << log2_wt) + lane) * Elem<N>::CW;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-}
-
 template <int N>
 __device__ __forceinline__ void store_elem(uint32_t* store, uint32_t slot, uint32_t lane, uint32_t log2_wt, const uint32_t* r) {
     using V = typename Vec<Elem<N>::CW>::T;

@@ -28,11 +28,12 @@ using namespace zkb;
 
 namespace zkb {
 
-// Device layout of the three matrices: SELL-32-sigma (sliced ELLPACK).  Rows are sorted by (|A_r|, |B_r|, |C_r|),
+// Device layout of the three matrices: SELL-32-sigma (sliced ELLPACK).  Rows are sorted by their six class counts,
 // heaviest first, inside windows of `sigma` consecutive rows (locality of the variables a window touches is kept,
 // e.g. the slack variables of neighbouring rows stay in the same L2-resident region) and cut into slices of 32
-// sorted rows.  A slice stores KA + KB + KC term groups (K* = the slice's largest LC of that matrix); a group is
-// 32 x {col, coef} with the row of the slice as the fast index, so
+// sorted rows.  The terms of a row fall in six classes — A, B, C times {coefficient one, general coefficient} — and a
+// slice stores K_class groups per class (the slice's largest count of that class); a group is 32 x {col, coef}
+// with the row of the slice as the fast index, so
 //   - with ONE assignment a warp works on the 32 rows of a slice: every group is one coalesced 256-byte load
 //     and all lanes run the same trip counts;
 //   - with a batch of assignments a warp works on one row for 32 assignments: the term is a broadcast load and
@@ -41,12 +42,29 @@ namespace zkb {
 constexpr uint32_t T_PAD = 0xFFFFFFFFu;  // no term
 constexpr uint32_t T_ONE = 0xFFFFFFFEu;  // coefficient 1: the multiplication is skipped
 
-struct R1csDev {
-    uint64_t n_rows = 0, n_vars = 0, nnz[3] = {0, 0, 0};
+// One sliced layout.  Two are kept, built on first use:
+//   kind 0 (tiles of < 32 assignments, in particular ONE assignment): six classes, sigma = 262144 rows — the lanes of a
+//          warp are different rows, so ones and general terms are separated and sorted on;
+//   kind 1 (tiles of >= 32 assignments): a warp is one row, nothing diverges: one class per matrix (ones tagged inside
+//          it), sorted by |A_r|, |B_r|, |C_r| only, sigma = 16384 rows so that the window's variables x the tile width
+//          stay L2-resident.
+struct R1csLayout {
+    bool built = false;
     uint64_t n_slices = 0, n_groups = 0;
-    uint4* d_slices = nullptr;     // {first group, KA, KB, KC}
+    uint4* d_slices = nullptr;     // {first group, A ones | A general << 16, B ones | B general << 16, C ones | C general << 16}
     uint2* d_terms = nullptr;      // [group][32] {col, coefficient index | T_ONE | T_PAD}
     uint32_t* d_row_ids = nullptr; // sorted position -> original row (the verdict names the original row)
+    // host copies (host-only contexts: zkb_debug_r1cs_layout)
+    std::vector<uint4> h_slices;
+    std::vector<uint2> h_terms;
+    std::vector<uint32_t> h_row_ids;
+};
+
+struct R1csDev {
+    uint64_t n_rows = 0, n_vars = 0, nnz[3] = {0, 0, 0};
+    // the system as loaded, zero coefficients dropped, coefficient one tagged (the layouts are built from this)
+    std::vector<uint32_t> h_rp[3], h_col[3], h_tag[3];
+    R1csLayout layout[2];
     uint32_t* d_coefs = nullptr;   // Montgomery form, nlimb limbs each
     uint32_t n_coefs = 0;
     uint32_t* d_z = nullptr;       // [var][chunk][lane][CW] Montgomery
@@ -58,18 +76,16 @@ struct R1csDev {
     uint32_t* d_first_fail = nullptr;
     size_t first_fail_cap = 0;
     bool uploaded = false;
-    // host copies of the layout (inspection: zkb_debug_r1cs_layout)
-    std::vector<uint4> h_slices;
-    std::vector<uint2> h_terms;
-    std::vector<uint32_t> h_row_ids;
 };
 
 void r1cs_free(zkb_ctx* c) {
     R1csDev* r = c->r1cs;
     if (!r) return;
-    cudaFree(r->d_slices);
-    cudaFree(r->d_terms);
-    cudaFree(r->d_row_ids);
+    for (auto& l : r->layout) {
+        cudaFree(l.d_slices);
+        cudaFree(l.d_terms);
+        cudaFree(l.d_row_ids);
+    }
     cudaFree(r->d_coefs);
     cudaFree(r->d_z);
     cudaFree(r->d_zraw);
@@ -101,65 +117,80 @@ k_r1cs_load_z(const uint8_t* __restrict__ zraw, uint64_t set_stride, uint32_t st
     }
 }
 
-// The term stream of one (row, assignment lane): terms are consumed in order A_r, B_r, C_r.  Four terms are in
-// flight per thread: the {col, coef} pair three terms ahead, an L2 prefetch of z two terms ahead, and the z limbs
-// of the next term in registers while the current term's integer chain runs.
+// The term stream of one (row, assignment lane): terms are consumed in storage order (A ones, A general, B ..., C ...).
+// Loads in flight per thread: the {col, coef} pair three terms ahead and the z limbs of the next kZDepth terms in
+// registers while the current term's integer chain runs (the gathers are random 32-byte sectors of a z that does not
+// fit in L2: their latency is what the kernel waits on, `long_scoreboard` in ncu).  `prefetch.global.L2` of later
+// terms was measured and made things worse at every distance (scripts/ab_r1cs_prefetch.sh: 0.535 ms without,
+// 0.561 / 0.629 / 0.649 / 0.662 ms at 3 / 6 / 10 / 16 terms ahead), like in the level kernel.
+#ifndef ZKB_R1CS_ZDEPTH
+#define ZKB_R1CS_ZDEPTH 1
+#endif
 template <int N>
 struct TermStream {
+    static constexpr int kZDepth = ZKB_R1CS_ZDEPTH;  // 1 or 2
     const uint2* tp;  // this row's column of the slice: term k at tp[32 * k]
     const uint32_t* z;
     uint32_t lane, log2_wt, k, K;
     uint2 t0, t1, t2;
-    uint32_t z0[N], z1[N];
+    uint32_t z0[N], z1[N], z2[kZDepth == 2 ? N : 1];
 
     __device__ __forceinline__ uint2 fetch(uint32_t i) const { return i < K ? __ldg(tp + (size_t)32 * i) : make_uint2(0, T_PAD); }
+    __device__ __forceinline__ void gather(uint32_t* dst, const uint2& t) const {
+#pragma unroll
+        for (int i = 0; i < N; i++) dst[i] = 0;
+        if (t.y != T_PAD) load_elem<N>(dst, z, t.x, lane, log2_wt);
+    }
     __device__ __forceinline__ void start(const uint2* tp_, const uint32_t* z_, uint32_t lane_, uint32_t log2_wt_, uint32_t K_) {
         tp = tp_; z = z_; lane = lane_; log2_wt = log2_wt_; k = 0; K = K_;
         t0 = fetch(0);
         t1 = fetch(1);
         t2 = fetch(2);
-#pragma unroll
-        for (int i = 0; i < N; i++) z0[i] = 0;
-        if (t0.y != T_PAD) load_elem<N>(z0, z, t0.x, lane, log2_wt);
-        if (t1.y != T_PAD) prefetch_elem_l2<N>(z, t1.x, lane, log2_wt);
+        gather(z0, t0);
+        if (kZDepth == 2) gather(z1, t1);
     }
     // issue the loads of the following terms; call before the current term's arithmetic
     __device__ __forceinline__ void prefetch(uint2& t3) {
         t3 = fetch(k + 3);
-        if (t2.y != T_PAD) prefetch_elem_l2<N>(z, t2.x, lane, log2_wt);
-#pragma unroll
-        for (int i = 0; i < N; i++) z1[i] = 0;
-        if (t1.y != T_PAD) load_elem<N>(z1, z, t1.x, lane, log2_wt);
+        if (kZDepth == 2) gather(z2, t2);
+        else gather(z1, t1);
     }
     __device__ __forceinline__ void advance(const uint2& t3) {
 #pragma unroll
-        for (int i = 0; i < N; i++) z0[i] = z1[i];
+        for (int i = 0; i < N; i++) {
+            z0[i] = z1[i];
+            if (kZDepth == 2) z1[i] = z2[i];
+        }
         t0 = t1; t1 = t2; t2 = t3;
         k++;
     }
 };
 
-// acc = sum of the next `n` terms of the stream (Montgomery residues)
+// acc = sum of the next n_one terms with coefficient one, then of the next n_gen terms with a general coefficient
+// (Montgomery residues).  The two kinds are stored apart so that the lanes of a warp never wait on a product they
+// do not need: a slice runs max(ones) additions and max(general) multiply-adds, not their union.
 template <int N>
-__device__ __forceinline__ void lc_dot(uint32_t* acc, TermStream<N>& st, uint32_t n, const uint32_t* __restrict__ coefs,
+__device__ __forceinline__ void lc_dot(uint32_t* acc, TermStream<N>& st, uint32_t n_one, uint32_t n_gen, const uint32_t* __restrict__ coefs,
                                        const FieldParams& fp) {
 #pragma unroll
     for (int i = 0; i < N; i++) acc[i] = 0;
-    for (uint32_t j = 0; j < n; j++) {
+    for (uint32_t j = 0; j < n_one; j++) {
+        uint2 t3;
+        st.prefetch(t3);
+        if (st.t0.y != T_PAD) fe_add<N>(acc, acc, st.z0, fp.p);
+        st.advance(t3);
+    }
+    for (uint32_t j = 0; j < n_gen; j++) {
         uint2 t3;
         st.prefetch(t3);
         const uint32_t ci = st.t0.y;
-        if (ci != T_PAD) {
-            uint32_t t[N];
-            if (ci != T_ONE) {
-                uint32_t cf[N];
+        if (ci == T_ONE) {  // layout kind 1 keeps the ones inside the general class (a warp-uniform branch there)
+            fe_add<N>(acc, acc, st.z0, fp.p);
+        } else if (ci != T_PAD) {
+            uint32_t t[N], cf[N];
 #pragma unroll
-                for (int i = 0; i < N; i++) cf[i] = __ldg(coefs + (size_t)ci * N + i);
-                fe_mont_mul<N>(t, st.z0, cf, fp.p, fp.n0inv);
-            } else {
-#pragma unroll
-                for (int i = 0; i < N; i++) t[i] = st.z0[i];
-            }
+            for (int i = 0; i < N; i++) cf[i] = __ldg(coefs + (size_t)ci * N + i);
+            fe_mont_mul<N>(t, st.z0, cf, fp.p, fp.n0inv);
             fe_add<N>(acc, acc, t, fp.p);
         }
         st.advance(t3);
@@ -181,13 +212,14 @@ k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, 
     for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total; tid += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t lane = (uint32_t)tid & wt_mask;
         const uint64_t srow = tid >> g.log2_wt;
-        const uint4 sl = __ldg(slices + (srow >> 5));
+        const uint4 sl = __ldg(slices + (srow >> 5));  // {first group, A ones | A general << 16, B ..., C ...}
+        const uint32_t ka1 = sl.y & 0xFFFF, kag = sl.y >> 16, kb1 = sl.z & 0xFFFF, kbg = sl.z >> 16, kc1 = sl.w & 0xFFFF, kcg = sl.w >> 16;
         TermStream<N> st;
-        st.start(terms + (size_t)sl.x * 32 + (srow & 31), z, lane, g.log2_wt, sl.y + sl.z + sl.w);
+        st.start(terms + (size_t)sl.x * 32 + (srow & 31), z, lane, g.log2_wt, ka1 + kag + kb1 + kbg + kc1 + kcg);
         uint32_t a[N], b[N], cc[N], ab[N];
-        lc_dot<N>(a, st, sl.y, coefs, fp);
-        lc_dot<N>(b, st, sl.z, coefs, fp);
-        lc_dot<N>(cc, st, sl.w, coefs, fp);
+        lc_dot<N>(a, st, ka1, kag, coefs, fp);
+        lc_dot<N>(b, st, kb1, kbg, coefs, fp);
+        lc_dot<N>(cc, st, kc1, kcg, coefs, fp);
         fe_mont_mul<N>(ab, a, b, fp.p, fp.n0inv);  // (aR)(bR)/R = abR, compared with cR
         uint32_t diff = 0;
 #pragma unroll
@@ -260,19 +292,51 @@ extern "C" int zkb_r1cs_load(zkb_ctx* c, const zkb_csr* A, const zkb_csr* B, con
         launch_to_mont(N, r->d_coefs, (uint32_t)n_coefs, c->prog.fp, c->stream);
     }
 
-    // ---- SELL-32-sigma ----
-    uint64_t sigma = 16384;
+    // keep the system (zero coefficients dropped: they contribute nothing, from_r1cs.rs:72-77; coefficient one tagged)
+    for (int m = 0; m < 3; m++) {
+        r->h_rp[m].assign(nr + 1, 0);
+        r->h_col[m].reserve(r->nnz[m]);
+        r->h_tag[m].reserve(r->nnz[m]);
+        for (uint64_t row = 0; row < nr; row++) {
+            for (uint64_t e = M[m]->row_ptr[row]; e < M[m]->row_ptr[row + 1]; e++) {
+                const uint32_t ci = M[m]->coef_idx[e];
+                if (coef_class[ci] == 0) continue;
+                r->h_col[m].push_back(M[m]->col[e]);
+                r->h_tag[m].push_back(coef_class[ci] == 1 ? T_ONE : ci);
+            }
+            r->h_rp[m][row + 1] = (uint32_t)r->h_col[m].size();
+        }
+    }
+    if (c->has_gpu) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ZKB_OK;
+}
+
+// SELL-32-sigma construction of one layout kind (see R1csLayout); uploads it unless the context is host-only
+static int build_layout(zkb_ctx* c, R1csDev* r, int kind) {
+    R1csLayout& L = r->layout[kind];
+    if (L.built) return ZKB_OK;
+    const uint64_t nr = r->n_rows;
+    const bool split = kind == 0;
+    uint64_t sigma = split ? 262144 : 16384;
     if (const char* e = getenv("ZKB_R1CS_SIGMA")) sigma = std::max<uint64_t>(32, (uint64_t)atoll(e) / 32 * 32);
-    auto cnt = [&](int m, uint64_t row) { return (uint64_t)(M[m]->row_ptr[row + 1] - M[m]->row_ptr[row]); };
+    // class of a term: 2 * matrix + (general ? 1 : 0); without the split everything is "general"
+    auto cls = [&](int m, uint32_t tag) { return 2 * m + ((split && tag == T_ONE) ? 0 : 1); };
+    std::vector<uint32_t> cls_cnt(std::max<uint64_t>(nr, 1) * 6, 0);
+    for (int m = 0; m < 3; m++)
+        for (uint64_t row = 0; row < nr; row++)
+            for (uint32_t e = r->h_rp[m][row]; e < r->h_rp[m][row + 1]; e++) {
+                uint32_t& n = cls_cnt[row * 6 + cls(m, r->h_tag[m][e])];
+                if (++n > 0xFFFF) return c->fail(ZKB_E_UNSUPPORTED, "zkb: more than 65535 terms of one kind in a constraint");
+            }
     std::vector<uint32_t> order(std::max<uint64_t>(nr, 1));
     for (uint64_t i = 0; i < nr; i++) order[i] = (uint32_t)i;
     for (uint64_t w0 = 0; w0 < nr; w0 += sigma) {
         uint64_t w1 = std::min(nr, w0 + sigma);
         std::stable_sort(order.begin() + w0, order.begin() + w1, [&](uint32_t x, uint32_t y) {
-            for (int m = 0; m < 3; m++) {
-                uint64_t cx = cnt(m, x), cy = cnt(m, y);
-                if (cx != cy) return cx > cy;
-            }
+            const uint32_t* cx = &cls_cnt[(size_t)x * 6];
+            const uint32_t* cy = &cls_cnt[(size_t)y * 6];
+            for (int k = 0; k < 6; k++)
+                if (cx[k] != cy[k]) return cx[k] > cy[k];
             return false;
         });
     }
@@ -280,59 +344,64 @@ extern "C" int zkb_r1cs_load(zkb_ctx* c, const zkb_csr* A, const zkb_csr* B, con
     std::vector<uint4> slices(std::max<uint64_t>(n_slices, 1));
     uint64_t n_groups = 0;
     for (uint64_t s = 0; s < n_slices; s++) {
-        uint64_t k[3] = {0, 0, 0};
+        uint32_t k[6] = {0, 0, 0, 0, 0, 0};
         for (uint64_t i = s * 32; i < std::min(nr, s * 32 + 32); i++)
-            for (int m = 0; m < 3; m++) k[m] = std::max(k[m], cnt(m, order[i]));
-        slices[s] = make_uint4((uint32_t)n_groups, (uint32_t)k[0], (uint32_t)k[1], (uint32_t)k[2]);
-        n_groups += k[0] + k[1] + k[2];
+            for (int q = 0; q < 6; q++) k[q] = std::max(k[q], cls_cnt[(size_t)order[i] * 6 + q]);
+        slices[s] = make_uint4((uint32_t)n_groups, k[0] | (k[1] << 16), k[2] | (k[3] << 16), k[4] | (k[5] << 16));
+        for (int q = 0; q < 6; q++) n_groups += k[q];
         if (n_groups >= (1ull << 32) / 32) return c->fail(ZKB_E_UNSUPPORTED, "zkb: R1CS too large for the sliced layout");
     }
     std::vector<uint2> terms(std::max<uint64_t>(n_groups, 1) * 32, make_uint2(0, T_PAD));
     for (uint64_t s = 0; s < n_slices; s++) {
-        uint64_t g0 = slices[s].x;
-        const uint32_t kk[3] = {slices[s].y, slices[s].z, slices[s].w};
+        const uint32_t packed[3] = {slices[s].y, slices[s].z, slices[s].w};
+        uint64_t base[6];  // first group of every class in this slice
+        uint64_t gpos = slices[s].x;
+        for (int q = 0; q < 6; q++) {
+            base[q] = gpos;
+            gpos += (packed[q / 2] >> (16 * (q & 1))) & 0xFFFF;
+        }
         for (uint64_t i = s * 32; i < std::min(nr, s * 32 + 32); i++) {
             const uint64_t row = order[i];
-            uint64_t gm = g0;
-            for (int m = 0; m < 3; m++) {
-                const uint64_t lo = M[m]->row_ptr[row], n = cnt(m, row);
-                for (uint64_t e = 0; e < n; e++) {
-                    const uint32_t ci = M[m]->coef_idx[lo + e];
-                    const uint32_t tag = coef_class[ci] == 0 ? T_PAD : coef_class[ci] == 1 ? T_ONE : ci;
-                    terms[(gm + e) * 32 + (i & 31)] = make_uint2(tag == T_PAD ? 0u : M[m]->col[lo + e], tag);
+            uint32_t fill[6] = {0, 0, 0, 0, 0, 0};
+            for (int m = 0; m < 3; m++)
+                for (uint32_t e = r->h_rp[m][row]; e < r->h_rp[m][row + 1]; e++) {
+                    const int q = cls(m, r->h_tag[m][e]);
+                    terms[(base[q] + fill[q]++) * 32 + (i & 31)] = make_uint2(r->h_col[m][e], r->h_tag[m][e]);
                 }
-                gm += kk[m];
-            }
         }
     }
-    r->n_slices = n_slices;
-    r->n_groups = n_groups;
+    L.n_slices = n_slices;
+    L.n_groups = n_groups;
+    L.built = true;
     if (!c->has_gpu) {  // host-only context: the layout can be inspected, every evaluation call fails with ZKB_E_CUDA
-        r->h_slices = std::move(slices);
-        r->h_terms = std::move(terms);
-        r->h_row_ids = std::move(order);
+        L.h_slices = std::move(slices);
+        L.h_terms = std::move(terms);
+        L.h_row_ids = std::move(order);
         return ZKB_OK;
     }
-    CUDA_TRY(c, cudaMalloc((void**)&r->d_slices, slices.size() * sizeof(uint4)));
-    CUDA_TRY(c, cudaMalloc((void**)&r->d_terms, terms.size() * sizeof(uint2)));
-    CUDA_TRY(c, cudaMalloc((void**)&r->d_row_ids, order.size() * 4));
-    CUDA_TRY(c, cudaMemcpy(r->d_slices, slices.data(), slices.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(r->d_terms, terms.data(), terms.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(r->d_row_ids, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMalloc((void**)&L.d_slices, slices.size() * sizeof(uint4)));
+    CUDA_TRY(c, cudaMalloc((void**)&L.d_terms, terms.size() * sizeof(uint2)));
+    CUDA_TRY(c, cudaMalloc((void**)&L.d_row_ids, order.size() * 4));
+    CUDA_TRY(c, cudaMemcpy(L.d_slices, slices.data(), slices.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(L.d_terms, terms.data(), terms.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(L.d_row_ids, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
     return ZKB_OK;
 }
 
-extern "C" int zkb_debug_r1cs_layout(zkb_ctx* c, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids) {
+extern "C" int zkb_debug_r1cs_layout(zkb_ctx* c, int kind, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids) {
     R1csDev* r = c->r1cs;
     if (!r) return c->fail(ZKB_E_ARG, "zkb_r1cs_load must be called first");
     if (c->has_gpu) return c->fail(ZKB_E_ARG, "zkb_debug_r1cs_layout needs a host-only context (device < 0)");
-    counts[0] = r->n_slices;
-    counts[1] = r->n_groups;
+    if (kind != 0 && kind != 1) return c->fail(ZKB_E_ARG, "layout kind must be 0 or 1");
+    int rc = build_layout(c, r, kind);
+    if (rc != ZKB_OK) return rc;
+    const R1csLayout& L = r->layout[kind];
+    counts[0] = L.n_slices;
+    counts[1] = L.n_groups;
     counts[2] = r->n_rows;
-    if (slices) memcpy(slices, r->h_slices.data(), r->n_slices * sizeof(uint4));
-    if (terms) memcpy(terms, r->h_terms.data(), r->n_groups * 32 * sizeof(uint2));
-    if (row_ids) memcpy(row_ids, r->h_row_ids.data(), r->n_rows * 4);
+    if (slices) memcpy(slices, L.h_slices.data(), L.n_slices * sizeof(uint4));
+    if (terms) memcpy(terms, L.h_terms.data(), L.n_groups * 32 * sizeof(uint2));
+    if (row_ids) memcpy(row_ids, L.h_row_ids.data(), r->n_rows * 4);
     return ZKB_OK;
 }
 
@@ -387,6 +456,10 @@ extern "C" int zkb_r1cs_upload(zkb_ctx* c, const uint8_t* z_le, uint64_t z_set_s
         CUDA_TRY(c, cudaMalloc((void**)&r->d_first_fail, (size_t)n_batch * 4));
         r->first_fail_cap = n_batch;
     }
+    {
+        int rc = build_layout(c, r, l2 < 5 ? 0 : 1);  // first use of this tile width class: build + upload the layout
+        if (rc != ZKB_OK) return rc;
+    }
     r->z_set_stride = z_set_stride;
     r->stride = value_stride;
     r->n_batch = n_batch;
@@ -423,9 +496,10 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
         DISPATCH_N(N, (k_r1cs_load_z<N><<<grid, 256, 0, c->stream>>>(r->d_zraw, r->z_set_stride, r->stride, r->n_vars, r->d_z, g,
                                                                      c->d_unreduced, fp)));
         cudaEventRecord(c->tile_ev[2 * t], c->stream);
-        grid = grid_for((r->n_slices * 32) << r->log2_wt, c->sm_count, 256);
-        DISPATCH_N(N, (k_r1cs_check<N><<<grid, 256, 0, c->stream>>>(r->d_slices, r->d_terms, r->d_row_ids, r->d_coefs, r->d_z, r->n_rows,
-                                                                    r->n_slices, r->d_first_fail, g, fp)));
+        const R1csLayout& L = r->layout[r->log2_wt < 5 ? 0 : 1];
+        grid = grid_for((L.n_slices * 32) << r->log2_wt, c->sm_count, 256);
+        DISPATCH_N(N, (k_r1cs_check<N><<<grid, 256, 0, c->stream>>>(L.d_slices, L.d_terms, L.d_row_ids, r->d_coefs, r->d_z, r->n_rows,
+                                                                    L.n_slices, r->d_first_fail, g, fp)));
         cudaEventRecord(c->tile_ev[2 * t + 1], c->stream);
         launches += 2;
     }
