@@ -660,4 +660,4 @@ class Stats:
             self._chk(_lib.zkb_metrics_ingest_paths(self._m, arr, len(source.paths)))
 
     def to_json_pretty(self) -> str:
-        return _lib.zkb_metrics_json(self._m).decode("utf-8")
+        return _lib.zkb_metrics_json(self._m).decode("utf-8", "replace")

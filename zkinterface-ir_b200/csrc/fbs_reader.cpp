@@ -118,7 +118,8 @@ void read_wirelist(const Table& t, WireList& out) {  // structs/wire.rs:145-157
     }
 }
 
-void read_iterexpr(const Table& t, IterExpr& e) {  // structs/iterators.rs:36-110
+void read_iterexpr(const Table& t, IterExpr& e, int depth = 0) {  // structs/iterators.rs:36-110
+    REQ(depth < 512, "zkb: iterator expression nested more than 512 levels deep");
     uint8_t ty = t.u8(4);
     REQ(ty >= 1 && ty <= 6, "Unknown Iterator Expression type");
     Table v = t.table(6);
@@ -133,14 +134,14 @@ void read_iterexpr(const Table& t, IterExpr& e) {  // structs/iterators.rs:36-11
             REQ(r, "Missing right operand");
             e.l.reset(new IterExpr());
             e.r.reset(new IterExpr());
-            read_iterexpr(l, *e.l);
-            read_iterexpr(r, *e.r);
+            read_iterexpr(l, *e.l, depth + 1);
+            read_iterexpr(r, *e.r, depth + 1);
         } break;
         default: {
             Table nmr = v.table(4);
             REQ(nmr, "Missing numerator");
             e.l.reset(new IterExpr());
-            read_iterexpr(nmr, *e.l);
+            read_iterexpr(nmr, *e.l, depth + 1);
             e.value = v.u64(6);
         }
     }
@@ -174,6 +175,8 @@ void read_iterexpr_list(const Table& t, IterExprList& out) {  // structs/iterato
 
 struct Ctx {
     Message* msg;
+    int depth = 0;  // nesting of gate vectors (AnonCall / Switch / For bodies): bounded, a hostile message must not
+                    // exhaust the stack (the walkers above the reader recurse over the same structure)
     uint32_t add_const(std::vector<uint8_t>&& v) {
         msg->consts.push_back(std::move(v));
         return (uint32_t)msg->consts.size() - 1;
@@ -326,8 +329,11 @@ void read_gate(Ctx& cx, const Table& d, Gate& g) {  // structs/gates.rs:60-259
 void read_gates(Ctx& cx, const Table& parent, int slot, const char* missing, std::vector<Gate>& out) {
     size_t at; uint32_t n;
     REQ(parent.vec(slot, at, n), missing);
+    REQ(cx.depth < 512, "zkb: gates nested more than 512 levels deep");
+    cx.depth++;
     out.resize(n);
     for (uint32_t i = 0; i < n; i++) read_gate(cx, parent.vec_at(at, i), out[i]);
+    cx.depth--;
 }
 
 void read_header(const Table& t, Header& h) {  // structs/header.rs:37-56

@@ -149,18 +149,43 @@ void json_gate_stats(std::string& out, const GateStats& s, const std::string& in
     out += indent + "}";
 }
 
+// JSON string literal; bytes that are not valid UTF-8 (a corrupted message: FlatBuffers strings are not validated by the
+// reference's reader either) become U+FFFD so that the output is always valid JSON
 std::string json_string(const std::string& s) {
     std::string o = "\"";
-    for (unsigned char c : s) {
+    for (size_t i = 0; i < s.size();) {
+        unsigned char c = (unsigned char)s[i];
         if (c == '"' || c == '\\') {
             o += '\\';
             o += (char)c;
+            i++;
         } else if (c < 0x20) {
             char b[8];
             snprintf(b, sizeof b, "\\u%04x", c);
             o += b;
-        } else {
+            i++;
+        } else if (c < 0x80) {
             o += (char)c;
+            i++;
+        } else {
+            int len = (c >= 0xC2 && c <= 0xDF) ? 2 : (c >= 0xE0 && c <= 0xEF) ? 3 : (c >= 0xF0 && c <= 0xF4) ? 4 : 0;
+            bool ok = len != 0 && i + (size_t)len <= s.size();
+            for (int k = 1; ok && k < len; k++) ok = ((unsigned char)s[i + k] & 0xC0) == 0x80;
+            if (ok && len == 3) {
+                unsigned char c1 = (unsigned char)s[i + 1];
+                ok = !(c == 0xE0 && c1 < 0xA0) && !(c == 0xED && c1 >= 0xA0);  // overlong / surrogates
+            }
+            if (ok && len == 4) {
+                unsigned char c1 = (unsigned char)s[i + 1];
+                ok = !(c == 0xF0 && c1 < 0x90) && !(c == 0xF4 && c1 >= 0x90);
+            }
+            if (ok) {
+                o.append(s, i, (size_t)len);
+                i += (size_t)len;
+            } else {
+                o += "\\ufffd";
+                i++;
+            }
         }
     }
     return o + "\"";
