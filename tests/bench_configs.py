@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Secondary configs of BASELINE.json (C1, C2, C4, C5): parity check + device timing (CUDA events inside
-libzkb, inputs resident).  One JSON line per config.  The headline (C3) is bench.py."""
+"""Secondary configs of BASELINE.json (C1, C2, C4, C5, C3 as a `.sieve` statement): parity check + device timing (CUDA
+events inside libzkb, inputs resident).  One JSON line per config.  The headline (C3) is bench.py.
+Lives under tests/ because it uses the oracle — as workload generator (structured relations, FlatBuffers messages), as
+the checker of every result it times and as the CPU figure printed beside them — never as the thing measured."""
 import argparse
 import importlib
 import json
