@@ -221,3 +221,26 @@ def test_slot_reuse_keeps_results(monkeypatch):
                 b.read_values(0, [circ.n_inputs + 50], 32)
         b.close()
     assert slots["1"] < slots["0"] / 10, slots
+
+
+@pytest.mark.parametrize("name,n_batch", [("goldilocks", 300), ("p61", 64), ("m31", 300), ("p101", 130), ("goldilocks", 63)])
+def test_narrow_fields_packed_lanes(name, n_batch):
+    """N = 1 / 2 limbs: tiles of >= 128 / 64 witnesses run 4 / 2 lanes per thread (16-byte vector loads); ragged batches,
+    corrupted witnesses on both lanes of a pair, every gate kind incl. constants; smaller tiles take the unpacked kernel"""
+    c = circuits()
+    p = FIELDS[name]
+    gates, pool, n_wires = random_flat_program(p, 1500, 5, 40, seed=n_batch)
+    rng = np.random.default_rng(n_batch + 7)
+    eb = c.elem_bytes(p)
+    inst = c.random_field_elements(rng, (n_batch, 5), p)
+    wit = c.random_field_elements(rng, (n_batch, 40), p)
+    v, ref, st = _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0, 1, n_batch - 1))
+    if n_batch >= 128:
+        assert st["tile_witnesses"] >= 128
+    circ = c.random_circuit(4000, 64, p, seed=21, n_ties=8)
+    corrupt = {0: 1, 1: 4, 2: 0, 7: 7, n_batch - 1: 3, n_batch - 2: 2}
+    w = c.make_witnesses(circ, n_batch, seed=6, corrupt=corrupt)
+    v, ref, _ = _check(c, circ.gates, circ.const_pool, p, None, w, n_batch, circ.n_wires, sample=(0, 3, n_batch - 1))
+    exp = c.expected_first_fail(circ, n_batch, corrupt)
+    for j in range(n_batch):
+        assert (int(v[j]["first_fail_seq"]) if not v[j]["ok"] else -1) == exp[j]

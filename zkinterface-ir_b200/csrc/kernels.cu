@@ -157,57 +157,75 @@ k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint6
 // operand limbs one iteration ahead, so a thread always has the next gate's 4 x 16-byte loads in flight
 // while it runs the current gate's integer chain (the dependent descriptor -> operand latency and the
 // compute phase no longer serialise with the memory phase).
-template <int N>
+// LPT = witness lanes per thread.  For the narrow fields (N = 1, 2 limbs) a thread takes 4 / 2 adjacent lanes: their
+// elements are adjacent in the wire store (witness-minor layout), so one 16-byte vector load brings them all and a
+// warp still moves 512 bytes per request — the "packed element" of LPT * N limbs is addressed exactly like a 4-limb
+// element of a tile with Wt / LPT lanes.  LPT = 1 for N >= 4.
+template <int N, int LPT>
 __device__ __forceinline__ void load_operands(uint32_t* a, uint32_t* b, const uint4& d, const uint32_t* __restrict__ store,
-                                              const uint32_t* __restrict__ consts_mont, uint32_t lane, uint32_t log2_wt) {
+                                              const uint32_t* __restrict__ consts_mont, uint32_t plane, uint32_t log2_pwt) {
+    constexpr int PN = N * LPT;
     const uint32_t opc = d.w & 0xff;
-    load_elem<N>(a, store, d.x, lane, log2_wt);
+    load_elem<PN>(a, store, d.x, plane, log2_pwt);
     if (opc == D_ADDC || opc == D_MULC) {
 #pragma unroll
-        for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)d.y * N + k);
+        for (int l = 0; l < LPT; l++)
+#pragma unroll
+            for (int k = 0; k < N; k++) b[l * N + k] = __ldg(consts_mont + (size_t)d.y * N + k);
     } else {
-        load_elem<N>(b, store, d.y, lane, log2_wt);
+        load_elem<PN>(b, store, d.y, plane, log2_pwt);
     }
 }
 
 #ifndef ZKB_LEVEL_PIPE_MIN_CTAS
 #define ZKB_LEVEL_PIPE_MIN_CTAS 4  // 64 registers: 4 resident CTAs per SM measured 6 % faster than 3 (scripts/ab_min_ctas.sh)
 #endif
-template <int N>
+template <int N, int LPT>
 __global__ void __launch_bounds__(256, ZKB_LEVEL_PIPE_MIN_CTAS)
 k_level_pipe(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
              const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
-    const uint64_t total = n_ops << g.log2_wt;
-    const uint32_t wt_mask = (1u << g.log2_wt) - 1;
+    constexpr int PN = N * LPT;
+    constexpr uint32_t kLog2Lpt = LPT == 4 ? 2 : LPT == 2 ? 1 : 0;
+    const uint32_t log2_pwt = g.log2_wt - kLog2Lpt;  // packed lanes per tile
+    const uint64_t total = n_ops << log2_pwt;
+    const uint32_t pwt_mask = (1u << log2_pwt) - 1;
     const bool single = g.log2_wt == 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint64_t t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t0 >= total) return;
     const uint4* dptr = reinterpret_cast<const uint4*>(ops);
     uint64_t t1 = t0 + stride, t2 = t1 + stride;
-    uint4 d0 = __ldg(dptr + (t0 >> g.log2_wt));
-    uint4 d1 = t1 < total ? __ldg(dptr + (t1 >> g.log2_wt)) : make_uint4(0, 0, 0, 0);
-    uint32_t a0[N], b0[N], a1[N], b1[N];
-    load_operands<N>(a0, b0, d0, store, consts_mont, (uint32_t)t0 & wt_mask, g.log2_wt);
+    uint4 d0 = __ldg(dptr + (t0 >> log2_pwt));
+    uint4 d1 = t1 < total ? __ldg(dptr + (t1 >> log2_pwt)) : make_uint4(0, 0, 0, 0);
+    uint32_t a0[PN], b0[PN], a1[PN], b1[PN];
+    load_operands<N, LPT>(a0, b0, d0, store, consts_mont, (uint32_t)t0 & pwt_mask, log2_pwt);
     while (true) {
         uint4 d2 = make_uint4(0, 0, 0, 0);
-        if (t2 < total) d2 = __ldg(dptr + (t2 >> g.log2_wt));
+        if (t2 < total) d2 = __ldg(dptr + (t2 >> log2_pwt));
         const bool more = t1 < total;
-        if (more) load_operands<N>(a1, b1, d1, store, consts_mont, (uint32_t)t1 & wt_mask, g.log2_wt);
+        if (more) load_operands<N, LPT>(a1, b1, d1, store, consts_mont, (uint32_t)t1 & pwt_mask, log2_pwt);
         // ---- current gate ----
         const uint32_t opc = d0.w & 0xff;
-        const uint32_t lane = (uint32_t)t0 & wt_mask;
-        uint32_t r[N];
-        if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a0, b0, fp.p);
-        else fe_mont_mul<N>(r, a0, b0, fp.p, fp.n0inv);
-        if (!(d0.w & F_NOSTORE)) store_elem<N>(store, d0.z, lane, g.log2_wt, r);
+        const uint32_t plane = (uint32_t)t0 & pwt_mask;
+        uint32_t r[PN];
+#pragma unroll
+        for (int l = 0; l < LPT; l++) {
+            if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r + l * N, a0 + l * N, b0 + l * N, fp.p);
+            else fe_mont_mul<N>(r + l * N, a0 + l * N, b0 + l * N, fp.p, fp.n0inv);
+        }
+        if (!(d0.w & F_NOSTORE)) store_elem<PN>(store, d0.z, plane, log2_pwt, r);
         if (d0.w & F_ASSERT) {
-            bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
-            report_fail(fail, __ldg(aseq + (t0 >> g.log2_wt)), first_fail, g.batch0 + lane, single);
+            const uint32_t seq = __ldg(aseq + (t0 >> log2_pwt));
+#pragma unroll
+            for (int l = 0; l < LPT; l++) {
+                const uint32_t lane = plane * LPT + l;
+                bool fail = !fe_is_zero<N>(r + l * N) && lane < g.n_valid;
+                report_fail(fail, seq, first_fail, g.batch0 + lane, single);
+            }
         }
         if (!more) break;
 #pragma unroll
-        for (int k = 0; k < N; k++) {
+        for (int k = 0; k < PN; k++) {
             a0[k] = a1[k];
             b0[k] = b1[k];
         }
@@ -458,7 +476,18 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
     unsigned grid = grid_for(n_ops << g.log2_wt, sm_count, grid_per_sm(256));
     if (!rare) {
         if (level_pipe_enabled()) {
-            ZKB_DISPATCH_N(nlimb, (k_level_pipe<N><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+            // narrow fields: 4 (one limb) or 2 (two limbs) witness lanes per thread when the tile still gives every warp
+            // 32 packed lanes of one gate (ZKB_LEVEL_LPT=1 switches the packing off)
+            static const bool pack = getenv("ZKB_LEVEL_LPT") == nullptr || atoi(getenv("ZKB_LEVEL_LPT")) != 1;
+            if (pack && nlimb == 2 && g.log2_wt >= 6) {
+                grid = grid_for(n_ops << (g.log2_wt - 1), sm_count, grid_per_sm(256));
+                k_level_pipe<2, 2><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp);
+            } else if (pack && nlimb == 1 && g.log2_wt >= 7) {
+                grid = grid_for(n_ops << (g.log2_wt - 2), sm_count, grid_per_sm(256));
+                k_level_pipe<1, 4><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp);
+            } else {
+                ZKB_DISPATCH_N(nlimb, (k_level_pipe<N, 1><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
+            }
         } else {
             ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rawflag, g, fp)));
         }
