@@ -305,9 +305,7 @@ struct zkb_evaluator {
                 expand_wirelist(g.cx->inputs, ei);
                 check_arity(g.cx->name, f, eo.size(), ei.size());
                 Iters fresh;  // named calls do NOT see the caller's iterators (:456)
-                auto body = f.body;
-                auto fc = f.consts;
-                ingest_subcircuit(*body, *fc, eo, ei, scope, fresh, instances, witnesses, weight);
+                ingest_subcircuit(*f.body, *f.consts, eo, ei, scope, fresh, instances, witnesses, weight);
             } break;
             case ir::G_ANON_CALL: {  // :473-491
                 std::vector<uint64_t> eo, ei;
@@ -318,20 +316,25 @@ struct zkb_evaluator {
             case ir::G_FOR: {  // :495-559
                 const ir::Complex& cx = *g.cx;
                 std::vector<uint64_t> eo, ei;
+                // the callee is resolved once per loop (definitions only happen at the head of a relation message, never
+                // while its gates run); an unknown function is still reported by the first iteration that needs it
+                const FunctionDecl* callee = nullptr;
+                if (!cx.body_is_anon) {
+                    auto it = known_functions.find(cx.fn_name);
+                    if (it != known_functions.end()) callee = &it->second;
+                }
+                Iters fresh;
                 for (uint64_t i = cx.first; i <= cx.last; i++) {
                     step();
                     iters_set(iters, cx.name, i);
                     if (!cx.body_is_anon) {
-                        auto it = known_functions.find(cx.fn_name);
-                        if (it == known_functions.end()) throw EvalErr{"Unknown function"};
-                        const FunctionDecl& f = it->second;
+                        if (!callee) throw EvalErr{"Unknown function"};
+                        const FunctionDecl& f = *callee;
                         eval_iterexpr_list(cx.it_outputs, iters, eo);
                         eval_iterexpr_list(cx.it_inputs, iters, ei);
                         check_arity(cx.fn_name, f, eo.size(), ei.size());
-                        Iters fresh;
-                        auto body = f.body;
-                        auto fc = f.consts;
-                        ingest_subcircuit(*body, *fc, eo, ei, scope, fresh, instances, witnesses, weight);
+                        fresh.clear();
+                        ingest_subcircuit(*f.body, *f.consts, eo, ei, scope, fresh, instances, witnesses, weight);
                     } else {
                         eval_iterexpr_list(cx.it_outputs, iters, eo);
                         eval_iterexpr_list(cx.it_inputs, iters, ei);
