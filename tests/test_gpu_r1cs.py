@@ -113,3 +113,46 @@ def test_r1cs_batch_tiles(tile, monkeypatch):
     b.r1cs_load(r.A, r.B, r.C, r.coef_table, r.n_vars)
     v = b.r1cs_check(np.stack(zs))
     assert [(-1 if x["ok"] else int(x["first_fail_seq"])) for x in v] == exp
+
+
+@pytest.mark.parametrize("name", ["goldilocks", "bn254"])
+def test_r1cs_wide_tiles_use_the_unsplit_layout(name):
+    """tiles of >= 32 assignments take layout kind 1 (one class per matrix, ones tagged inside the general class):
+    70 assignments, ragged last warp, a third of them violated at known rows; coefficient table with 0 and p + 1"""
+    c = circuits()
+    z_ = zkb()
+    p = FIELDS[name]
+    eb = c.elem_bytes(p)
+    r = c.random_r1cs(700, 90, p, seed=17)
+    table = np.concatenate([r.coef_table, c.le_bytes(0, eb)[None]])
+    zero_idx = len(r.coefs)
+    good = c.r1cs_assignment(r, seed=4)
+    # zero out some coefficients of B and fix the slack values accordingly through a fresh assignment
+    B = (r.B[0], r.B[1], r.B[2].copy())
+    B[2][::9] = zero_idx
+    coefs = r.coefs + [0]
+    r.B = B
+    r.coefs = coefs
+    good = c.r1cs_assignment(r, seed=4)
+    n = 70
+    zs, exp = [], []
+    for j in range(n):
+        zv = list(good)
+        if j % 3 == 1:
+            row = (j * 29) % r.n_rows
+            var = r.n_free + 1 + row
+            zv[var] = (zv[var] + 1 + j) % p
+            exp.append(min(row, c.r1cs_first_row_reading(r, var)))
+        else:
+            exp.append(-1)
+        zs.append(c.assignment_bytes(zv, p))
+    b = z_.GpuBackend(0)
+    b.set_field(p)
+    b.r1cs_load(r.A, r.B, r.C, table, r.n_vars)
+    v = b.r1cs_check(np.stack(zs))
+    assert [(-1 if x["ok"] else int(x["first_fail_seq"])) for x in v] == exp
+    # the same system, one assignment at a time (layout kind 0), agrees
+    for j in (0, 1, 4):
+        b.r1cs_upload(np.stack(zs[j:j + 1]))
+        x = b.r1cs_run()[0]
+        assert (-1 if x["ok"] else int(x["first_fail_seq"])) == exp[j]
