@@ -335,6 +335,7 @@ class GpuBackend:
         inst, iss, wit, wss, stride = self._strides(instances, witnesses)
         out = np.zeros(n_batch, dtype=VERDICT_DTYPE)
         self._chk(_lib.zkb_evaluate(self._c, _buf(inst), iss, _buf(wit), wss, stride, n_batch, _buf(out)))
+        self._n_batch = n_batch          # the inputs stay resident: run() re-evaluates them
         return out
 
     def upload_inputs(self, instances, witnesses, n_batch: int):
@@ -343,6 +344,8 @@ class GpuBackend:
         self._n_batch = n_batch
 
     def run(self) -> np.ndarray:
+        if not getattr(self, "_n_batch", 0):
+            raise ZkbError(ZKB_E_ARG, "run() needs inputs: call upload_inputs() or evaluate() first")
         out = np.zeros(self._n_batch, dtype=VERDICT_DTYPE)
         self._chk(_lib.zkb_run(self._c, _buf(out)))
         return out
