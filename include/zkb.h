@@ -245,6 +245,12 @@ const char* zkb_evaluator_last_error(zkb_evaluator* ev);
  *   zkb_evaluator_flatten        : MemorySink — three buffers of size-prefixed messages, owned by ev
  *   zkb_evaluator_flatten_to_dir : FilesSink::new_clean — 000_instance / 001_witness / 002_relation .sieve */
 int zkb_evaluator_set_flatten(zkb_evaluator* ev, int on);
+/* `zki_sieve expand-definable --gate-set <s>` (cli.rs:513-553): flatten mode with `ExpandDefinable`
+ * (consumers/exp_definable.rs:24-139) in front of the flattener — gates outside the given gate set ("arithmetic",
+ * "boolean" or a comma-separated list of @add,@addc,@mul,@mulc,@xor,@and,@not; relation.rs:144-167) are rewritten
+ * (AddConstant/MulConstant -> Constant + Add/Mul, And <-> Mul, Xor <-> Add, Not -> AddConstant(1)); an impossible
+ * rewrite is ZKB_E_FATAL with the reference's panic text. */
+int zkb_evaluator_set_expand_definable(zkb_evaluator* ev, const char* gate_set);
 int zkb_evaluator_flatten(zkb_evaluator* ev, const uint8_t** instance, size_t* instance_len, const uint8_t** witness,
                           size_t* witness_len, const uint8_t** relation, size_t* relation_len);
 int zkb_evaluator_flatten_to_dir(zkb_evaluator* ev, const char* out_dir);

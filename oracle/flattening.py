@@ -131,3 +131,92 @@ class IRFlattener:
                 self.witness_msgs.append(ir.Witness(self.header, self._wit))
                 self._wit = []
         return self._create("Witness")
+
+
+class ExpandDefinable:
+    """`rust/src/consumers/exp_definable.rs:24-139`: a ZKBackend that rewrites the gates outside `gate_mask` and forwards
+    everything to an inner IRFlattener.  The `panic!`s become OraclePanic."""
+
+    def __init__(self, gate_mask: int):
+        self.inner = IRFlattener()
+        self.gate_mask = gate_mask
+
+    def finish(self):
+        return self.inner.finish()
+
+    from_bytes_le = staticmethod(IRFlattener.from_bytes_le)
+
+    def set_field(self, modulus, degree, is_boolean):
+        self.inner.set_field(modulus, degree, is_boolean)
+
+    def one(self):
+        return self.inner.one()
+
+    def minus_one(self):
+        return self.inner.minus_one()
+
+    def zero(self):
+        return self.inner.zero()
+
+    def copy(self, w):
+        return self.inner.copy(w)
+
+    def constant(self, v):
+        return self.inner.constant(v)
+
+    def assert_zero(self, w):
+        self.inner.assert_zero(w)
+
+    def _has(self, bit):
+        return ir.contains_feature(self.gate_mask, bit)
+
+    def add(self, a, b):                              # :58-67
+        if not self._has(ir.ADD):
+            if not self._has(ir.XOR):
+                raise ir.OraclePanic("Cannot replace ADD by XOR if XOR is not supported.")
+            return self.inner.xor(a, b)
+        return self.inner.add(a, b)
+
+    def multiply(self, a, b):                         # :69-78
+        if not self._has(ir.MUL):
+            if not self._has(ir.AND):
+                raise ir.OraclePanic("Cannot replace MUL by AND if AND is not supported.")
+            return self.inner.and_(a, b)
+        return self.inner.multiply(a, b)
+
+    def add_constant(self, a, b):                     # :80-87
+        if not self._has(ir.ADDC):
+            return self.add(a, self.constant(b))
+        return self.inner.add_constant(a, b)
+
+    def mul_constant(self, a, b):                     # :89-96
+        if not self._has(ir.MULC):
+            return self.multiply(a, self.constant(b))
+        return self.inner.mul_constant(a, b)
+
+    def and_(self, a, b):                             # :98-107
+        if not self._has(ir.AND):
+            if not self._has(ir.MUL):
+                raise ir.OraclePanic("Cannot replace AND by MUL if MUL is not supported.")
+            return self.multiply(a, b)
+        return self.inner.and_(a, b)
+
+    def xor(self, a, b):                              # :109-118
+        if not self._has(ir.XOR):
+            if not self._has(ir.ADD):
+                raise ir.OraclePanic("Cannot replace XOR by ADD if ADD is not supported.")
+            return self.add(a, b)
+        return self.inner.xor(a, b)
+
+    def not_(self, a):                                # :120-129
+        if not self._has(ir.NOT):
+            if not self._has(ir.ADD):
+                raise ir.OraclePanic("Cannot replace NOT by ADD if ADD is not supported.")
+            return self.add_constant(a, self.one())
+        return self.inner.not_(a)
+
+    def instance(self, v):
+        return self.inner.instance(v)
+
+    def witness(self, v):
+        return self.inner.witness(v)

@@ -145,3 +145,81 @@ def test_writer_round_trips_the_reference_binary_fixtures():
             assert F.read_message(b.rewrite_message(raw)) == F.read_message(raw), path
             n += 1
     assert n >= 9
+
+
+# ---- ExpandDefinable (consumers/exp_definable.rs) in front of the flattener ---------------------------------
+EXPAND_CASES = [
+    ("example", "@add,@mul"),                  # AddConstant / MulConstant become Constant + Add / Mul
+    ("example", "arithmetic"),                 # nothing to rewrite
+    ("builder_switch", "@add,@mul,@mulc"),
+    ("boolean", "@add,@mul"),                  # And -> Mul, Xor -> Add, Not -> Constant(1) + Add
+    ("boolean", "@xor,@and,@addc"),            # Not needs ADD: panic
+    ("example", "@xor,@and"),                  # Add -> Xor, Mul -> And (nonsense over p = 101, but that is what it does)
+    ("example", "@mul"),                       # Add cannot be replaced: panic
+]
+
+
+@pytest.mark.parametrize("name,gate_set", EXPAND_CASES)
+def test_expand_definable_matches_the_reference(name, gate_set):
+    z = zkb()
+    msgs = STATEMENTS[name]()
+    mask = ir.parse_gate_set(gate_set) if hasattr(ir, "parse_gate_set") else None
+    if mask is None:
+        bits = {"@add": ir.ADD, "@addc": ir.ADDC, "@mul": ir.MUL, "@mulc": ir.MULC, "@xor": ir.XOR, "@and": ir.AND, "@not": ir.NOT,
+                "arithmetic": ir.ARITH, "boolean": ir.BOOL}
+        mask = 0
+        for tok in gate_set.split(","):
+            mask |= bits[tok]
+    x = fl.ExpandDefinable(mask)
+    panic = None
+    try:
+        ev.Evaluator.from_messages(msgs, x)
+    except ir.OraclePanic as e:
+        panic = str(e)
+    e = z.Evaluator(expand_gate_set=gate_set)
+    if panic is not None:
+        with pytest.raises(z.ZkbError) as err:
+            e.ingest_source(z.Source.from_buffers([F.write_messages(msgs)]))
+        assert err.value.code == z.ZKB_E_FATAL and str(err.value) == panic
+        return
+    want = x.finish()
+    e.ingest_source(z.Source.from_buffers([F.write_messages(msgs)]))
+    ib, wb, rb = e.flatten()
+    got = F.read_messages(ib) + F.read_messages(wb) + F.read_messages(rb)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert type(g) is type(w)
+        if isinstance(w, ir.Relation):
+            assert g.gates == w.gates and g.gate_mask == w.gate_mask
+        elif isinstance(w, ir.Instance):
+            assert g.common_inputs == w.common_inputs
+        else:
+            assert g.short_witness == w.short_witness
+    allowed = {"Constant", "AssertZero", "Copy", "Instance", "Witness"}
+    names = {"@add": "Add", "@addc": "AddConstant", "@mul": "Mul", "@mulc": "MulConstant", "@xor": "Xor", "@and": "And", "@not": "Not"}
+    if gate_set == "arithmetic":
+        allowed |= {"Add", "AddConstant", "Mul", "MulConstant"}
+    else:
+        allowed |= {names[t] for t in gate_set.split(",")}
+    for m in got:
+        if isinstance(m, ir.Relation):
+            assert {g[0] for g in m.gates} <= allowed
+    if gate_set in ("@add,@mul", "arithmetic", "@add,@mul,@mulc"):
+        assert ev.evaluate(got) == ev.evaluate(msgs) == []      # the rewritten statement means the same
+
+
+def test_expand_definable_gate_set_errors_and_cli(tmp_path):
+    import subprocess
+    z = zkb()
+    with pytest.raises(z.ZkbError) as err:
+        z.Evaluator(expand_gate_set="@nope")
+    assert "Unable to parse the following gateset" in str(err.value)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "zkinterface-ir_b200", "zkb")
+    out = tmp_path / "expanded"
+    r = subprocess.run([cli, "expand-definable", "--gate-set", "@add,@mul", "--out", str(out),
+                        os.path.join(root, "tests", "golden", "example")], capture_output=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    msgs = [m for n in sorted(os.listdir(out)) for m in F.read_messages((out / n).read_bytes())]
+    kinds = {g[0] for m in msgs if isinstance(m, ir.Relation) for g in m.gates}
+    assert "AddConstant" not in kinds and "MulConstant" not in kinds and ev.evaluate(msgs) == []

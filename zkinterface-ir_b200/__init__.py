@@ -71,7 +71,7 @@ EXPORTED = [
     "zkb_upload_inputs", "zkb_run", "zkb_assert_info", "zkb_pending_error", "zkb_read_values", "zkb_scope_lookup",
     "zkb_get_stats", "zkb_get_timing", "zkb_get_program", "zkb_get_const", "zkb_assert_value", "zkb_level_info", "zkb_evaluator_create", "zkb_evaluator_destroy", "zkb_evaluator_ingest_message",
     "zkb_evaluator_ingest_buffer", "zkb_evaluator_ingest_paths", "zkb_evaluator_get_violations",
-    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_evaluator_set_flatten", "zkb_evaluator_flatten",
+    "zkb_evaluator_violation", "zkb_evaluator_get_wire", "zkb_evaluator_lookup", "zkb_evaluator_last_error", "zkb_evaluator_set_flatten", "zkb_evaluator_set_expand_definable", "zkb_evaluator_flatten",
     "zkb_evaluator_flatten_to_dir", "zkb_validator_create", "zkb_validator_destroy", "zkb_validator_ingest_message",
     "zkb_validator_ingest_buffer", "zkb_validator_ingest_paths", "zkb_validator_get_violations", "zkb_validator_violation",
     "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_metrics_create", "zkb_metrics_destroy", "zkb_metrics_ingest_message",
@@ -133,6 +133,7 @@ _sig("zkb_evaluator_get_wire", _i, _vp, _u64, _u8p, _sz, C.POINTER(C.c_size_t))
 _sig("zkb_evaluator_lookup", _i, _vp, _u64, _u64p)
 _sig("zkb_evaluator_last_error", C.c_char_p, _vp)
 _sig("zkb_evaluator_set_flatten", _i, _vp, _i)
+_sig("zkb_evaluator_set_expand_definable", _i, _vp, C.c_char_p)
 _sig("zkb_evaluator_flatten", _i, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
      C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
 _sig("zkb_evaluator_flatten_to_dir", _i, _vp, C.c_char_p)
@@ -505,12 +506,16 @@ class Source:
 class Evaluator:
     """`Evaluator<GpuBackend>` (evaluator.rs:158-753) over `.sieve` bytes."""
 
-    def __init__(self, backend: Optional[GpuBackend] = None, device: int = 0, flatten: bool = False):
+    def __init__(self, backend: Optional[GpuBackend] = None, device: int = 0, flatten: bool = False,
+                 expand_gate_set: Optional[str] = None):
         """flatten=True: the Evaluator drives the IRFlattener instead of an evaluating backend
         (consumers/flattening.rs); the statement can then be written out with flatten() / flatten_to_dir()."""
+        flatten = flatten or expand_gate_set is not None
         self.backend = backend or GpuBackend(-1 if flatten else device)
         self._e = _lib.zkb_evaluator_create(self.backend._c)
-        if flatten:
+        if expand_gate_set is not None:   # ExpandDefinable in front of the flattener (consumers/exp_definable.rs)
+            self._chk(_lib.zkb_evaluator_set_expand_definable(self._e, expand_gate_set.encode()))
+        elif flatten:
             self._chk(_lib.zkb_evaluator_set_flatten(self._e, 1))
 
     def close(self):

@@ -1,6 +1,7 @@
 // zkb — verbs of zki_sieve (rust/src/cli.rs) on the GPU backend.
 //   zkb evaluate [--device N] <workspace dir | *.sieve ... | ->       cli.rs:130, 315-320, 557-571
 //   zkb flatten --out <dir | -> <workspace dir | *.sieve ... | ->     cli.rs:442-472 (host only)
+//   zkb expand-definable --gate-set <s> --out <dir | -> <paths...>    cli.rs:513-553 (host only)
 //   zkb validate <workspace dir | *.sieve ... | ->                    cli.rs:297-313 (host only)
 //   zkb metrics <workspace dir | *.sieve ... | ->                     cli.rs:322-330 (host only; JSON on stdout)
 //   zkb valid-eval-metrics [--device N] <paths...>                    cli.rs:333-363 (all three in one go)
@@ -20,10 +21,11 @@ static int usage(const char* argv0) {
     fprintf(stderr,
             "usage: %s evaluate [--device N] <paths...>\n"
             "       %s flatten --out <dir|-> <paths...>\n"
+            "       %s expand-definable --gate-set <gateset> --out <dir|-> <paths...>\n"
             "       %s validate <paths...>\n"
             "       %s metrics <paths...>\n"
             "       %s valid-eval-metrics [--device N] <paths...>\n",
-            argv0, argv0, argv0, argv0, argv0);
+            argv0, argv0, argv0, argv0, argv0, argv0);
     return 2;
 }
 
@@ -46,10 +48,12 @@ int main(int argc, char** argv) {
     const std::string verb = argv[1];
     int device = 0;
     const char* out = nullptr;
+    const char* gate_set = nullptr;
     std::vector<const char*> paths;
     for (int i = 2; i < argc; i++) {
         if (strcmp(argv[i], "--device") == 0 && i + 1 < argc) device = atoi(argv[++i]);
         else if (strcmp(argv[i], "--out") == 0 && i + 1 < argc) out = argv[++i];
+        else if (strcmp(argv[i], "--gate-set") == 0 && i + 1 < argc) gate_set = argv[++i];
         else paths.push_back(argv[i]);
     }
     if (verb == "evaluate") {
@@ -73,11 +77,12 @@ int main(int argc, char** argv) {
         zkb_destroy(ctx);
         return status;
     }
-    if (verb == "flatten") {
+    if (verb == "flatten" || verb == "expand-definable") {
         if (!out) return usage(argv[0]);
+        if (verb == "expand-definable" && !gate_set) return 0;  // main_expand_definable does nothing without --gate-set (cli.rs:521)
         zkb_ctx* ctx = zkb_create(-1);
         zkb_evaluator* ev = zkb_evaluator_create(ctx);
-        int rc = zkb_evaluator_set_flatten(ev, 1);
+        int rc = verb == "flatten" ? zkb_evaluator_set_flatten(ev, 1) : zkb_evaluator_set_expand_definable(ev, gate_set);
         if (rc == ZKB_OK) rc = zkb_evaluator_ingest_paths(ev, paths.data(), paths.size());
         if (rc == ZKB_OK) {
             if (strcmp(out, "-") == 0) {  // MemorySink, then instance / witness / relation messages to stdout

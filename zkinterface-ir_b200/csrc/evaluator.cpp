@@ -485,6 +485,9 @@ struct zkb_evaluator {
         } catch (const Fatal& f) {
             fatal = true;
             return fail(ZKB_E_FATAL, f.msg);
+        } catch (const Program::ProgramPanic& f) {  // ExpandDefinable's panics (exp_definable.rs:62-64, ...)
+            fatal = true;
+            return fail(ZKB_E_FATAL, f.msg);
         }
         return ZKB_OK;
     }
@@ -753,6 +756,18 @@ extern "C" int zkb_debug_write_flat_relation(zkb_ctx* c, const uint8_t* modulus_
 extern "C" int zkb_evaluator_set_flatten(zkb_evaluator* ev, int on) {
     if (ev->prog().n_values() > 0) return ev->fail(ZKB_E_ARG, "flatten mode must be chosen before anything is recorded");
     ev->prog().keep_copies = on != 0;
+    return ZKB_OK;
+}
+
+// `zki_sieve expand-definable --gate-set <s>` (cli.rs:513-553): ExpandDefinable wraps the flattener
+extern "C" int zkb_evaluator_set_expand_definable(zkb_evaluator* ev, const char* gate_set) {
+    if (ev->prog().n_values() > 0) return ev->fail(ZKB_E_ARG, "expand-definable must be chosen before anything is recorded");
+    uint16_t mask = 0;
+    std::string e;
+    if (!ir::parse_gate_set(gate_set ? gate_set : "", mask, e)) return ev->fail(ZKB_E_SEMANTIC, e);  // relation.rs:144-167
+    ev->prog().keep_copies = true;
+    ev->prog().expand_on = true;
+    ev->prog().expand_mask = mask;
     return ZKB_OK;
 }
 

@@ -117,13 +117,67 @@ public:
         cb_count[CB_COPY]++;
         return keep_copies ? push_value(V_COPY, a, 0) : a;
     }
-    uint32_t add(uint32_t a, uint32_t b) { cb_count[CB_ADD]++; return push_value(V_ADD, a, b); }
-    uint32_t multiply(uint32_t a, uint32_t b) { cb_count[CB_MUL]++; return push_value(V_MUL, a, b); }
-    uint32_t add_constant(uint32_t a, const uint8_t* le, size_t n) { cb_count[CB_ADDC]++; return push_value(V_ADDC, a, intern_const(le, n)); }
-    uint32_t mul_constant(uint32_t a, const uint8_t* le, size_t n) { cb_count[CB_MULC]++; return push_value(V_MULC, a, intern_const(le, n)); }
-    uint32_t and_(uint32_t a, uint32_t b) { cb_count[CB_AND]++; return push_value(V_AND, a, b); }
-    uint32_t xor_(uint32_t a, uint32_t b) { cb_count[CB_XOR]++; return push_value(V_XOR, a, b); }
-    uint32_t not_(uint32_t a) { cb_count[CB_NOT]++; return push_value(V_NOT, a, 0); }
+    // `ExpandDefinable` (rust/src/consumers/exp_definable.rs:24-139) in front of the flattener: with expand_on, gates
+    // outside `expand_mask` (gate-set bits of relation.rs:15-25) are rewritten — AddConstant / MulConstant into
+    // Constant + Add / Mul, And <-> Mul, Xor <-> Add, Not into AddConstant(1) — and the conditions on which the
+    // reference panics throw ProgramPanic with its text.
+    struct ProgramPanic {
+        std::string msg;
+    };
+    bool expand_on = false;
+    uint16_t expand_mask = 0;
+    bool allowed(uint16_t bit) const { return !expand_on || (expand_mask & bit) == bit; }
+    uint32_t add(uint32_t a, uint32_t b) {
+        if (!allowed(0x0001)) {
+            if (!allowed(0x0100)) throw ProgramPanic{"Cannot replace ADD by XOR if XOR is not supported."};
+            return raw(CB_XOR, V_XOR, a, b);
+        }
+        return raw(CB_ADD, V_ADD, a, b);
+    }
+    uint32_t multiply(uint32_t a, uint32_t b) {
+        if (!allowed(0x0004)) {
+            if (!allowed(0x0200)) throw ProgramPanic{"Cannot replace MUL by AND if AND is not supported."};
+            return raw(CB_AND, V_AND, a, b);
+        }
+        return raw(CB_MUL, V_MUL, a, b);
+    }
+    uint32_t add_constant(uint32_t a, const uint8_t* le, size_t n) {
+        if (!allowed(0x0002)) return add(a, constant(le, n));
+        cb_count[CB_ADDC]++;
+        return push_value(V_ADDC, a, intern_const(le, n));
+    }
+    uint32_t mul_constant(uint32_t a, const uint8_t* le, size_t n) {
+        if (!allowed(0x0008)) return multiply(a, constant(le, n));
+        cb_count[CB_MULC]++;
+        return push_value(V_MULC, a, intern_const(le, n));
+    }
+    uint32_t and_(uint32_t a, uint32_t b) {
+        if (!allowed(0x0200)) {
+            if (!allowed(0x0004)) throw ProgramPanic{"Cannot replace AND by MUL if MUL is not supported."};
+            return multiply(a, b);
+        }
+        return raw(CB_AND, V_AND, a, b);
+    }
+    uint32_t xor_(uint32_t a, uint32_t b) {
+        if (!allowed(0x0100)) {
+            if (!allowed(0x0001)) throw ProgramPanic{"Cannot replace XOR by ADD if ADD is not supported."};
+            return add(a, b);
+        }
+        return raw(CB_XOR, V_XOR, a, b);
+    }
+    uint32_t not_(uint32_t a) {
+        if (!allowed(0x0400)) {
+            if (!allowed(0x0001)) throw ProgramPanic{"Cannot replace NOT by ADD if ADD is not supported."};
+            const uint8_t one = 1;
+            return add_constant(a, &one, 1);
+        }
+        cb_count[CB_NOT]++;
+        return push_value(V_NOT, a, 0);
+    }
+    uint32_t raw(int cb, uint8_t kind, uint32_t a, uint32_t b) {
+        cb_count[cb]++;
+        return push_value(kind, a, b);
+    }
     void assert_zero(uint32_t v, uint64_t src_wire) {
         cb_count[CB_ASSERT_ZERO]++;
         asserts.push_back(AssertRec{v, n_values(), src_wire});
