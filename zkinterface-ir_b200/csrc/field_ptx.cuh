@@ -35,8 +35,10 @@ __device__ __forceinline__ void mul_pairs4(uint32_t* acc, uint32_t x0, uint32_t 
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
 }
 
-// acc pairs += x_k * y with one carry chain; returns the carry out of the top pair
-__device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y) {
+// acc pairs += x_k * y with one carry chain; returns cin + the carry out of the top pair (cin: the carries this limb
+// position has already collected in this row, so that two chains into the same accumulator need no separate addition)
+__device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y,
+                                               uint32_t cin = 0) {
     uint32_t c;
     asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
         "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
@@ -46,9 +48,9 @@ __device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint3
         "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
-        "addc.u32 %8, 0, 0;"
+        "addc.u32 %8, %14, 0;"
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
-        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(cin));
     return c;
 }
 
@@ -81,15 +83,15 @@ __device__ __forceinline__ void mul_pairs2(uint32_t* acc, uint32_t x0, uint32_t 
         : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3])
         : "r"(x0), "r"(x1), "r"(y));
 }
-__device__ __forceinline__ uint32_t mad_chain2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y) {
+__device__ __forceinline__ uint32_t mad_chain2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y, uint32_t cin = 0) {
     uint32_t c;
     asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
         "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
         "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
         "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
-        "addc.u32 %4, 0, 0;"
+        "addc.u32 %4, %8, 0;"
         : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
-        : "r"(x0), "r"(x1), "r"(y));
+        : "r"(x0), "r"(x1), "r"(y), "r"(cin));
     return c;
 }
 __device__ __forceinline__ uint32_t mad_chain2_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, uint32_t x0, uint32_t x1,
@@ -197,8 +199,8 @@ template <>
 struct PtxChains<8> {
     static __device__ __forceinline__ void mul_even(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs4(acc, x[0], x[2], x[4], x[6], y); }
     static __device__ __forceinline__ void mul_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs4(acc, x[1], x[3], x[5], x[7], y); }
-    static __device__ __forceinline__ uint32_t mad_even(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain4(acc, x[0], x[2], x[4], x[6], y); }
-    static __device__ __forceinline__ uint32_t mad_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain4(acc, x[1], x[3], x[5], x[7], y); }
+    static __device__ __forceinline__ uint32_t mad_even(uint32_t* acc, const uint32_t* x, uint32_t y, uint32_t cin = 0) { return mad_chain4(acc, x[0], x[2], x[4], x[6], y, cin); }
+    static __device__ __forceinline__ uint32_t mad_odd(uint32_t* acc, const uint32_t* x, uint32_t y, uint32_t cin = 0) { return mad_chain4(acc, x[1], x[3], x[5], x[7], y, cin); }
     static __device__ __forceinline__ uint32_t mad_odd_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, const uint32_t* x, uint32_t y) {
         return mad_chain4_fold(e0, f0, f1, acc, x[1], x[3], x[5], x[7], y);
     }
@@ -207,8 +209,8 @@ template <>
 struct PtxChains<4> {
     static __device__ __forceinline__ void mul_even(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs2(acc, x[0], x[2], y); }
     static __device__ __forceinline__ void mul_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { mul_pairs2(acc, x[1], x[3], y); }
-    static __device__ __forceinline__ uint32_t mad_even(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain2(acc, x[0], x[2], y); }
-    static __device__ __forceinline__ uint32_t mad_odd(uint32_t* acc, const uint32_t* x, uint32_t y) { return mad_chain2(acc, x[1], x[3], y); }
+    static __device__ __forceinline__ uint32_t mad_even(uint32_t* acc, const uint32_t* x, uint32_t y, uint32_t cin = 0) { return mad_chain2(acc, x[0], x[2], y, cin); }
+    static __device__ __forceinline__ uint32_t mad_odd(uint32_t* acc, const uint32_t* x, uint32_t y, uint32_t cin = 0) { return mad_chain2(acc, x[1], x[3], y, cin); }
     static __device__ __forceinline__ uint32_t mad_odd_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, const uint32_t* x, uint32_t y) {
         return mad_chain2_fold(e0, f0, f1, acc, x[1], x[3], y);
     }
@@ -236,8 +238,8 @@ __device__ __forceinline__ void fe_mont_mul_chain(uint32_t* r, const uint32_t* a
         cO = Ch::mad_odd_fold(nE[0], O[0], E[1], nO, a, b[i]);   // nE[0] = O[0] + E[1]; carry rides into the odd chain
         cE = Ch::mad_even(nE, a, b[i]);
         m = nE[0] * n0inv;
-        cE += Ch::mad_even(nE, p, m);
-        cO += Ch::mad_odd(nO, p, m);
+        cE = Ch::mad_even(nE, p, m, cE);
+        cO = Ch::mad_odd(nO, p, m, cO);
 #pragma unroll
         for (int j = 0; j < N; j++) {
             E[j] = nE[j];
