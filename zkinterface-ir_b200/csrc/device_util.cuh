@@ -95,9 +95,15 @@ template <int N>
 __device__ __forceinline__ void load_raw_value(uint32_t* out, bool& ge_p, const uint8_t* src, uint32_t stride, const FieldParams& fp) {
     uint32_t v[N];
     if (stride == 4 * N && ((uintptr_t)src & 3) == 0) {
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        if (N >= 4 && ((uintptr_t)src & 15) == 0) {  // whole elements as 16-byte vectors
+            const uint4* s128 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
-        for (int k = 0; k < N; k++) v[k] = s32[k];
+            for (int k = 0; k < N / 4; k++) unpack(__ldg(s128 + k), v + 4 * k);
+        } else {
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+            for (int k = 0; k < N; k++) v[k] = s32[k];
+        }
         uint32_t borrow = 0;
 #pragma unroll
         for (int k = 0; k < N; k++) {
