@@ -309,6 +309,10 @@ def main():
             roofline["traffic"] = ratio * roofline["algorithmic_bytes_per_launch"]
             roofline["traffic_source"] = ("profiles/traffic.json: dram__bytes_read+write of 3 captured k_level launches = "
                                           f"{ratio:.3f} x their algorithmic bytes, scaled to the average launch")
+            roofline["dram_frac"] = roofline["frac"] * ratio
+            roofline["note"] = ("frac counts ALGORITHMIC bytes (3E per two-input gate, E per assertion) and can exceed 1: "
+                                f"{(1 - ratio) * 100:.1f} % of them never reach DRAM (operands shared inside a wavefront hit L2, "
+                                "fused-assert-only values are not stored); dram_frac = measured DRAM traffic / copy peak")
         except Exception:
             pass
 
