@@ -113,6 +113,22 @@ def test_binary_field_flat():
     _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0, 31, 32, 69))
 
 
+@pytest.mark.parametrize("n_batch", [128, 200, 1000])
+def test_binary_field_wide_tiles_four_words_per_thread(n_batch):
+    """>= 128 witnesses: the Boolean kernel takes four 32-witness words per thread (16-byte vectors); ragged tiles, raw
+    input values >= 2 (trap 1) in some witnesses, assertions failing in different words"""
+    c = circuits()
+    p = 2
+    gates, pool, n_wires = random_flat_program(p, 3000, 6, 10, seed=78 + n_batch, bool_ops=True)
+    rng = np.random.default_rng(n_batch)
+    inst = rng.integers(0, 2, size=(n_batch, 6, 1), dtype=np.uint8)
+    wit = rng.integers(0, 2, size=(n_batch, 10, 1), dtype=np.uint8)
+    for j in (1, 33, 97, n_batch - 1):
+        wit[j, 3, 0] = 2 + (j % 5)          # unreduced inputs: non-zero integers that are 0 or 1 mod 2
+        inst[j, 1, 0] = 3
+    _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0, 1, 31, 32, 97, 127, n_batch - 1))
+
+
 def test_structural_errors_match_reference_text():
     z = zkb()
     c = circuits()

@@ -352,49 +352,76 @@ k_bool_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32
     }
 }
 
+// one 32-witness word of a Boolean gate
+__device__ __forceinline__ uint32_t bool_gate_word(uint32_t opc, uint32_t a, uint32_t b, uint32_t cbit) {
+    switch (opc) {
+        case D_ADD:
+        case D_XOR: return a ^ b;
+        case D_MUL:
+        case D_AND: return a & b;
+        case D_ADDC: return a ^ (0u - cbit);
+        case D_MULC: return a & (0u - cbit);
+        case D_NOT: return ~a;
+        default: return a;
+    }
+}
+
+// thread <-> (gate, WPT consecutive 32-witness words).  WPT = 4 (one 16-byte vector per operand, 512 bytes per warp
+// request) whenever a tile holds at least 128 witnesses; WPT = 1 for narrower tiles.
+template <int WPT>
 __global__ void __launch_bounds__(256)
 k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
              const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag,
              TileGeom g) {
+    using V = typename Vec<WPT>::T;
+    constexpr uint32_t kLog2Wpt = WPT == 4 ? 2 : 0;
     const uint32_t log2_words = g.log2_wt - 5;
-    const uint64_t total = n_ops << log2_words;
-    const uint32_t wmask = (1u << log2_words) - 1;
+    const uint32_t log2_vecs = log2_words - kLog2Wpt;  // vectors per slot
+    const uint64_t total = n_ops << log2_vecs;
+    const uint32_t vmask = (1u << log2_vecs) - 1;
+    V* vstore = reinterpret_cast<V*>(store);
     for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
          tid += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t w = (uint32_t)tid & wmask;
-        const uint64_t gi = tid >> log2_words;
+        const uint32_t vw = (uint32_t)tid & vmask;
+        const uint64_t gi = tid >> log2_vecs;
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ops) + gi);
         const uint32_t opc = raw.w & 0xff;
-        const uint32_t a = store[((size_t)raw.x << log2_words) + w];
-        uint32_t r;
-        switch (opc) {
-            case D_ADD:
-            case D_XOR: r = a ^ store[((size_t)raw.y << log2_words) + w]; break;
-            case D_MUL:
-            case D_AND: r = a & store[((size_t)raw.y << log2_words) + w]; break;
-            case D_ADDC: r = a ^ (0u - (__ldg(const_bits + raw.y) & 1)); break;
-            case D_MULC: r = a & (0u - (__ldg(const_bits + raw.y) & 1)); break;
-            case D_NOT: r = ~a; break;
-            default: r = a; break;
-        }
+        const bool two = opc == D_ADD || opc == D_XOR || opc == D_MUL || opc == D_AND;
+        uint32_t a[WPT], b[WPT], r[WPT];
+        unpack(vstore[((size_t)raw.x << log2_vecs) + vw], a);
+        if (two) unpack(vstore[((size_t)raw.y << log2_vecs) + vw], b);
+        const uint32_t cbit = (opc == D_ADDC || opc == D_MULC) ? (__ldg(const_bits + raw.y) & 1) : 0u;
+#pragma unroll
+        for (int k = 0; k < WPT; k++) r[k] = bool_gate_word(opc, a[k], two ? b[k] : 0u, cbit);
         if ((raw.w & F_RAW) && rawflag != nullptr) {  // input values >= 2 are non-zero integers (trap 1)
-            uint32_t nz = 0;
-            const uint8_t* f = rawflag + ((size_t)raw.x << g.log2_wt) + ((size_t)w << 5);
-            for (int bq = 0; bq < 32; bq++) nz |= (uint32_t)(f[bq] != 0) << bq;
-            if (opc == D_NOT) r &= ~nz;
-            else r |= nz;
+#pragma unroll
+            for (int k = 0; k < WPT; k++) {
+                const uint32_t w = vw * WPT + k;
+                uint32_t nz = 0;
+                const uint8_t* f = rawflag + ((size_t)raw.x << g.log2_wt) + ((size_t)w << 5);
+                for (int bq = 0; bq < 32; bq++) nz |= (uint32_t)(f[bq] != 0) << bq;
+                if (opc == D_NOT) r[k] &= ~nz;
+                else r[k] |= nz;
+            }
         }
-        if (!(raw.w & F_NOSTORE)) store[((size_t)raw.z << log2_words) + w] = r;
+        if (!(raw.w & F_NOSTORE)) {
+            V v;
+            pack(v, r);
+            vstore[((size_t)raw.z << log2_vecs) + vw] = v;
+        }
         if (raw.w & F_ASSERT) {
-            uint32_t first_lane = w << 5;
-            uint32_t valid = g.n_valid > first_lane ? (g.n_valid - first_lane >= 32 ? 0xFFFFFFFFu : ((1u << (g.n_valid - first_lane)) - 1)) : 0u;
-            uint32_t bad = r & valid;
-            if (bad) {
-                uint32_t seq = __ldg(aseq + gi);
-                while (bad) {
-                    int bpos = __ffs(bad) - 1;
-                    bad &= bad - 1;
-                    atomicMin(first_fail + g.batch0 + first_lane + bpos, seq);
+#pragma unroll
+            for (int k = 0; k < WPT; k++) {
+                const uint32_t first_lane = (vw * WPT + k) << 5;
+                uint32_t valid = g.n_valid > first_lane ? (g.n_valid - first_lane >= 32 ? 0xFFFFFFFFu : ((1u << (g.n_valid - first_lane)) - 1)) : 0u;
+                uint32_t bad = r[k] & valid;
+                if (bad) {
+                    uint32_t seq = __ldg(aseq + gi);
+                    while (bad) {
+                        int bpos = __ffs(bad) - 1;
+                        bad &= bad - 1;
+                        atomicMin(first_fail + g.batch0 + first_lane + bpos, seq);
+                    }
                 }
             }
         }
@@ -541,8 +568,13 @@ void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t*
 void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
                        uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, int sm_count, cudaStream_t s) {
     if (n_ops == 0) return;
-    unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, grid_per_sm(256));
-    k_bool_level<<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g);
+    if (g.log2_wt >= 7) {  // >= 128 witnesses: four words per thread
+        unsigned grid = grid_for(n_ops << (g.log2_wt - 7), sm_count, grid_per_sm(256));
+        k_bool_level<4><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g);
+    } else {
+        unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, grid_per_sm(256));
+        k_bool_level<1><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g);
+    }
 }
 
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
