@@ -533,8 +533,6 @@ struct zkb_validator {
                     }
                 if (!match_name(cx.name))
                     violate("The iterator name (" + cx.name + ") should match the following format (" + kNamesRegex + ").");
-                known_iterators->push_back({cx.name, cx.first});
-                const size_t slot = known_iterators->size() - 1;
                 for (uint64_t i = cx.first; i <= cx.last; i++) {
                     step();
                     // HashMap::insert on the shared map: a nested loop may have removed / re-added the name
@@ -545,7 +543,6 @@ struct zkb_validator {
                             found = true;
                         }
                     if (!found) known_iterators->push_back({cx.name, i});
-                    (void)slot;
                     std::vector<uint64_t> eo = iterexprs(cx.it_outputs), ei = iterexprs(cx.it_inputs);
                     for (uint64_t w : ei) ensure_defined_and_set(w);
                     uint64_t ic = 0, wc = 0;
