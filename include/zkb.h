@@ -320,6 +320,9 @@ int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops
  * {first group, A ones | A general << 16, B ones | B general << 16, C ones | C general << 16} (group counts per term
  * class); terms: 32 x {col, coefficient tag} per group (tag 0xFFFFFFFF: padding, 0xFFFFFFFE: coefficient one, else the
  * table index; zero coefficients are dropped); row_ids: sorted position -> row.  NULL pointers are skipped. */
+/* hash of the finalized device plan (ops, assertion table, input loads, slot map): the levelizer's threaded passes must
+ * give the plan its sequential form gives (ZKB_PLAN_THREADS) */
+int zkb_debug_plan_hash(zkb_ctx* ctx, uint64_t* out);
 /* FlatBuffers reader -> owned structs -> writer on one size-prefixed message (round-trip tests); *out is valid until
  * the next call on this thread. */
 int zkb_debug_rewrite_message(zkb_ctx* ctx, const uint8_t* buf, size_t len, const uint8_t** out, size_t* out_len);

@@ -76,7 +76,7 @@ EXPORTED = [
     "zkb_validator_ingest_buffer", "zkb_validator_ingest_paths", "zkb_validator_get_violations", "zkb_validator_violation",
     "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_metrics_create", "zkb_metrics_destroy", "zkb_metrics_ingest_message",
     "zkb_metrics_ingest_buffer", "zkb_metrics_ingest_paths", "zkb_metrics_json", "zkb_metrics_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
-    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_write_flat_relation",
+    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_plan_hash", "zkb_debug_write_flat_relation",
 ]
 
 _vp, _u8p, _sz, _u64, _u32, _i = C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
@@ -162,6 +162,7 @@ _sig("zkb_r1cs_run", _i, _vp, _vp)
 _sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
 _sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
 _sig("zkb_debug_r1cs_layout", _i, _vp, _i, _u64p, _vp, _vp, _vp)
+_sig("zkb_debug_plan_hash", _i, _vp, _u64p)
 _sig("zkb_debug_rewrite_message", _i, _vp, _u8p, _sz, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
 _sig("zkb_debug_write_flat_relation", _i, _vp, _u8p, _sz, _i, _vp, _u64, _u8p, _sz, _u64, C.POINTER(C.c_void_p),
      C.POINTER(C.c_size_t))
@@ -448,6 +449,11 @@ class GpuBackend:
         self._chk(_lib.zkb_debug_write_flat_relation(self._c, _buf(m), len(m), int(is_boolean), gates.ctypes.data, len(gates),
                                                      _buf(pool), pool.shape[1], pool.shape[0], C.byref(ptr), C.byref(n)))
         return C.string_at(ptr.value, n.value)
+
+    def plan_hash(self) -> int:
+        out = C.c_uint64()
+        self._chk(_lib.zkb_debug_plan_hash(self._c, C.byref(out)))
+        return out.value
 
     def rewrite_message(self, buf: bytes) -> bytes:
         """C++ reader -> owned structs -> C++ writer (round-trip tests)"""

@@ -680,6 +680,33 @@ extern "C" int zkb_set_limits(zkb_ctx* c, uint64_t max_values, uint64_t max_step
     return ZKB_OK;
 }
 
+// FNV-1a over the whole device plan (ops, assertion table, input loads, slot map, level offsets): two plans of the
+// same program must be identical whatever the number of host threads that built them
+extern "C" int zkb_debug_plan_hash(zkb_ctx* c, uint64_t* out) {
+    if (!c->finalized) return c->fail(ZKB_E_ARG, "zkb_finalize must be called first");
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) {
+        const uint8_t* b = (const uint8_t*)p;
+        for (size_t i = 0; i < n; i++) {
+            h ^= b[i];
+            h *= 1099511628211ull;
+        }
+    };
+    const Plan& pl = c->plan;
+    mix(pl.ops.data(), pl.ops.size() * sizeof(GateOp));
+    mix(pl.op_assert_seq.data(), pl.op_assert_seq.size() * 4);
+    mix(pl.loads.data(), pl.loads.size() * sizeof(InputLoad));
+    mix(pl.slot_of_value.data(), pl.slot_of_value.size() * 4);
+    mix(pl.readable.data(), pl.readable.size());
+    mix(pl.level_off.data(), pl.level_off.size() * 8);
+    mix(pl.level_rare.data(), pl.level_rare.size() * 8);
+    mix(&pl.n_slots, 4);
+    mix(&pl.n_reused_slots, 8);
+    mix(pl.n_dev_ops, sizeof(pl.n_dev_ops));
+    *out = h;
+    return ZKB_OK;
+}
+
 extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
     memset(s, 0, sizeof(*s));
     const Program& p = c->prog;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 
 namespace zkb {
 
@@ -139,6 +140,43 @@ static inline uint32_t dev_op_of(uint8_t k) {
     }
 }
 
+// The passes of Plan::build that walk values in sorted (i.e. random) order wait on DRAM latency, not on arithmetic:
+// a few threads multiply the misses in flight.  Every parallel pass produces exactly what its sequential form does
+// (positions, slots and release order are derived from prefix sums, not from arrival order).
+static unsigned plan_threads() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZKB_PLAN_THREADS");
+        unsigned hw = std::thread::hardware_concurrency();
+        v = e ? atoi(e) : (int)std::min(8u, hw ? hw : 1u);
+        if (v < 1) v = 1;
+    }
+    return (unsigned)v;
+}
+
+// fn(chunk index, begin, end) over [0, n) cut into T equal chunks
+template <class F>
+static void parallel_chunks(unsigned T, uint64_t n, F fn) {
+    if (T < 2 || n == 0) {
+        fn(0u, (uint64_t)0, n);
+        return;
+    }
+    const uint64_t chunk = (n + T - 1) / T;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < T; t++) {
+        uint64_t b = std::min(n, t * chunk), e = std::min(n, (t + 1) * chunk);
+        pool.emplace_back([=, &fn]() { fn(t, b, e); });
+    }
+    fn(0u, (uint64_t)0, std::min(n, chunk));
+    for (auto& th : pool) th.join();
+}
+
+static inline void atomic_max_u32(uint32_t* p, uint32_t val) {
+    uint32_t cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (cur < val && !__atomic_compare_exchange_n(p, &cur, val, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+    }
+}
+
 void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>* live_values) {
     const bool timing = getenv("ZKB_TIMING") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
@@ -149,6 +187,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         t_last = now;
     };
     const uint32_t n = prog.n_values();
+    const unsigned T = n >= (1u << 18) ? plan_threads() : 1;
     const uint8_t* kind = prog.kind.data();
     const uint32_t* opa = prog.opa.data();
     const uint32_t* opb = prog.opb.data();
@@ -188,8 +227,14 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint8_t> observable;
     if (!keep_all) {
         observable.assign(n, 0);
-        if (live_values)
-            for (uint32_t v : *live_values) observable[v] = 1;
+        if (live_values) {
+            const uint32_t* lv = live_values->data();
+            uint8_t* obs = observable.data();
+            parallel_chunks(live_values->size() >= (1u << 18) ? T : 1, live_values->size(),
+                            [&](unsigned, uint64_t b, uint64_t e) {
+                                for (uint64_t i = b; i < e; i++) obs[lv[i]] = 1;
+                            });
+        }
     }
 
     // standalone asserts on level-0 values run in level 1
@@ -204,11 +249,19 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     n_levels = max_level;
 
     lap("asserts/observable");
-    // counting sort of device ops by (level, opcode)
+    // counting sort of device ops by (level, opcode); per-thread histograms over contiguous chunks of the value list give
+    // every thread its own starting offsets, so the placement below is stable (same order as a sequential sort)
     const size_t n_keys = (size_t)n_levels * D_OPS;
+    const unsigned Tsort = (T > 1 && n_keys * T <= n / 4) ? T : 1;
+    std::vector<std::vector<uint64_t>> hist(Tsort, std::vector<uint64_t>(n_keys, 0));
+    parallel_chunks(Tsort, n, [&](unsigned t, uint64_t b, uint64_t e) {
+        uint64_t* h = hist[t].data();
+        for (uint64_t v = b; v < e; v++)
+            if (kind[v] > V_WITNESS) h[(size_t)(level[v] - 1) * D_OPS + dev_op_of(kind[v])]++;
+    });
     std::vector<uint64_t> cnt(n_keys + 1, 0);
-    for (uint32_t v = 0; v < n; v++)
-        if (kind[v] > V_WITNESS) cnt[(size_t)(level[v] - 1) * D_OPS + dev_op_of(kind[v]) + 1]++;
+    for (unsigned t = 0; t < Tsort; t++)
+        for (size_t k = 0; k < n_keys; k++) cnt[k + 1] += hist[t][k];
     cnt[(size_t)0 * D_OPS + D_ASSERT + 1] += input_assert_seq.size();
     for (size_t i = 0; i < n_keys; i++) cnt[i + 1] += cnt[i];
     const uint64_t n_ops = cnt[n_keys];
@@ -227,21 +280,25 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint32_t> last_use;
     if (reuse) {
         last_use.assign(n, 0);
-        for (uint32_t v = 0; v < n; v++) {
-            if (v + kAhead < n) {
-                __builtin_prefetch(&last_use[opa[v + kAhead]], 1);
-                __builtin_prefetch(&last_use[opb[v + kAhead] < n ? opb[v + kAhead] : 0], 1);
+        uint32_t* lu = last_use.data();
+        parallel_chunks(T, n, [&](unsigned, uint64_t b, uint64_t e) {  // a maximum: order of the updates is irrelevant
+            for (uint64_t v = b; v < e; v++) {
+                if (v + kAhead < e) {
+                    __builtin_prefetch(&lu[opa[v + kAhead]], 1);
+                    __builtin_prefetch(&lu[opb[v + kAhead] < n ? opb[v + kAhead] : 0], 1);
+                }
+                uint8_t k = kind[v];
+                if (k <= V_WITNESS) continue;
+                atomic_max_u32(&lu[opa[v]], level[v]);
+                if (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR) atomic_max_u32(&lu[opb[v]], level[v]);
             }
-            uint8_t k = kind[v];
-            if (k <= V_WITNESS) continue;
-            if (level[v] > last_use[opa[v]]) last_use[opa[v]] = level[v];
-            if (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR)
-                if (level[v] > last_use[opb[v]]) last_use[opb[v]] = level[v];
-        }
+        });
         for (uint32_t v : input_assert_value)
             if (last_use[v] < 1) last_use[v] = 1;
-        for (uint32_t v = 0; v < n; v++)
-            if (observable[v]) last_use[v] = kForever;
+        parallel_chunks(T, n, [&](unsigned, uint64_t b, uint64_t e) {
+            for (uint64_t v = b; v < e; v++)
+                if (observable[v]) lu[v] = kForever;
+        });
     }
     // slots released once wavefront l has run (re-usable from wavefront l + 1 on: inside one launch a slot is
     // never both read and written)
@@ -264,16 +321,24 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             if (reuse && last_use[v] != kForever) release_after[last_use[v]].push(next_slot, kInputWriter);
             next_slot++;
         }
-    std::vector<uint64_t> pos_of_value(n, 0);
-    {
-        std::vector<uint64_t> cur(cnt.begin(), cnt.end() - 1);
-        for (uint32_t v = 0; v < n; v++)
-            if (kind[v] > V_WITNESS) pos_of_value[v] = cur[(size_t)(level[v] - 1) * D_OPS + dev_op_of(kind[v])]++;
-    }
-    // slots must follow the sorted order, so walk ops by position
+    // slots must follow the sorted order, so ops are walked by position: value_at[position] = value
     std::vector<uint32_t> value_at(n_ops, kNoSlot);
-    for (uint32_t v = 0; v < n; v++)
-        if (kind[v] > V_WITNESS) value_at[pos_of_value[v]] = v;
+    {
+        // start[t][key] = first position of thread t's values with that key
+        std::vector<uint64_t> run(cnt.begin(), cnt.end() - 1);
+        for (unsigned t = 0; t < Tsort; t++)
+            for (size_t k = 0; k < n_keys; k++) {
+                uint64_t c = hist[t][k];
+                hist[t][k] = run[k];
+                run[k] += c;
+            }
+        uint32_t* va = value_at.data();
+        parallel_chunks(Tsort, n, [&](unsigned t, uint64_t b, uint64_t e) {
+            uint64_t* cur = hist[t].data();
+            for (uint64_t v = b; v < e; v++)
+                if (kind[v] > V_WITNESS) va[cur[(size_t)(level[v] - 1) * D_OPS + dev_op_of(kind[v])]++] = (uint32_t)v;
+        });
+    }
     lap("placement");
     ops.assign(n_ops, GateOp{0, 0, 0, 0});
     op_assert_seq.assign(n_ops, kNoSeq);
@@ -294,79 +359,116 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                 ReleaseList().slots.swap(rel.slots);
             }
         }
-        for (uint64_t i = level_off[l]; i < level_off[l + 1]; i++) {
-            if (i + kAhead < n_ops) {  // values arrive in sorted, i.e. random, order: start their loads early
-                uint32_t va = value_at[i + kAhead];
-                if (va != kNoSlot) {
-                    __builtin_prefetch(&kind[va]);
-                    __builtin_prefetch(&aseq[va]);
-                    __builtin_prefetch(&used[va]);
-                    if (!keep_all) __builtin_prefetch(&observable[va]);
-                    if (reuse) __builtin_prefetch(&last_use[va]);
-                    __builtin_prefetch(&slot_of_value[va], 1);
-                    __builtin_prefetch(&readable[va], 1);
+        // The k-th stored value of the wavefront takes the k-th free slot (ascending), then fresh slots: positions come
+        // from a prefix sum over chunks of the wavefront, so the chunks can be processed by different threads.
+        const uint64_t lo = level_off[l], hi = level_off[l + 1];
+        const unsigned Tl = (T > 1 && hi - lo >= (1u << 16)) ? T : 1;
+        std::vector<uint64_t> stored(Tl + 1, 0);
+        // pass A: the store decision and the flags of every op
+        parallel_chunks(Tl, hi - lo, [&](unsigned t, uint64_t b, uint64_t e) {
+            uint64_t cnt_store = 0;
+            for (uint64_t i = lo + b; i < lo + e; i++) {
+                if (i + kAhead < lo + e) {  // values arrive in sorted, i.e. random, order: start their loads early
+                    uint32_t va = value_at[i + kAhead];
+                    if (va != kNoSlot) {
+                        __builtin_prefetch(&kind[va]);
+                        __builtin_prefetch(&aseq[va]);
+                        __builtin_prefetch(&used[va]);
+                        if (!keep_all) __builtin_prefetch(&observable[va]);
+                    }
                 }
+                uint32_t v = value_at[i];
+                if (v == kNoSlot) continue;  // standalone assert position
+                uint32_t meta = dev_op_of(kind[v]);
+                bool has_assert = aseq[v] != kNoSeq;
+                if (has_assert) meta |= F_ASSERT;
+                // stored unless nothing will ever read it: a value only tested by its own fused assertion, or
+                // (with slot re-use on) a dead value — it is still computed
+                bool store = keep_all || used[v] || observable[v] || (!has_assert && !reuse);
+                if (!store) meta |= F_NOSTORE;
+                else cnt_store++;
+                meta_of[i] = meta;
             }
-            uint32_t v = value_at[i];
-            if (v == kNoSlot) continue;  // standalone assert position
-            uint32_t meta = dev_op_of(kind[v]);
-            bool has_assert = aseq[v] != kNoSeq;
-            if (has_assert) meta |= F_ASSERT;
-            // stored unless nothing will ever read it: a value only tested by its own fused assertion, or
-            // (with slot re-use on) a dead value — it is still computed
-            bool store = keep_all || used[v] || observable[v] || (!has_assert && !reuse);
-            if (!store) {
-                meta |= F_NOSTORE;
-            } else {
-                uint32_t slot;
-                if (free_head < free_slots.size()) {
-                    slot = free_slots[free_head++];
-                    n_reused_slots++;
-                } else {
-                    slot = next_slot++;
+            stored[t + 1] = cnt_store;
+        });
+        for (unsigned t = 0; t < Tl; t++) stored[t + 1] += stored[t];
+        const uint64_t n_free = free_slots.size() - free_head, n_store = stored[Tl];
+        // pass B: hand out the slots, collect what each stored value releases later
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> released(Tl);  // (wavefront after which it is free, slot)
+        parallel_chunks(Tl, hi - lo, [&](unsigned t, uint64_t b, uint64_t e) {
+            uint64_t k = stored[t];
+            for (uint64_t i = lo + b; i < lo + e; i++) {
+                if (i + kAhead < lo + e) {
+                    uint32_t va = value_at[i + kAhead];
+                    if (va != kNoSlot) {
+                        if (reuse) __builtin_prefetch(&last_use[va]);
+                        if (!keep_all) __builtin_prefetch(&observable[va]);
+                        __builtin_prefetch(&slot_of_value[va], 1);
+                        __builtin_prefetch(&readable[va], 1);
+                    }
                 }
+                uint32_t v = value_at[i];
+                if (v == kNoSlot || (meta_of[i] & F_NOSTORE)) continue;
+                const uint32_t slot = k < n_free ? free_slots[free_head + k] : next_slot + (uint32_t)(k - n_free);
+                k++;
                 slot_of_value[v] = slot;
                 readable[v] = keep_all || observable[v];
-                if (reuse && last_use[v] != kForever) release_after[std::max(last_use[v], l + 1)].push(slot, l);
+                if (reuse && last_use[v] != kForever) released[t].push_back({std::max(last_use[v], l + 1), slot});
             }
-            meta_of[i] = meta;
-        }
+        });
+        const uint64_t n_reused = std::min(n_store, n_free);
+        n_reused_slots += n_reused;
+        free_head += n_reused;
+        next_slot += (uint32_t)(n_store - n_reused);
+        for (unsigned t = 0; t < Tl; t++)  // chunk order = ascending slots: one ascending run per target list
+            for (const auto& rs : released[t]) release_after[rs.first].push(rs.second, l);
     }
     n_slots = next_slot;
     lap("slot assignment");
     // pass 2: emit ops with operand slots
-    for (uint64_t i = 0; i < n_ops; i++) {
-        if (i + 2 * kAhead < n_ops) {  // two-stage prefetch: the value's record, then its operands' slots
-            uint32_t v2 = value_at[i + 2 * kAhead];
-            if (v2 != kNoSlot) {
-                __builtin_prefetch(&opa[v2]);
-                __builtin_prefetch(&opb[v2]);
-                __builtin_prefetch(&kind[v2]);
-                __builtin_prefetch(&aseq[v2]);
-                __builtin_prefetch(&slot_of_value[v2]);
+    {
+        const unsigned Te = (T > 1 && n_ops >= (1u << 16)) ? T : 1;
+        std::vector<std::vector<uint64_t>> dev_cnt(Te, std::vector<uint64_t>(D_OPS + 1, 0));  // [D_OPS]: raw ops
+        parallel_chunks(Te, n_ops, [&](unsigned t, uint64_t b, uint64_t e) {
+            uint64_t* dc = dev_cnt[t].data();
+            for (uint64_t i = b; i < e; i++) {
+                if (i + 2 * kAhead < e) {  // two-stage prefetch: the value's record, then its operands' slots
+                    uint32_t v2 = value_at[i + 2 * kAhead];
+                    if (v2 != kNoSlot) {
+                        __builtin_prefetch(&opa[v2]);
+                        __builtin_prefetch(&opb[v2]);
+                        __builtin_prefetch(&kind[v2]);
+                        __builtin_prefetch(&aseq[v2]);
+                        __builtin_prefetch(&slot_of_value[v2]);
+                    }
+                    uint32_t v1 = value_at[i + kAhead];
+                    if (v1 != kNoSlot) {
+                        __builtin_prefetch(&slot_of_value[opa[v1]]);
+                        if (opb[v1] < n) __builtin_prefetch(&slot_of_value[opb[v1]]);
+                    }
+                }
+                uint32_t v = value_at[i];
+                if (v == kNoSlot) continue;
+                uint8_t k = kind[v];
+                GateOp g;
+                g.meta = meta_of[i];
+                g.a = slot_of_value[opa[v]];
+                bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
+                g.b = two ? slot_of_value[opb[v]] : opb[v];
+                g.out = slot_of_value[v];
+                if (k == V_NOT && kind[opa[v]] <= V_WITNESS) {  // not(input): the reference tests the RAW integer
+                    g.meta |= F_RAW;
+                    dc[D_OPS]++;
+                }
+                ops[i] = g;
+                op_assert_seq[i] = aseq[v];
+                dc[g.meta & 0xff]++;
             }
-            uint32_t v1 = value_at[i + kAhead];
-            if (v1 != kNoSlot) {
-                __builtin_prefetch(&slot_of_value[opa[v1]]);
-                if (opb[v1] < n) __builtin_prefetch(&slot_of_value[opb[v1]]);
-            }
+        });
+        for (unsigned t = 0; t < Te; t++) {
+            for (int k = 0; k < D_OPS; k++) n_dev_ops[k] += dev_cnt[t][k];
+            n_raw_ops += dev_cnt[t][D_OPS];
         }
-        uint32_t v = value_at[i];
-        if (v == kNoSlot) continue;
-        uint8_t k = kind[v];
-        GateOp g;
-        g.meta = meta_of[i];
-        g.a = slot_of_value[opa[v]];
-        bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
-        g.b = two ? slot_of_value[opb[v]] : opb[v];
-        g.out = slot_of_value[v];
-        if (k == V_NOT && kind[opa[v]] <= V_WITNESS) {  // not(input): the reference tests the RAW integer
-            g.meta |= F_RAW;
-            n_raw_ops++;
-        }
-        ops[i] = g;
-        op_assert_seq[i] = aseq[v];
-        n_dev_ops[g.meta & 0xff]++;
     }
     {
         uint64_t p = cnt[(size_t)0 * D_OPS + D_ASSERT];
