@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <iterator>
 #include <chrono>
 #include <thread>
 
@@ -304,6 +305,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     // never both read and written)
     std::vector<ReleaseList> release_after(reuse ? (size_t)n_levels + 1 : 0);
     std::vector<uint32_t> free_slots;  // ascending from free_head on: the lowest free slot is handed out first
+    std::vector<uint32_t> free_spare;
     size_t free_head = 0;
     constexpr uint32_t kInputWriter = 0xFFFFFFFEu;
     readable.assign(n, 0);
@@ -346,19 +348,27 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint32_t> meta_of(n_ops, 0);
     n_reused_slots = 0;
     n_raw_ops = 0;
+    double t_free = 0, t_dist = 0;
     for (uint32_t l = 0; l < n_levels; l++) {
+        auto tf0 = std::chrono::steady_clock::now();
         if (reuse) {  // wavefront l+1 may overwrite everything whose last reader ran in wavefront <= l
             ReleaseList& rel = release_after[l];
             if (!rel.slots.empty()) {
                 rel.merge_runs();
-                std::vector<uint32_t> merged;
-                merged.resize(rel.slots.size() + (free_slots.size() - free_head));
-                std::merge(free_slots.begin() + free_head, free_slots.end(), rel.slots.begin(), rel.slots.end(), merged.begin());
-                free_slots.swap(merged);
+                if (free_head == free_slots.size()) {  // nothing left over: the released list is the free list
+                    free_slots.swap(rel.slots);
+                } else {
+                    free_spare.clear();  // capacity is kept from wavefront to wavefront: no fresh pages to fault in
+                    free_spare.reserve(rel.slots.size() + (free_slots.size() - free_head));
+                    std::merge(free_slots.begin() + free_head, free_slots.end(), rel.slots.begin(), rel.slots.end(),
+                               std::back_inserter(free_spare));
+                    free_slots.swap(free_spare);
+                }
                 free_head = 0;
                 ReleaseList().slots.swap(rel.slots);
             }
         }
+        t_free += std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();
         // The k-th stored value of the wavefront takes the k-th free slot (ascending), then fresh slots: positions come
         // from a prefix sum over chunks of the wavefront, so the chunks can be processed by different threads.
         const uint64_t lo = level_off[l], hi = level_off[l + 1];
@@ -397,6 +407,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         std::vector<std::vector<std::pair<uint32_t, uint32_t>>> released(Tl);  // (wavefront after which it is free, slot)
         parallel_chunks(Tl, hi - lo, [&](unsigned t, uint64_t b, uint64_t e) {
             uint64_t k = stored[t];
+            if (reuse) released[t].reserve(stored[t + 1] - stored[t]);
             for (uint64_t i = lo + b; i < lo + e; i++) {
                 if (i + kAhead < lo + e) {
                     uint32_t va = value_at[i + kAhead];
@@ -420,9 +431,12 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         n_reused_slots += n_reused;
         free_head += n_reused;
         next_slot += (uint32_t)(n_store - n_reused);
+        auto td0 = std::chrono::steady_clock::now();
         for (unsigned t = 0; t < Tl; t++)  // chunk order = ascending slots: one ascending run per target list
             for (const auto& rs : released[t]) release_after[rs.first].push(rs.second, l);
+        t_dist += std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
     }
+    if (timing) fprintf(stderr, "  plan   (free-list merges %.3f s, release distribution %.3f s)\n", t_free, t_dist);
     n_slots = next_slot;
     lap("slot assignment");
     // pass 2: emit ops with operand slots
