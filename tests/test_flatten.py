@@ -223,3 +223,21 @@ def test_expand_definable_gate_set_errors_and_cli(tmp_path):
     msgs = [m for n in sorted(os.listdir(out)) for m in F.read_messages((out / n).read_bytes())]
     kinds = {g[0] for m in msgs if isinstance(m, ir.Relation) for g in m.gates}
     assert "AddConstant" not in kinds and "MulConstant" not in kinds and ev.evaluate(msgs) == []
+
+
+def test_flatten_without_a_witness_like_the_verifier():
+    """the IRFlattener takes witness(None) (flattening.rs:178-190): flattening a relation without a witness file emits the
+    Witness gates and no witness message; the evaluating backend would have panicked instead"""
+    z = zkb()
+    msgs = [fx.example_instance(), fx.example_relation()]
+    want, _ = oracle_flatten(msgs)
+    e, (ib, wb, rb) = ours_flatten(msgs)
+    assert wb == b""
+    got = F.read_messages(ib) + F.read_messages(rb)
+    assert [type(m) for m in got] == [type(m) for m in want]
+    assert got[-1].gates == want[-1].gates and got[0].common_inputs == want[0].common_inputs
+    assert sum(1 for g in got[-1].gates if g[0] == "Witness") > 0
+    with pytest.raises(z.ZkbError) as err:                      # not in flatten mode: PlaintextBackend::witness(None) panics
+        ev2 = z.Evaluator(z.GpuBackend(-1))
+        ev2.ingest_source(z.Source.from_buffers([F.write_messages(msgs)]))
+    assert err.value.code == z.ZKB_E_FATAL and str(err.value) == "Missing witness value for PlaintextBackend"

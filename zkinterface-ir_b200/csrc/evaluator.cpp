@@ -39,6 +39,7 @@ struct FunctionDecl {  // evaluator.rs:130-136
 };
 
 using Queue = std::deque<uint32_t>;  // positions in the instance / witness value streams
+constexpr uint32_t kNoWitnessValue = 0xFFFFFFFFu;  // flatten mode: a Witness gate recorded without a value
 using Iters = std::vector<std::pair<std::string, uint64_t>>;
 
 std::string u64s(uint64_t v) { return std::to_string((unsigned long long)v); }
@@ -281,6 +282,13 @@ struct zkb_evaluator {
                 set(scope, g.w0, p.push_value(V_INSTANCE, 0, pos));
             } break;
             case ir::G_WITNESS: {  // :429-432 + PlaintextBackend::witness :944-946 (None => panic)
+                if (witnesses.empty() && p.keep_copies) {
+                    // the IRFlattener accepts witness(None): the gate is emitted, no value is pushed (flattening.rs:178-190,
+                    // builder.rs:261-263) — flattening a relation as the verifier, without a witness file
+                    p.cb_count[CB_WITNESS]++;
+                    set(scope, g.w0, p.push_value(V_WITNESS, 0, kNoWitnessValue));
+                    break;
+                }
                 if (witnesses.empty()) throw Fatal{"Missing witness value for PlaintextBackend"};
                 uint32_t pos = witnesses.front();
                 witnesses.pop_front();
@@ -664,6 +672,7 @@ static int flatten_statement(zkb_evaluator* ev, std::vector<uint8_t>& inst_out, 
             } break;
             case V_WITNESS: {
                 g.type = ir::G_WITNESS;
+                if (b == kNoWitnessValue) break;  // witness(None): gate only
                 const auto& val = ev->witness_values[b];
                 wit.values.push_back(minimal_le(val.data(), val.size()));
                 if (wit.values.size() == kMaxLen) {
