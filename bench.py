@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--log2-gates", type=int, default=24)
     ap.add_argument("--witnesses", type=int, default=4096)
     ap.add_argument("--inputs", type=int, default=1024)
-    ap.add_argument("--field", default="bls381", choices=["bls381", "bn254", "goldilocks"])
+    ap.add_argument("--field", default="bls381", choices=["bls381", "bn254", "goldilocks", "p124", "m31"])
     ap.add_argument("--cpu-sample-log2-gates", type=int, default=22)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verdicts-only", action="store_true",
@@ -44,7 +44,9 @@ def parse():
 
 FIELD = {"bls381": 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
          "bn254": 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
-         "goldilocks": (1 << 64) - (1 << 32) + 1}
+         "goldilocks": (1 << 64) - (1 << 32) + 1,
+         "p124": 16249742125730185677094195492597105093,      # 4 limbs (the modulus of evaluator.rs:956)
+         "m31": (1 << 31) - 1}                                 # 1 limb
 SEED = 0x5EED0003
 
 
