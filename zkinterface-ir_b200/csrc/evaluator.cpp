@@ -36,7 +36,43 @@ struct FunctionDecl {  // evaluator.rs:130-136
     std::shared_ptr<std::vector<ir::Gate>> body;
     std::shared_ptr<std::vector<std::vector<uint8_t>>> consts;  // the message's constant table the body indexes
     uint64_t instance_nbr, witness_nbr, output_count, input_count;
+    // A body made of plain gates only (no Free, Instance, Witness, no nested structure) that is well formed for a fresh
+    // scope — every wire read was written before or is an input, nothing is written twice, every output is written —
+    // behaves identically on every invocation: it is run over a flat array of local wires instead of a Scope
+    // (n_local > 0).  Anything else goes through ingest_subcircuit, which reports errors where the reference does.
+    uint32_t n_local = 0;
 };
+
+uint32_t simple_body_locals(const std::vector<ir::Gate>& body, uint64_t n_out, uint64_t n_in) {
+    constexpr uint64_t kMaxLocal = 1u << 16;
+    if (n_out + n_in >= kMaxLocal) return 0;
+    uint64_t top = n_out + n_in;
+    for (const auto& g : body) {
+        switch (g.type) {
+            case ir::G_CONSTANT: case ir::G_ASSERT_ZERO: case ir::G_COPY: case ir::G_ADD: case ir::G_MUL: case ir::G_ADD_CONSTANT:
+            case ir::G_MUL_CONSTANT: case ir::G_AND: case ir::G_XOR: case ir::G_NOT: break;
+            default: return 0;
+        }
+        if (g.w0 >= kMaxLocal || g.w1 >= kMaxLocal || g.w2 >= kMaxLocal) return 0;
+        top = std::max(top, std::max(g.w0, std::max(g.w1, g.w2)) + 1);
+    }
+    std::vector<uint8_t> defined(top, 0);
+    for (uint64_t w = n_out; w < n_out + n_in; w++) defined[w] = 1;
+    for (const auto& g : body) {
+        const bool two = g.type == ir::G_ADD || g.type == ir::G_MUL || g.type == ir::G_AND || g.type == ir::G_XOR;
+        if (g.type == ir::G_ASSERT_ZERO) {
+            if (!defined[g.w0]) return 0;
+            continue;
+        }
+        if (g.type != ir::G_CONSTANT && !defined[g.w1]) return 0;
+        if (two && !defined[g.w2]) return 0;
+        if (defined[g.w0]) return 0;
+        defined[g.w0] = 1;
+    }
+    for (uint64_t w = 0; w < n_out; w++)
+        if (!defined[w]) return 0;
+    return (uint32_t)std::max<uint64_t>(top, 1);
+}
 
 using Queue = std::deque<uint32_t>;  // positions in the instance / witness value streams
 constexpr uint32_t kNoWitnessValue = 0xFFFFFFFFu;  // flatten mode: a Witness gate recorded without a value
@@ -218,6 +254,56 @@ struct zkb_evaluator {
                           " / Got " + u64s(n_in) + ")."};
     }
 
+    // ingest_subcircuit for a FunctionDecl with n_local > 0: same callbacks in the same order (a copy per input, the
+    // gates, a copy per output: evaluator.rs:698-746 with the simple arms of :344-418 inlined), local wires in an array
+    std::vector<uint32_t> locals;
+    void ingest_simple_function(const FunctionDecl& f, const std::vector<uint64_t>& outs, const std::vector<uint64_t>& ins, Scope& scope,
+                                const uint32_t* weight) {
+        Program& p = prog();
+        if (locals.size() < f.n_local) locals.resize(f.n_local);
+        uint32_t* L = locals.data();
+        const size_t n_out = outs.size();
+        for (size_t idx = 0; idx < ins.size(); idx++) L[n_out + idx] = p.copy(get(scope, ins[idx]));
+        const auto& consts = *f.consts;
+        for (const ir::Gate& g : *f.body) {
+            if (p.n_values() >= c->max_values) throw EvalErr{"zkb: resource limit exceeded (max_values)"};
+            step();
+            switch (g.type) {
+                case ir::G_CONSTANT: {
+                    const auto& v = consts[g.const_idx];
+                    L[g.w0] = p.constant(v.data(), v.size());
+                } break;
+                case ir::G_ASSERT_ZERO: {
+                    uint32_t z = weight ? as_mul(*weight, L[g.w0]) : p.copy(L[g.w0]);
+                    p.assert_zero(z, g.w0);
+                    p.ir_gates++;
+                } break;
+                case ir::G_COPY: L[g.w0] = p.copy(L[g.w1]); break;
+                case ir::G_ADD: L[g.w0] = p.add(L[g.w1], L[g.w2]); p.ir_gates++; break;
+                case ir::G_MUL: L[g.w0] = p.multiply(L[g.w1], L[g.w2]); p.ir_gates++; break;
+                case ir::G_AND: L[g.w0] = p.and_(L[g.w1], L[g.w2]); p.ir_gates++; break;
+                case ir::G_XOR: L[g.w0] = p.xor_(L[g.w1], L[g.w2]); p.ir_gates++; break;
+                case ir::G_ADD_CONSTANT: {
+                    const auto& v = consts[g.const_idx];
+                    L[g.w0] = p.add_constant(L[g.w1], v.data(), v.size());
+                    p.ir_gates++;
+                } break;
+                case ir::G_MUL_CONSTANT: {
+                    const auto& v = consts[g.const_idx];
+                    L[g.w0] = p.mul_constant(L[g.w1], v.data(), v.size());
+                    p.ir_gates++;
+                } break;
+                default: L[g.w0] = p.not_(L[g.w1]); p.ir_gates++; break;  // G_NOT
+            }
+        }
+        for (size_t idx = 0; idx < n_out; idx++) set(scope, outs[idx], p.copy(L[idx]));
+    }
+    void call_function(const FunctionDecl& f, const std::vector<uint64_t>& outs, const std::vector<uint64_t>& ins, Scope& scope,
+                       Iters& fresh, Queue& instances, Queue& witnesses, const uint32_t* weight) {
+        if (f.n_local) ingest_simple_function(f, outs, ins, scope, weight);
+        else ingest_subcircuit(*f.body, *f.consts, outs, ins, scope, fresh, instances, witnesses, weight);
+    }
+
     // ---- evaluator.rs:698-746 --------------------------------------------------------------------
     void ingest_subcircuit(const std::vector<ir::Gate>& sub, const std::vector<std::vector<uint8_t>>& consts,
                            const std::vector<uint64_t>& outs, const std::vector<uint64_t>& ins, Scope& scope, Iters& iters,
@@ -313,7 +399,7 @@ struct zkb_evaluator {
                 expand_wirelist(g.cx->inputs, ei);
                 check_arity(g.cx->name, f, eo.size(), ei.size());
                 Iters fresh;  // named calls do NOT see the caller's iterators (:456)
-                ingest_subcircuit(*f.body, *f.consts, eo, ei, scope, fresh, instances, witnesses, weight);
+                call_function(f, eo, ei, scope, fresh, instances, witnesses, weight);
             } break;
             case ir::G_ANON_CALL: {  // :473-491
                 std::vector<uint64_t> eo, ei;
@@ -342,7 +428,7 @@ struct zkb_evaluator {
                         eval_iterexpr_list(cx.it_inputs, iters, ei);
                         check_arity(cx.fn_name, f, eo.size(), ei.size());
                         fresh.clear();
-                        ingest_subcircuit(*f.body, *f.consts, eo, ei, scope, fresh, instances, witnesses, weight);
+                        call_function(f, eo, ei, scope, fresh, instances, witnesses, weight);
                     } else {
                         eval_iterexpr_list(cx.it_outputs, iters, eo);
                         eval_iterexpr_list(cx.it_inputs, iters, ei);
@@ -404,9 +490,7 @@ struct zkb_evaluator {
                             check_arity(br.name, f, eo.size(), ei.size());
                             for (uint64_t w : ei) bs->set(w, p.copy(get(scope, w)));  // HashMap::insert (:626-629)
                             Iters fresh;
-                            auto body = f.body;
-                            auto fc = f.consts;
-                            ingest_subcircuit(*body, *fc, eo, ei, *bs, fresh, qi, qw, &wbw);
+                            call_function(f, eo, ei, *bs, fresh, qi, qw, &wbw);
                         } else {
                             expand_wirelist(br.inputs, ei);
                             for (uint64_t w : ei) bs->set(w, p.copy(get(scope, w)));
@@ -464,6 +548,7 @@ struct zkb_evaluator {
             d.witness_nbr = f.witness_count;
             d.output_count = f.output_count;
             d.input_count = f.input_count;
+            d.n_local = getenv("ZKB_NO_SIMPLE_CALLS") ? 0 : simple_body_locals(*d.body, d.output_count, d.input_count);
             known_functions[f.name] = std::move(d);
         }
         Iters iters;
