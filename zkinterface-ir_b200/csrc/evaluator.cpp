@@ -159,14 +159,61 @@ struct zkb_evaluator {
     }
 
     // ---- structs/iterators.rs:349-403 ----------------------------------------------------------
+    // affine form of an expression, or false (a DivConst, or a product of two iterator-dependent sides, inside)
+    static bool affine_of(const ir::IterExpr& e, ir::AffineIterExpr& out) {
+        auto add_term = [](ir::AffineIterExpr& f, const std::string& name, uint64_t coef) {
+            for (auto& t : f.terms)
+                if (t.first == name) {
+                    t.second += coef;
+                    return;
+                }
+            f.terms.push_back({name, coef});
+        };
+        switch (e.type) {
+            case 1: out.c0 = e.value; return true;
+            case 2: out.terms.push_back({e.name, 1}); return true;
+            case 3: case 4: case 5: {
+                ir::AffineIterExpr a, b;
+                if (!affine_of(*e.l, a) || !affine_of(*e.r, b)) return false;
+                if (e.type == 5) {
+                    if (!a.terms.empty() && !b.terms.empty()) return false;
+                    const ir::AffineIterExpr& k = a.terms.empty() ? a : b;   // the constant side
+                    const ir::AffineIterExpr& x = a.terms.empty() ? b : a;
+                    out.c0 = k.c0 * x.c0;
+                    for (const auto& t : x.terms) out.terms.push_back({t.first, t.second * k.c0});
+                    return true;
+                }
+                out = a;
+                if (e.type == 3) out.c0 += b.c0;
+                else out.c0 -= b.c0;
+                for (const auto& t : b.terms) add_term(out, t.first, e.type == 3 ? t.second : (uint64_t)0 - t.second);
+                return true;
+            }
+            default: return false;
+        }
+    }
+    static uint64_t lookup_iter(const std::string& name, const Iters& known) {
+        for (size_t i = known.size(); i-- > 0;)
+            if (known[i].first == name) return known[i].second;
+        // evaluate_iterexpr_list unwraps the Err: a panic in the reference (iterators.rs:400)
+        throw Fatal{"Unknown iterator name " + name};
+    }
     static uint64_t eval_iterexpr(const ir::IterExpr& e, const Iters& known) {
+        if (!e.affine_tried) {
+            e.affine_tried = true;
+            if (e.type >= 3) {  // constants and names are already one step
+                auto f = std::make_shared<ir::AffineIterExpr>();
+                if (affine_of(e, *f)) e.affine = f;
+            }
+        }
+        if (e.affine) {
+            uint64_t v = e.affine->c0;
+            for (const auto& t : e.affine->terms) v += t.second * lookup_iter(t.first, known);
+            return v;
+        }
         switch (e.type) {
             case 1: return e.value;
-            case 2:
-                for (size_t i = known.size(); i-- > 0;)
-                    if (known[i].first == e.name) return known[i].second;
-                // evaluate_iterexpr_list unwraps the Err: a panic in the reference (iterators.rs:400)
-                throw Fatal{"Unknown iterator name " + e.name};
+            case 2: return lookup_iter(e.name, known);
             case 3: return eval_iterexpr(*e.l, known) + eval_iterexpr(*e.r, known);  // release build: wrapping
             case 4: return eval_iterexpr(*e.l, known) - eval_iterexpr(*e.r, known);
             case 5: return eval_iterexpr(*e.l, known) * eval_iterexpr(*e.r, known);

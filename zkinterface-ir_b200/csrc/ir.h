@@ -31,11 +31,21 @@ struct WireEl {  // WireListElement: Wire(first) or WireRange(first, last)
 };
 using WireList = std::vector<WireEl>;
 
+// c0 + sum coef_k * iterator(name_k) over Z / 2^64 (the reference's wrapping u64 arithmetic): what an expression made
+// of Const / Name / Add / Sub / Mul-by-a-constant-side is, evaluated without walking the tree
+struct AffineIterExpr {
+    uint64_t c0 = 0;
+    std::vector<std::pair<std::string, uint64_t>> terms;  // first-occurrence order (= the tree's evaluation order)
+};
+
 struct IterExpr {  // IterExprWireNumber, iterators.rs:17-30
     uint8_t type = 0;  // 1 Const, 2 Name, 3 Add, 4 Sub, 5 Mul, 6 DivConst
     uint64_t value = 0;  // Const value / DivConst denominator
     std::string name;
     std::unique_ptr<IterExpr> l, r;
+    // filled by the Evaluator on first use (one evaluator thread per message)
+    mutable bool affine_tried = false;
+    mutable std::shared_ptr<const AffineIterExpr> affine;
 };
 struct IterExprEl {  // Single(first) or Range(first, last)
     bool is_range = false;
