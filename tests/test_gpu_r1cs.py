@@ -156,3 +156,35 @@ def test_r1cs_wide_tiles_use_the_unsplit_layout(name):
         b.r1cs_upload(np.stack(zs[j:j + 1]))
         x = b.r1cs_run()[0]
         assert (-1 if x["ok"] else int(x["first_fail_seq"])) == exp[j]
+
+
+def test_r1cs_row_sharding_over_devices():
+    """one assignment, constraints sharded in row blocks over the GPUs (z replicated), first violated row =
+    MIN over the blocks of (block's first row + local row).  Uses every visible device (1 on the test box: the blocks
+    then run one after the other on device 0); the MIN all-reduce itself is covered by tests/test_sharding_gloo.py."""
+    import importlib
+    import torch
+    c = circuits()
+    z_ = zkb()
+    shard = importlib.import_module("zkir_b200.sharding")
+    p = FIELDS["bn254"]
+    r = c.random_r1cs(3000, 200, p, seed=23)
+    good = c.r1cs_assignment(r, seed=6)
+    bad = list(good)
+    row = 1777
+    bad[r.n_free + 1 + row] = (bad[r.n_free + 1 + row] + 5) % p
+    want = min(row, c.r1cs_first_row_reading(r, r.n_free + 1 + row))
+    n_dev = max(1, torch.cuda.device_count())
+    world = 4
+    for zv, exp in ((good, -1), (bad, want)):
+        zb = c.assignment_bytes(zv, p)[None]
+        parts = []
+        for rank in range(world):
+            A, B, Cm, row0 = shard.shard_r1cs_rows(r.A, r.B, r.C, rank, world)
+            b = z_.GpuBackend(rank % n_dev)
+            b.set_field(p)
+            b.r1cs_load(A, B, Cm, r.coef_table, r.n_vars)
+            parts.append(shard.global_first_row(b.r1cs_check(zb), row0))
+            b.close()
+        ff = np.minimum.reduce(parts)
+        assert (-1 if ff[0] == shard.NO_FAIL else int(ff[0])) == exp

@@ -28,6 +28,9 @@ for k, j in enumerate(range(lo, hi)):
 full = shard.allreduce_first_fail(shard.first_fail_vector(v), lo, hi, total)
 exp = np.array([1000 + j if j % 5 == 0 else int(shard.NO_FAIL) for j in range(total)])
 assert (full == exp).all(), (rank, full, exp)
+# row-sharded R1CS: every rank holds a first violated row per assignment, already shifted to global row numbers
+m = shard.allreduce_min(np.array([500 + rank, int(shard.NO_FAIL) if rank == 0 else 3, int(shard.NO_FAIL)], dtype=np.int64))
+assert m.tolist() == [500, 3, int(shard.NO_FAIL)], m
 print("rank", rank, "ok", lo, hi)
 dist.destroy_process_group()
 '''
@@ -60,3 +63,29 @@ def test_verdict_allreduce_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "rank 0 ok" in outs[0] and "rank 1 ok" in outs[1]
+
+
+def test_r1cs_row_blocks_cover_the_system():
+    import importlib
+    import zkb_loader
+    zkb_loader.load()
+    shard = importlib.import_module("zkir_b200.sharding")
+    c = importlib.import_module("zkir_b200.circuits")
+    r = c.random_r1cs(1001, 50, 101, seed=2)
+    for world in (1, 2, 3, 8):
+        rows = 0
+        for rank in range(world):
+            A, B, C, row0 = shard.shard_r1cs_rows(r.A, r.B, r.C, rank, world)
+            assert row0 == rows
+            n = len(A[0]) - 1
+            for full, part in ((r.A, A), (r.B, B), (r.C, C)):
+                assert int(part[0][0]) == 0 and len(part[1]) == int(part[0][-1]) == len(part[2])
+                e0 = int(full[0][row0])
+                assert (np.asarray(full[1])[e0:e0 + len(part[1])] == part[1]).all()
+                assert (np.diff(part[0].astype(np.int64)) == np.diff(np.asarray(full[0], dtype=np.int64)[row0:row0 + n + 1])).all()
+            rows += n
+        assert rows == r.n_rows
+    v = np.zeros(3, dtype=np.dtype([("ok", "u1"), ("pad", "u1", (7,)), ("first_fail_seq", "<u8")]))
+    v["ok"] = [1, 0, 0]
+    v["first_fail_seq"] = [(1 << 64) - 1, 0, 17]
+    assert shard.global_first_row(v, 500).tolist() == [int(shard.NO_FAIL), 500, 517]
