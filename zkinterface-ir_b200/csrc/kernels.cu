@@ -241,15 +241,17 @@ k_level_pipe(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
 // too small to fill the chip (single-witness statements, deep narrow circuits) the per-level launch latency
 // (~4-5 us) dominates; a grid.sync() costs ~1-2 us.  Operands are read with ld.global.cg because they were
 // written by other SMs earlier in this same launch.
-template <int N>
-__global__ void __launch_bounds__(256)
+// CLUSTER = true: the same loop for programs so narrow that ONE thread-block cluster (8 CTAs on neighbouring SMs of
+// one die) holds a whole wavefront: the barrier between levels is the hardware cluster barrier (barrier.cluster
+// arrive.release / wait.acquire, ~0.2 us) instead of a grid barrier through L2 atomics.
+template <int N, bool CLUSTER>
+__global__ void __launch_bounds__(CLUSTER ? 512 : 256)
 k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
               uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
               const uint8_t* __restrict__ rawflag, TileGeom g, FieldParams fp) {
-    cg::grid_group grid = cg::this_grid();
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // CLUSTER: the grid is exactly one cluster
     const uint64_t tid0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint4* dptr = reinterpret_cast<const uint4*>(ops);
     // the first descriptor of each level is fetched BEFORE the barrier that precedes the level (descriptors
@@ -296,7 +298,10 @@ k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq,
         first = next_first;
         lo = nlo;
         hi = nhi;
-        if (l + 1 < n_levels) grid.sync();
+        if (l + 1 < n_levels) {
+            if (CLUSTER) cg::this_cluster().sync();
+            else cg::this_grid().sync();
+        }
     }
 }
 
@@ -527,12 +532,32 @@ template <int N>
 static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
                                  const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, FieldParams fp,
                                  int sm_count, uint64_t max_level_items, cudaStream_t s) {
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels_coop<N>, 256, 0);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
                     (void*)&first_fail, (void*)&rawflag, (void*)&g, (void*)&fp};
+    // a wavefront that fits one cluster of 8 x 512 threads (two items per thread at most): cluster barrier
+    static const bool no_cluster = getenv("ZKB_NO_CLUSTER") != nullptr;
+    static bool cluster_ok = true;
+    if (!no_cluster && cluster_ok && max_level_items <= 8 * 512 * 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8);
+        cfg.blockDim = dim3(512);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 8;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t ec = cudaLaunchKernelExC(&cfg, (const void*)k_levels_coop<N, true>, args);
+        if (ec == cudaSuccess) return ec;
+        cudaGetLastError();
+        cluster_ok = false;  // not launchable as a cluster here: grid barrier below
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels_coop<N, false>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     // the grid barrier costs more the more CTAs take part: use only as many CTAs (a multiple of the SM count)
     // as the widest level can occupy
     uint64_t want = (max_level_items + 255) / 256;
@@ -540,7 +565,7 @@ static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const 
     if (blocks < (uint64_t)sm_count) blocks = sm_count;
     if (blocks > (uint64_t)sm_count * per_sm) blocks = (uint64_t)sm_count * per_sm;
     if (const char* e = getenv("ZKB_COOP_BLOCKS")) blocks = (uint64_t)atoi(e);
-    return cudaLaunchCooperativeKernel((void*)k_levels_coop<N>, dim3((unsigned)blocks), dim3(256), args, 0, s);
+    return cudaLaunchCooperativeKernel((void*)k_levels_coop<N, false>, dim3((unsigned)blocks), dim3(256), args, 0, s);
 }
 
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
