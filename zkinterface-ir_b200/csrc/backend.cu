@@ -481,21 +481,49 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     // launch-bound programs (levels far too small to fill the chip): all wavefronts in one cooperative launch
     bool coop = !p.binary && pl.n_levels > 1 && ((uint64_t)pl.max_level_ops << c->log2_wt) <= (uint64_t)c->sm_count * 8192;
     if (const char* e = getenv("ZKB_COOP")) coop = coop && atoi(e) != 0;
+    uint32_t first_level = 0;  // levels [0, first_level) have been run by the all-levels launches below
     if (coop && c->coop_supported) {
-        cudaError_t e = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, rawflag,
-                                           g, p.fp, c->sm_count, (uint64_t)pl.max_level_ops << c->log2_wt, c->stream);
-        if (e == cudaSuccess) {
+        // Runs of at least three consecutive wavefronts that each fit one thread-block cluster (8 x 512 threads, two
+        // items per thread) go to the cluster-barrier kernel, the wavefronts between them to the grid-barrier kernel:
+        // a random circuit is narrow at both ends and wide in the middle.
+        const uint64_t kClusterItems = 8 * 512 * 2;
+        auto items = [&](uint32_t l) { return (pl.level_off[l + 1] - pl.level_off[l]) << c->log2_wt; };
+        std::vector<uint8_t> narrow(pl.n_levels);
+        for (uint32_t l = 0; l < pl.n_levels; l++) narrow[l] = items(l) <= kClusterItems;
+        for (uint32_t l = 0; l < pl.n_levels;) {  // short narrow runs are not worth a launch of their own
+            uint32_t e = l;
+            while (e < pl.n_levels && narrow[e] == narrow[l]) e++;
+            if (narrow[l] && e - l < 3 && !(l == 0 && e == pl.n_levels))
+                for (uint32_t k = l; k < e; k++) narrow[k] = 0;
+            l = e;
+        }
+        bool ok = true;
+        for (uint32_t l = 0; l < pl.n_levels && ok;) {
+            uint32_t e = l;
+            uint64_t widest = 0;
+            while (e < pl.n_levels && narrow[e] == narrow[l]) widest = std::max(widest, items(e++));
+            cudaError_t err = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off + l, e - l, c->d_store, c->d_consts, d_fail,
+                                                 rawflag, g, p.fp, c->sm_count, narrow[l] ? widest : std::max(widest, kClusterItems + 1),
+                                                 c->stream);
+            if (err != cudaSuccess) {
+                if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: cooperative launch failed: %s\n", cudaGetErrorString(err));
+                cudaGetLastError();          // not launchable cooperatively: one launch per level from here on
+                c->coop_supported = false;
+                ok = false;
+                break;
+            }
             (*launches)++;
             if (level_launches) (*level_launches)++;
+            first_level = e;
+            l = e;
+        }
+        if (first_level == pl.n_levels) {
             if (timed) cudaEventRecord(c->tile_ev[2 * tile + 1], c->stream);
             c->resident_tile = tile;
             return;
         }
-        if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: cooperative launch failed: %s\n", cudaGetErrorString(e));
-        cudaGetLastError();          // not launchable cooperatively: fall through to one launch per level
-        c->coop_supported = false;
     }
-    for (uint32_t l = 0; l < pl.n_levels; l++) {
+    for (uint32_t l = first_level; l < pl.n_levels; l++) {
         uint64_t lo = pl.level_off[l], mid = pl.level_rare[l], hi = pl.level_off[l + 1];
         if (p.binary) {
             if (hi > lo) {
