@@ -63,3 +63,51 @@ def test_sell_layout_reproduces_the_csr(n_rows, sigma, kind, monkeypatch):
     with pytest.raises(z.ZkbError) as e:
         b.r1cs_upload(np.zeros((1, r.n_vars, 32), dtype=np.uint8))
     assert e.value.code in (z.ZKB_E_CUDA, z.ZKB_E_FATAL)
+
+
+def test_r1cs_load_rejects_malformed_systems():
+    """argument validation of zkb_r1cs_load (host-only context): the reference's own error text for an undefined variable
+    (from_r1cs.rs:90), plain argument errors for the rest"""
+    c = circuits()
+    z = zkb()
+    p = FIELDS["bn254"]
+    r = c.random_r1cs(50, 10, p, seed=1)
+
+    def load(A=None, B=None, C=None, table=None, n_vars=None, field=True):
+        b = z.GpuBackend(-1)
+        if field:
+            b.set_field(p)
+        b.r1cs_load(A or r.A, B or r.B, C or r.C, r.coef_table if table is None else table, r.n_vars if n_vars is None else n_vars)
+        return b
+
+    load()
+    with pytest.raises(z.ZkbError) as e:                              # set_field first
+        load(field=False)
+    assert e.value.code == z.ZKB_E_ARG
+    bad_col = (r.A[0], r.A[1].copy(), r.A[2])
+    bad_col[1][3] = r.n_vars + 5
+    with pytest.raises(z.ZkbError) as e:
+        load(A=bad_col)
+    assert e.value.code == z.ZKB_E_SEMANTIC and str(e.value) == f"The WireId {r.n_vars + 5} has not been defined yet."
+    bad_ci = (r.B[0], r.B[1], r.B[2].copy())
+    bad_ci[2][0] = len(r.coefs) + 1
+    with pytest.raises(z.ZkbError) as e:
+        load(B=bad_ci)
+    assert e.value.code == z.ZKB_E_ARG
+    bad_rp = (r.C[0].copy(), r.C[1], r.C[2])
+    bad_rp[0][10] = bad_rp[0][9] - 1 if bad_rp[0][9] > 0 else 10 ** 6
+    with pytest.raises(z.ZkbError) as e:
+        load(C=bad_rp)
+    assert e.value.code == z.ZKB_E_ARG
+    short = (r.C[0][:-1], r.C[1][:-1], r.C[2][:-1])                   # one row fewer than A and B
+    with pytest.raises(z.ZkbError) as e:
+        load(C=short)
+    assert e.value.code == z.ZKB_E_ARG
+    with pytest.raises(z.ZkbError) as e:
+        load(n_vars=0)
+    assert e.value.code == z.ZKB_E_ARG
+    b = z.GpuBackend(-1)
+    b.set_field(2)
+    with pytest.raises(z.ZkbError) as e:
+        b.r1cs_load(r.A, r.B, r.C, r.coef_table, r.n_vars)
+    assert e.value.code == z.ZKB_E_UNSUPPORTED
