@@ -35,8 +35,10 @@ def parse():
     ap.add_argument("--witnesses", type=int, default=4096)
     ap.add_argument("--inputs", type=int, default=1024)
     ap.add_argument("--field", default="bls381", choices=["bls381", "bn254", "goldilocks", "p124", "m31"])
-    ap.add_argument("--cpu-sample-log2-gates", type=int, default=22)
+    ap.add_argument("--cpu-sample-log2-gates", type=int, default=0,
+                    help="cap the CPU arms at the relation's first 2^k counted gates (0: the whole relation when the time budget allows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-value-check", action="store_true", help="skip the sampled wire-value comparison with the oracle")
     ap.add_argument("--verdicts-only", action="store_true",
                     help="do not keep the live wires readable: slot re-use + dead-store elimination (not the headline)")
     return ap.parse_args()
@@ -85,6 +87,18 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def load_circuits():
+    """the workload generator (numpy only), imported by path: the reference arm must not load libzkb.so"""
+    import importlib.util
+    if "zkb_circuits" in sys.modules:
+        return sys.modules["zkb_circuits"]
+    spec = importlib.util.spec_from_file_location("zkb_circuits", os.path.join(ROOT, "zkinterface-ir_b200", "circuits.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["zkb_circuits"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def host_threads():
     n = os.cpu_count() or 1
     try:
@@ -94,30 +108,27 @@ def host_threads():
     return max(1, min(n, 64))
 
 
-def cpu_reference_rate(circ_mod, flat, p, circuit, n_threads, log2_sample_gates, steps, warmup):
-    """Times the oracle (restatement of Evaluator<PlaintextBackend>) on a bounded sample:
-    the first 2^k counted gates of the SAME relation x n_threads witnesses, one witness per thread."""
+def counted_prefix(circ_mod, circuit, n_counted_gates):
+    """the first gates of the relation that hold `n_counted_gates` counted gates (Add / Mul / AssertZero)"""
     g = circuit.gates
+    if n_counted_gates >= circuit.n_gates:
+        return g, circuit.n_gates
     counted = np.isin(g["op"], [circ_mod.G_ADD, circ_mod.G_MUL, circ_mod.G_ASSERT_ZERO])
     cum = np.cumsum(counted)
-    want = min(1 << log2_sample_gates, int(cum[-1]))
-    cut = int(np.searchsorted(cum, want, side="left")) + 1
-    sub = g[:cut]
-    n_counted = int(cum[cut - 1])
-    w = circ_mod.make_witnesses(circuit, n_threads, seed=SEED + 99)
+    cut = int(np.searchsorted(cum, n_counted_gates, side="left")) + 1
+    return g[:cut], int(cum[cut - 1])
+
+
+def cpu_reference_run(circ_mod, flat, p, circuit, gates, n_counted, witnesses, n_threads):
+    """one pass of the oracle (restatement of Evaluator<PlaintextBackend>, oracle/plaintext_flat.c) over `gates` for
+    len(witnesses) witnesses on n_threads threads (the reference itself is single-threaded: one witness per thread is
+    the data-parallel CPU figure); returns (gate-evals/s, seconds, results)"""
     eb = circ_mod.elem_bytes(p)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        res = flat.eval_batch(sub, circuit.const_pool, p.to_bytes(eb, "little"), None, w, n_threads, n_threads=n_threads)
-        dt = time.perf_counter() - t0
-        assert (res["status"] == 0).all(), "oracle found an unsatisfied witness in the baseline sample"
-        if it >= warmup:
-            times.append(dt)
-    per_step = float(np.mean(times))
-    rate = n_counted * n_threads / per_step
-    sample = f"first {n_counted} counted gates of the 2^{int(np.log2(circuit.n_gates))}-gate relation x {n_threads} witnesses (1 per thread)"
-    return rate, per_step, sample
+    n = len(witnesses)
+    t0 = time.perf_counter()
+    res = flat.eval_batch(gates, circuit.const_pool, p.to_bytes(eb, "little"), None, witnesses, n, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return n_counted * n / dt, dt, res
 
 
 def workload_name(args):
@@ -144,33 +155,56 @@ def main():
     p = FIELD[args.field]
     n_gates = 1 << args.log2_gates
 
-    import __graft_entry__ as ge
-    import zkb_loader
     import importlib
-    if args.impl == "reference" or world == 1:
-        ge.build()
+    if args.impl != "reference":
+        import __graft_entry__ as ge
+        import zkb_loader
+        if world == 1:
+            ge.build()
 
     if args.impl == "reference":
         if rank != 0:
             return
-        zkb_loader.load()
-        circ_mod = importlib.import_module("zkir_b200.circuits")
+        # the reference's own CPU implementation of the path, timed on this box's host cores.  The Rust binary cannot
+        # be built in this image (no cargo / rustc, crates not vendored), so this is the C restatement that keeps the
+        # reference's structure (oracle/plaintext_flat.c).  libzkb.so is NOT loaded in this arm.
+        circ_mod = load_circuits()
         from oracle import flat
         flat.build()
         circuit = circ_mod.random_circuit(n_gates, args.inputs, p, SEED)
         nt = host_threads()
-        rate, per_step, sample = cpu_reference_rate(circ_mod, flat, p, circuit, nt, args.cpu_sample_log2_gates,
-                                                    args.steps, max(1, min(args.warmup, 1)))
+        # every step = the relation's first 2^k counted gates x one witness per host thread; k is the largest that keeps
+        # the whole (warmup + steps) run within ~3 minutes at ~2 M gates/s/thread (the full relation when it fits)
+        budget_s = 170.0 / max(1, args.steps + args.warmup)
+        k = args.log2_gates
+        while k > 16 and (1 << k) / 2.0e6 > budget_s:
+            k -= 1
+        if args.cpu_sample_log2_gates:
+            k = min(k, args.cpu_sample_log2_gates)
+        gates, n_counted = counted_prefix(circ_mod, circuit, 1 << k)
+        w = circ_mod.make_witnesses(circuit, nt, seed=SEED + 99)
+        times = []
+        for it in range(args.warmup + args.steps):
+            rate, dt, res = cpu_reference_run(circ_mod, flat, p, circuit, gates, n_counted, w, nt)
+            assert (res["status"] == 0).all(), "oracle found an unsatisfied witness in the baseline sample"
+            if it >= args.warmup:
+                times.append(dt)
+        per_step = float(np.mean(times))
+        rate = n_counted * nt / per_step
+        sample = (f"{'the whole relation' if n_counted == circuit.n_gates else 'first ' + str(n_counted) + ' counted gates of the relation'}"
+                  f" ({circuit.n_gates} gates) x {nt} witnesses, one per host thread, per step")
         line = {
             "impl": "reference", "metric": "field gates evaluated/sec", "value": rate, "unit": "gate-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field, Montgomery)",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (255-bit field)",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "gates": circuit.n_gates, "gate_histogram": circuit.hist,
-                       "witnesses": args.witnesses, "witness_inputs": args.inputs},
+                       "witnesses": args.witnesses, "witness_inputs": circuit.n_inputs},
             "cpu_baseline": {"value": rate, "unit": "gate-evals/s", "cores": nt, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "gate-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "CPU restatement of zki_sieve 3.0.0 Evaluator<PlaintextBackend> (oracle/plaintext_flat.c), not the Rust binary",
+            "note": "CPU restatement of zki_sieve 3.0.0 Evaluator<PlaintextBackend> (oracle/plaintext_flat.c: hash-map wire "
+                    "store, heap big integers, generic long division), not the Rust binary; the reference is single-threaded, "
+                    "this is one witness per host thread",
         }
         emit(line)
         return
@@ -209,7 +243,7 @@ def main():
     # 1 % of the witnesses are corrupted; their first failing assertion is known by construction
     rng = np.random.default_rng(SEED + 1)
     bad = rng.choice(total_w, size=max(1, total_w // 100), replace=False)
-    corrupt_global = {int(j): int(rng.integers(0, max(circuit.n_ties, 1))) for j in bad} if circuit.n_ties else {}
+    corrupt_global = {int(j): int(rng.integers(0, max(circuit.n_tracked, 1))) for j in bad} if circuit.n_tracked else {}
     corrupt_local = {j - lo: k for j, k in corrupt_global.items() if lo <= j < hi}
     w_np = circ_mod.make_witnesses(circuit, n_local, seed=SEED + 7 + rank, corrupt=corrupt_local)
     eb = circ_mod.elem_bytes(p)
@@ -318,13 +352,60 @@ def main():
         except Exception:
             pass
 
+    # ---- parity at the headline shape (every run): sampled wire values of three witnesses — the first, one across the
+    # first tile boundary, the last — against the oracle's evaluation of the whole relation; the oracle is the checker here
+    values_checked = 0
+    value_witnesses = []
+    if rank == 0 and not args.no_value_check and not args.verdicts_only:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import flat
+        tile_w = st["tile_witnesses"]
+        good = [j for j in range(n_local) if j not in corrupt_local]
+        picks = sorted({good[0], min((j for j in good if j >= tile_w), default=good[len(good) // 2]), good[-1]})
+        nw = circuit.n_wires
+        wires = np.unique(np.concatenate([np.linspace(0, nw - 1, 12000).astype(np.int64), np.arange(max(0, nw - 1000), nw),
+                                          np.arange(min(64, nw))]))
+        handles = [be.scope_lookup(int(i)) for i in wires]
+        mod_le = p.to_bytes(eb, "little")
+        with ThreadPoolExecutor(len(picks)) as ex:
+            dumps = list(ex.map(lambda j: flat.eval_dump(circuit.gates, circuit.const_pool, mod_le, None, w_np[j], nw, stride=eb), picks))
+        for j, (res, dump) in zip(picks, dumps):
+            assert int(res["status"]) == flat.EV_TRUE, f"oracle: witness {j} is not satisfying"
+            got = be.read_values(j, handles, eb)
+            want = [int.from_bytes(dump[i].tobytes(), "little") for i in wires]
+            bad_at = [int(wires[q]) for q in range(len(wires)) if got[q] != want[q]]
+            assert not bad_at, f"witness {lo + j}: {len(bad_at)} wire values differ from the oracle, first at wire {bad_at[0]}"
+            values_checked += len(wires)
+            value_witnesses.append(lo + j)
+        del dumps
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle over the WHOLE relation, 1 core (the reference is
+    # single-threaded) and one witness per host thread; its verdicts double as a check of ours for those witnesses
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import flat
         nt = host_threads()
-        rate, per_step, sample = cpu_reference_rate(circ_mod, flat, p, circuit, nt, args.cpu_sample_log2_gates, 1, 0)
-        cpu_baseline = {"value": rate, "unit": "gate-evals/s", "cores": nt, "kind": "port", "sample": sample,
-                        "seconds": per_step}
+        try:    # the restatement's hash-map wire store takes ~0.2 KB per live wire and thread
+            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+            nt = max(1, min(nt, int(avail * 0.6 / (circuit.n_wires * 200 + 1))))
+        except Exception:
+            pass
+        gates_cpu, n_counted = counted_prefix(circ_mod, circuit, 1 << args.cpu_sample_log2_gates if args.cpu_sample_log2_gates else circuit.n_gates)
+        whole = n_counted == circuit.n_gates
+        rate1, dt1, res1 = cpu_reference_run(circ_mod, flat, p, circuit, gates_cpu, n_counted, w_np[:1], 1)
+        rate, dt, res = cpu_reference_run(circ_mod, flat, p, circuit, gates_cpu, n_counted, w_np[:nt], nt)
+        if whole:
+            for j in range(min(nt, n_local)):
+                ok_ref = int(res[j]["status"]) == flat.EV_TRUE
+                assert ok_ref == (expected[j] < 0) and (ok_ref or int(res[j]["fail_assert_seq"]) == expected[j]), \
+                    f"witness {j}: the oracle's verdict differs from the device's"
+        what = "the whole relation" if whole else f"first {n_counted} counted gates of the relation"
+        cpu_baseline = {"value": rate, "unit": "gate-evals/s", "cores": nt, "kind": "port",
+                        "sample": f"{what} ({circuit.n_gates} gates) x {nt} witnesses, one per host thread, {dt:.1f} s",
+                        "seconds": dt, "one_core": {"value": rate1, "seconds": dt1, "sample": f"{what} x 1 witness, 1 thread"},
+                        "verdicts_checked_against_oracle": min(nt, n_local) if whole else 0,
+                        "what": "C restatement of zki_sieve 3.0.0 Evaluator<PlaintextBackend> (oracle/plaintext_flat.c), gate loop only "
+                                "(no .sieve parsing); the Rust binary cannot be built in this image"}
 
     if rank == 0:
         line = {
@@ -334,7 +415,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args),
                        "gates": circuit.n_gates, "gate_histogram": circuit.hist, "witnesses": total_w,
-                       "witness_inputs": args.inputs, "levels": st["n_levels"], "tile_witnesses": st["tile_witnesses"],
+                       "witness_inputs": circuit.n_inputs, "levels": st["n_levels"], "tile_witnesses": st["tile_witnesses"],
                        "tiles_per_rank": st["n_tiles"], "wire_store_gb": st["n_slots"] * eb * st["tile_witnesses"] / 1e9,
                        "l2": "working set (wire store) is >> L2, no flush needed", "parallelism": f"witness-shard x{world}",
                        "wires_kept_readable": "none (verdicts only)" if args.verdicts_only else "all live top-scope wires"},
@@ -346,7 +427,10 @@ def main():
             "clocks": sampler.summary(),
             "prep_s": {"generate_circuit": t_gen, "flatten_levelize_upload": t_prep},
             "wall_ms_per_step": wall_ms / args.steps,
-            "verdicts": {"true": int((ff >= (1 << 40)).sum()), "false": int((ff < (1 << 40)).sum())},
+            "verdicts": {"true": int((ff >= (1 << 40)).sum()), "false": int((ff < (1 << 40)).sum()),
+                         "checked": "all, against the generator's expectation (1 % corrupted, first failing assertion known)"},
+            "values_checked": values_checked,
+            "values_checked_witnesses": value_witnesses,
         }
         emit(line)
     be.close()

@@ -58,10 +58,11 @@ def c2(log2_gates, window):
     b.finalize(False)
     prep = time.perf_counter() - t0
     good = c.make_witnesses(circ, 1, seed=3)
-    bad = c.make_witnesses(circ, 1, seed=3, corrupt={0: 5})
+    k = next(k for k in range(circ.n_tracked) if circ.first_fail_of_input[k] >= 0)   # a tracked input some assertion sees
+    bad = c.make_witnesses(circ, 1, seed=3, corrupt={0: k})
     b.upload_inputs(None, bad, 1)
     vb = b.run()
-    assert int(vb[0]["first_fail_seq"]) == int(circ.tie_assert_seq[5])
+    assert int(vb[0]["first_fail_seq"]) == int(circ.first_fail_of_input[k])
     b.upload_inputs(None, good, 1)
     assert int(b.run()[0]["ok"]) == 1
     tot, lv = timed_runs(b.run, b.timing)

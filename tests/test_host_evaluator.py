@@ -194,7 +194,7 @@ def test_library_exports_every_declared_symbol():
 def test_levelizer_invariants():
     c = __import__("importlib").import_module("zkir_b200.circuits")
     z = zkb()
-    circ = c.random_circuit(20000, 100, c.GOLDILOCKS, seed=3, n_ties=10)
+    circ = c.random_circuit(20000, 100, c.GOLDILOCKS, seed=3, n_tracked=10)
     b = z.GpuBackend(-1)
     b.set_field(c.GOLDILOCKS)
     b.push_gates(circ.gates, circ.const_pool)

@@ -4,19 +4,25 @@ These are the INPUTS of the benchmark and of the parity tests — flat relations
 `zkb_gate` array form (the simple arms of the reference's `Gate`,
 rust/src/structs/gates.rs:18-45) plus witness vectors.  Nothing here evaluates a gate.
 
-random_circuit  "random Add/Mul/AssertZero circuit" (configs C2, C3):
-    wire 0            Constant(p-1)                                   (not a counted gate)
-    wires 1..n_in     Witness                                         (not counted)
-    then slots drawn 45 % Add, 45 % Mul, 10 % assertion, operands uniform over all earlier
-    wires (or over the last `window` wires).  An assertion slot is either
-      identity:  n = Mul(t, w0); s = Add(t, n); AssertZero(s)     -- (p-1)*t + t == 0 for any t:
-                 exercises modular mul/add, holds for every witness            (3 counted gates)
-      tie:       s = Add(x_2k, x_2k+1); AssertZero(s)             -- holds iff the witness was
-                 built with x_2k+1 = p - x_2k; corrupting x_2k+1 makes exactly this assertion
-                 (and possibly later ones) fail                                (2 counted gates)
-    so every witness vector is satisfiable WITHOUT evaluating the circuit, and a corrupted one
-    has a first failing assertion known by construction.  Counted gates (Add + Mul +
-    AssertZero) are exactly `n_gates`.
+random_circuit  "random Add/Mul/AssertZero circuit" (configs C2, C3), SURVEY.md section 8(d):
+    wires 0..n_in-1   Witness: x_0 .. x_{h-1}, then x'_0 .. x'_{h-1} with x'_i = p - x_i   (not counted gates)
+    then slots drawn 41 % Add, 41 % Mul, 18 % assertion; operands uniform over all earlier wires (or over the last
+    `window` of them).  Every wire w has a twin w' whose value is sign(w) * value(w), sign in {+1, -1}:
+      Add / Mul slot  g = op(a, b) and its twin g' = op(a', b')          (2 counted gates; Add needs sign(a) = sign(b),
+                      so b is snapped to the nearest earlier wire with a's sign; sign(Mul) = sign(a) * sign(b))
+      assertion slot  s = Add(t, t'); AssertZero(s) on an arbitrary earlier wire t with sign -1   (2 counted gates)
+    so an assertion holds iff the witness is consistent (x'_i = -x_i) AND every gate in the cones of t and t' was
+    computed correctly: a wrong value anywhere upstream makes t + t' non-zero.  This is section 8(d)'s
+    witness-dependent assertion `Witness(k) = p - v(t); s = Add(t, k); AssertZero(s)` with k computed inside the circuit
+    by the twin gates instead of being shipped as one extra witness value per assertion: at C3's size that would be
+    1.5 M x 32 B = 48 MB per witness, 196 GB for the batch of 4096 -- more than a B200's HBM, let alone beside the
+    wire store.  No operand is shared between gates by construction and there are no constants.  Gate histogram:
+    Add 50 %, Mul 41 %, AssertZero 9 % of `n_gates` (section 8(d)'s mix).
+    Corrupting the mirror x'_k of a tracked input (k < n_tracked <= 64) makes every assertion whose t depends on x_k or
+    x'_k fail (up to a 2^-250 coincidence): the first such assertion in program order is known from a taint pass
+    done while generating (`first_fail_of_input`), and the tests confirm it with the oracle.
+    Generated block-wise with numpy: the operands of a block come from earlier blocks only (blocks of 1/8 of the
+    wires that exist, at most 4096 slots), which is what lets the signs and taints be propagated vectorised.
 """
 from __future__ import annotations
 
@@ -44,112 +50,169 @@ class FlatCircuit:
     def __init__(self):
         self.p = 0
         self.gates = None          # GATE_DTYPE
-        self.const_pool = None     # uint8 [n_consts, stride]
-        self.n_inputs = 0          # Witness gates
+        self.const_pool = None     # uint8 [n_consts, stride] (empty: the circuit has no constants)
+        self.n_inputs = 0          # Witness gates: x_0 .. x_{h-1}, then their mirrors x'_i = -x_i
         self.n_gates = 0           # counted gates: Add + Mul + AssertZero
         self.n_wires = 0
-        self.n_ties = 0
-        self.tie_assert_seq = None  # assert seq of tie k
+        self.n_tracked = 0         # inputs 0 .. n_tracked-1 can be corrupted with a known first failing assertion
+        self.first_fail_of_input = None  # assert seq of the first assertion that sees tracked input k (-1: none)
         self.n_asserts = 0
         self.hist = {}
 
 
-def random_circuit(n_gates: int, n_inputs: int, p: int, seed: int, n_ties: int = 32, window: int = 0,
-                   assert_frac: float = 0.10) -> FlatCircuit:
+def _block_size(pool: int, window: int) -> int:
+    span = min(pool, window) if window else pool
+    return int(min(4096, max(4, span // 8)))
+
+
+def random_circuit(n_gates: int, n_inputs: int, p: int, seed: int, n_tracked: int = 32, window: int = 0,
+                   assert_frac: float = 0.18) -> FlatCircuit:
+    """See the module docstring.  n_gates must be even (every slot costs two counted gates)."""
+    if n_gates % 2 or n_gates < 2:
+        raise ValueError("n_gates must be even")
+    if n_inputs < 2:
+        raise ValueError("at least two inputs (one value and its mirror)")
     rng = np.random.default_rng(seed)
-    n_ties = min(n_ties, n_inputs // 2)
-    # --- draw slot kinds until the counted gates reach n_gates -----------------------------
-    est = int(n_gates / (1.0 + 2.0 * assert_frac)) + 16
-    kinds = rng.choice(3, size=est + 64, p=[(1 - assert_frac) / 2, (1 - assert_frac) / 2, assert_frac]).astype(np.int8)
-    # kinds: 0 add, 1 mul, 2 identity-assert ; a few assertion slots become ties (kind 3)
-    a_slots = np.flatnonzero(kinds == 2)
-    if len(a_slots) < n_ties:
-        n_ties = len(a_slots)
-    tie_slots = np.sort(rng.choice(a_slots, size=n_ties, replace=False)) if n_ties else np.zeros(0, np.int64)
-    kinds[tie_slots] = 3
-    cost = np.array([1, 1, 3, 2], dtype=np.int64)[kinds]
-    cum = np.cumsum(cost)
-    n_slots = int(np.searchsorted(cum, n_gates, side="right"))
-    kinds = kinds[:n_slots]
-    cost = cost[:n_slots]
-    missing = n_gates - (int(cum[n_slots - 1]) if n_slots else 0)
-    if missing:  # pad with Add slots to hit n_gates exactly
-        kinds = np.concatenate([kinds, np.zeros(missing, np.int8)])
-        cost = np.concatenate([cost, np.ones(missing, np.int64)])
-        n_slots += missing
-    tie_slots = tie_slots[tie_slots < n_slots]
-    n_ties = len(tie_slots)
-    # --- wire ids ------------------------------------------------------------------------------
-    wires_per = np.array([1, 1, 2, 1], dtype=np.int64)[kinds]
-    first_wire = 1 + n_inputs + np.concatenate([[0], np.cumsum(wires_per)[:-1]])
-    n_wires = int(1 + n_inputs + wires_per.sum())
+    h = n_inputs // 2
+    n_in = 2 * h
+    n_slots = n_gates // 2
+    n_tracked = min(n_tracked, h, 64)
+    kinds_all = rng.choice(3, size=n_slots, p=[(1 - assert_frac) / 2, (1 - assert_frac) / 2, assert_frac]).astype(np.int8)
+    n_emit = n_in + n_gates
+    g = np.zeros(n_emit, dtype=GATE_DTYPE)
+    g["op"][:n_in] = G_WITNESS
+    g["out"][:n_in] = np.arange(n_in, dtype=np.uint32)
+    # the pool: every wire an operand may be drawn from, with the wire that holds its negated-or-equal twin
+    cap = n_in + 2 * n_slots
+    pool_wire = np.empty(cap, dtype=np.int64)
+    pool_partner = np.empty(cap, dtype=np.int64)
+    pool_sign = np.empty(cap, dtype=np.int8)        # value(partner) = sign * value(wire)
+    pool_taint = np.zeros(cap, dtype=np.uint64)      # which tracked inputs (either twin) the wire depends on
+    last_minus = np.empty(cap, dtype=np.int64)       # largest pool index <= i with sign -1 / +1 (-1: none)
+    last_plus = np.empty(cap, dtype=np.int64)
+    pool_wire[:n_in] = np.arange(n_in)
+    pool_partner[:h] = np.arange(h, n_in)
+    pool_partner[h:n_in] = np.arange(h)
+    pool_sign[:n_in] = -1
+    bits = np.uint64(1) << np.arange(n_tracked, dtype=np.uint64)
+    pool_taint[:n_tracked] = bits
+    pool_taint[h:h + n_tracked] = bits
+    last_minus[:n_in] = np.arange(n_in)
+    last_plus[:n_in] = -1
+    P = n_in                 # pool size
+    n_wires = n_in
+    e = n_in                 # gates emitted
+    n_asserts = 0
+    first_fail = np.full(n_tracked, -1, dtype=np.int64)
+    missing = np.uint64((1 << n_tracked) - 1) if n_tracked else np.uint64(0)
+    s0 = 0
+    while s0 < n_slots:
+        B = min(_block_size(P, window), n_slots - s0)
+        k = kinds_all[s0:s0 + B].copy()
+        lo = max(0, P - window) if window else 0
+        ia = lo + (rng.random(B) * (P - lo)).astype(np.int64)
+        ib = lo + (rng.random(B) * (P - lo)).astype(np.int64)
+        sa = pool_sign[ia]
+        # Add needs operands of equal sign: snap b down to the nearest wire with a's sign (never a's own twin, whose
+        # sum with a would be the constant zero); where there is none the slot becomes a Mul
+        is_add = k == 0
+        snapped = np.where(sa < 0, last_minus[ib], last_plus[ib])
+        twin = is_add & (snapped == pool_partner[ia])
+        below = np.maximum(snapped - 1, 0)
+        snapped = np.where(twin, np.where(snapped > 0, np.where(sa < 0, last_minus[below], last_plus[below]), -1), snapped)
+        to_mul = is_add & ((snapped < 0) | (snapped == pool_partner[ia]))
+        k[to_mul] = 1
+        is_add = k == 0
+        ib = np.where(is_add, snapped, ib)
+        # assertion slots test a wire t whose twin holds -t
+        is_as = k == 2
+        it = last_minus[ia]
+        am = ~is_as
+        n_am = int(am.sum())
+        n_as = B - n_am
+        j = np.arange(B)
+        rank_am = np.cumsum(am) - 1
+        cost1 = np.where(is_as, 2, 1)
+        off1 = e + np.cumsum(cost1) - cost1
+        wire1 = n_wires + j
+        # ---- phase 1: the gates of the block in slot order
+        sel = np.flatnonzero(am)
+        gi = off1[sel]
+        a_idx, b_idx = ia[sel], ib[sel]
+        g["op"][gi] = np.where(k[sel] == 0, G_ADD, G_MUL)
+        g["out"][gi] = wire1[sel]
+        g["a"][gi] = pool_wire[a_idx]
+        g["b"][gi] = pool_wire[b_idx]
+        asel = np.flatnonzero(is_as)
+        if n_as:
+            gi = off1[asel]
+            t = it[asel]
+            g["op"][gi] = G_ADD
+            g["out"][gi] = wire1[asel]
+            g["a"][gi] = pool_wire[t]
+            g["b"][gi] = pool_wire[pool_partner[t]]
+            g["op"][gi + 1] = G_ASSERT_ZERO
+            g["a"][gi + 1] = wire1[asel]
+            if missing:
+                tm = pool_taint[t]
+                if np.bitwise_or.reduce(tm) & missing:
+                    for q in range(n_as):
+                        hit = tm[q] & missing
+                        if hit:
+                            for bit in range(n_tracked):
+                                if (int(hit) >> bit) & 1:
+                                    first_fail[bit] = n_asserts + q
+                            missing = missing & ~hit
+            n_asserts += n_as
+        # ---- phase 2: the twins of the block's Add / Mul gates, on the twins of their operands
+        e2 = e + int(cost1.sum())
+        gi = e2 + np.arange(n_am)
+        wire2 = n_wires + B + np.arange(n_am)
+        g["op"][gi] = g["op"][off1[sel]]
+        g["out"][gi] = wire2
+        g["a"][gi] = pool_wire[pool_partner[a_idx]]
+        g["b"][gi] = pool_wire[pool_partner[b_idx]]
+        # ---- the block's wires join the pool
+        sgn = np.where(k[sel] == 0, sa[sel], sa[sel] * pool_sign[b_idx]).astype(np.int8)
+        tnt = pool_taint[a_idx] | pool_taint[b_idx]
+        lo_p, mid_p, hi_p = P, P + n_am, P + 2 * n_am
+        pool_wire[lo_p:mid_p] = wire1[sel]
+        pool_wire[mid_p:hi_p] = wire2
+        pool_partner[lo_p:mid_p] = np.arange(mid_p, hi_p)
+        pool_partner[mid_p:hi_p] = np.arange(lo_p, mid_p)
+        pool_sign[lo_p:mid_p] = sgn
+        pool_sign[mid_p:hi_p] = sgn
+        pool_taint[lo_p:mid_p] = tnt
+        pool_taint[mid_p:hi_p] = tnt
+        idx = np.arange(lo_p, hi_p)
+        s2 = pool_sign[lo_p:hi_p]
+        last_minus[lo_p:hi_p] = np.maximum(np.maximum.accumulate(np.where(s2 < 0, idx, -1)), last_minus[lo_p - 1])
+        last_plus[lo_p:hi_p] = np.maximum(np.maximum.accumulate(np.where(s2 > 0, idx, -1)), last_plus[lo_p - 1])
+        P = hi_p
+        n_wires += B + n_am
+        e = e2 + n_am
+        s0 += B
+    assert e == n_emit, (e, n_emit)
     if n_wires >= (1 << 32) - 16:
         raise ValueError("circuit too large for 32-bit wire ids")
-    emit_per = np.array([1, 1, 3, 2], dtype=np.int64)[kinds]  # gates emitted (all counted)
-    first_gate = 1 + n_inputs + np.concatenate([[0], np.cumsum(emit_per)[:-1]])
-    n_emit = int(1 + n_inputs + emit_per.sum())
-
-    def pick(limit):  # operand uniform over wires [lo, limit)
-        u = rng.random(len(limit))
-        if window:
-            lo = np.maximum(limit - window, 0)
-            return (lo + (u * (limit - lo)).astype(np.int64)).astype(np.uint32)
-        return (u * limit).astype(np.int64).astype(np.uint32)
-
-    opa = pick(first_wire)
-    opb = pick(first_wire)
-    g = np.zeros(n_emit, dtype=GATE_DTYPE)
-    g["op"][0] = G_CONSTANT
-    g["out"][0] = 0
-    g["b"][0] = 0
-    g["op"][1:1 + n_inputs] = G_WITNESS
-    g["out"][1:1 + n_inputs] = np.arange(1, 1 + n_inputs, dtype=np.uint32)
-    for k, opc in ((0, G_ADD), (1, G_MUL)):
-        s = np.flatnonzero(kinds == k)
-        gi = first_gate[s]
-        g["op"][gi] = opc
-        g["out"][gi] = first_wire[s]
-        g["a"][gi] = opa[s]
-        g["b"][gi] = opb[s]
-    s = np.flatnonzero(kinds == 2)  # identity: n = Mul(t, w0); s = Add(t, n); AssertZero(s)
-    gi = first_gate[s]
-    g["op"][gi] = G_MUL
-    g["out"][gi] = first_wire[s]
-    g["a"][gi] = opa[s]
-    g["b"][gi] = 0
-    g["op"][gi + 1] = G_ADD
-    g["out"][gi + 1] = first_wire[s] + 1
-    g["a"][gi + 1] = opa[s]
-    g["b"][gi + 1] = first_wire[s]
-    g["op"][gi + 2] = G_ASSERT_ZERO
-    g["a"][gi + 2] = first_wire[s] + 1
-    s = tie_slots  # tie k: s = Add(x_2k, x_2k+1); AssertZero(s)   (inputs are wires 1..n_in)
-    gi = first_gate[s]
-    kk = np.arange(n_ties, dtype=np.uint32)
-    g["op"][gi] = G_ADD
-    g["out"][gi] = first_wire[s]
-    g["a"][gi] = 1 + 2 * kk
-    g["b"][gi] = 2 + 2 * kk
-    g["op"][gi + 1] = G_ASSERT_ZERO
-    g["a"][gi + 1] = first_wire[s]
 
     c = FlatCircuit()
     c.p = p
     c.gates = g
-    eb = elem_bytes(p)
-    c.const_pool = le_bytes(p - 1, eb).reshape(1, eb).copy()
-    c.n_inputs = n_inputs
-    c.n_gates = int(emit_per.sum())
-    assert c.n_gates == n_gates, (c.n_gates, n_gates)
+    c.const_pool = np.zeros((0, elem_bytes(p)), dtype=np.uint8)
+    c.n_inputs = n_in
+    c.n_gates = n_gates
     c.n_wires = n_wires
-    c.n_ties = n_ties
-    # assert sequence numbers (program order)
-    is_assert = g["op"] == G_ASSERT_ZERO
-    seq_of_gate = np.cumsum(is_assert) - 1
-    c.tie_assert_seq = seq_of_gate[first_gate[tie_slots] + 1].astype(np.int64) if n_ties else np.zeros(0, np.int64)
-    c.n_asserts = int(is_assert.sum())
-    c.hist = {"add": int((g["op"] == G_ADD).sum()), "mul": int((g["op"] == G_MUL).sum()), "assert_zero": c.n_asserts}
+    c.n_tracked = n_tracked
+    c.first_fail_of_input = first_fail
+    c.n_asserts = n_asserts
+    c.hist = {"add": int((g["op"] == G_ADD).sum()), "mul": int((g["op"] == G_MUL).sum()), "assert_zero": n_asserts}
+    assert c.hist["add"] + c.hist["mul"] + n_asserts == n_gates
     return c
+
+
+def _limbs_of(p: int, nl: int) -> np.ndarray:
+    return np.array([(p >> (32 * i)) & 0xFFFFFFFF for i in range(nl)], dtype=np.uint64)
 
 
 def random_field_elements(rng, shape, p: int) -> np.ndarray:
@@ -158,7 +221,7 @@ def random_field_elements(rng, shape, p: int) -> np.ndarray:
     n = int(np.prod(shape))
     bits = p.bit_length()
     nl = eb // 4
-    plimbs = np.array([(p >> (32 * i)) & 0xFFFFFFFF for i in range(nl)], dtype=np.uint32)
+    plimbs = _limbs_of(p, nl).astype(np.uint32)
     out = np.zeros((n, nl), dtype=np.uint32)
     todo = np.arange(n)
     top_bits = bits - 32 * (nl - 1)
@@ -177,28 +240,45 @@ def random_field_elements(rng, shape, p: int) -> np.ndarray:
     return out.view(np.uint8).reshape(*shape, eb)
 
 
+def negate_mod(x: np.ndarray, p: int) -> np.ndarray:
+    """(p - x) mod p limb-wise for uint8 [..., elem_bytes(p)] little-endian values below p"""
+    eb = x.shape[-1]
+    nl = eb // 4
+    xl = np.ascontiguousarray(x).view(np.uint32).reshape(-1, nl).astype(np.uint64)
+    pl = _limbs_of(p, nl)
+    out = np.zeros_like(xl)
+    borrow = np.zeros(len(xl), dtype=np.uint64)
+    for i in range(nl):
+        d = pl[i] + (np.uint64(1) << np.uint64(32)) - xl[:, i] - borrow
+        out[:, i] = d & np.uint64(0xFFFFFFFF)
+        borrow = np.uint64(1) - (d >> np.uint64(32))
+    out[(xl == 0).all(axis=1)] = 0
+    return out.astype(np.uint32).view(np.uint8).reshape(x.shape)
+
+
 def make_witnesses(c: FlatCircuit, n_batch: int, seed: int, corrupt=None) -> np.ndarray:
-    """uint8 [n_batch, n_inputs, elem_bytes]; tie inputs satisfy x_2k+1 = p - x_2k.
-    corrupt: {witness index: tie index} -> that tie is broken (x_2k+1 += 1 mod p)."""
+    """uint8 [n_batch, n_inputs, elem_bytes]: x_0 .. x_{h-1} uniform, then the mirrors x'_i = p - x_i.
+    corrupt: {witness index: tracked input k} -> x'_k is off by one for that witness."""
     rng = np.random.default_rng(seed ^ 0x5EED)
     eb = elem_bytes(c.p)
-    w = random_field_elements(rng, (n_batch, c.n_inputs), c.p)
-    for k in range(c.n_ties):
-        xs = w[:, 2 * k, :]
-        for j in range(n_batch):
-            x = int.from_bytes(xs[j].tobytes(), "little")
-            y = (c.p - x) % c.p
-            if corrupt and corrupt.get(j) == k:
-                y = (y + 1) % c.p
-            w[j, 2 * k + 1, :] = le_bytes(y, eb)
+    h = c.n_inputs // 2
+    w = np.empty((n_batch, c.n_inputs, eb), dtype=np.uint8)
+    w[:, :h, :] = random_field_elements(rng, (n_batch, h), c.p)
+    w[:, h:, :] = negate_mod(w[:, :h, :], c.p)
+    for j, k in (corrupt or {}).items():
+        if k >= c.n_tracked:
+            raise ValueError("only the tracked inputs can be corrupted")
+        y = (int.from_bytes(w[j, h + k].tobytes(), "little") + 1) % c.p
+        w[j, h + k, :] = le_bytes(y, eb)
     return w
 
 
 def expected_first_fail(c: FlatCircuit, n_batch: int, corrupt=None) -> np.ndarray:
-    """first failing assert seq per witness (-1: TRUE), by construction"""
+    """first failing assert seq per witness (-1: TRUE): the first assertion, in program order, on a wire that
+    depends on the corrupted input or on its twin"""
     out = np.full(n_batch, -1, dtype=np.int64)
     for j, k in (corrupt or {}).items():
-        out[j] = int(c.tie_assert_seq[k])
+        out[j] = int(c.first_fail_of_input[k])
     return out
 
 
