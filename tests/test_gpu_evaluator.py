@@ -160,3 +160,26 @@ def test_batch_through_evaluator_program():
     v = b.evaluate(inst, wit, 6)
     assert [int(x) for x in v["ok"]] == [1, 0, 1, 1, 0, 1]
     assert b.assert_wire(int(v[1]["first_fail_seq"])) == 9
+
+
+def test_failing_assertion_before_a_missing_witness_value_is_the_violation():
+    """The reference evaluates as it goes: an assertion that fails before the Witness gate that finds its queue empty
+    latches its error (evaluator.rs:213-221, 357-362) and the panic of PlaintextBackend::witness(None) (:944-946) is never
+    reached.  The deferred backend records first, so it resolves the recorded prefix when the panic condition is met."""
+    z = zkb()
+    h = fx.example_header()
+    rel = ir.Relation(h, ir.ARITH, ir.SIMPLE, [], [
+        ("Witness", 0), ("Instance", 1), ("Add", 2, 0, 1), ("AssertZero", 2),       # 3 + 25 != 0 (mod 101)
+        ("Witness", 3), ("Witness", 4), ("Mul", 5, 3, 4), ("AssertZero", 5)])
+    wit_short = ir.Witness(h, [ir.literal32(3)])
+    msgs = [fx.example_instance(), wit_short, rel]
+    assert ev.evaluate(msgs) == ["Wire_2 (may be weighted) should be 0, while it is not"]
+    e = z.Evaluator(z.GpuBackend(0))
+    e.ingest_source(z.Source.from_buffers([F.write_messages(msgs)]))
+    assert e.get_violations() == ["Wire_2 (may be weighted) should be 0, while it is not"]
+    # with a witness that satisfies the first assertion the missing value is reached: the reference panics
+    wit_ok = ir.Witness(h, [ir.literal32(101 - 25)])
+    e = z.Evaluator(z.GpuBackend(0))
+    with pytest.raises(z.ZkbError) as err:
+        e.ingest_source(z.Source.from_buffers([F.write_messages([fx.example_instance(), wit_ok, rel])]))
+    assert err.value.code == z.ZKB_E_FATAL and "Missing witness value" in str(err.value)

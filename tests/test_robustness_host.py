@@ -121,3 +121,114 @@ def test_deep_nesting_is_a_format_error_not_a_stack_overflow():
     with pytest.raises(z.ZkbError) as err:
         z.Validator(True).ingest_message(buf)
     assert err.value.code == z.ZKB_E_FORMAT
+
+
+def test_recursive_functions_end_in_an_error_not_a_stack_overflow():
+    """Functions are registered before the relation's gates run, so a body may call itself or a sibling; the reference
+    recurses until its stack overflows, here the nesting bound of the reader (512) also bounds dynamic nesting."""
+    from oracle import ir
+    z = zkb()
+    h = fx.example_header()
+    inst, wit = F.write_message(fx.example_instance()), F.write_message(fx.example_witness())
+    selfrec = ir.Function("f", 0, 0, 0, 0, [("Call", "f", [], [])])
+    ping = ir.Function("ping", 0, 0, 0, 0, [("Call", "pong", [], [])])
+    pong = ir.Function("pong", 0, 0, 0, 0, [("AnonCall", [], [], 0, 0, [("Call", "ping", [], [])])])
+    for fns, entry in (([selfrec], "f"), ([ping, pong], "ping")):
+        rel = F.write_message(ir.Relation(h, ir.ARITH, ir.FOR_FUNCTION_SWITCH, fns, [("Call", entry, [], [])]))
+        ev = z.Evaluator(z.GpuBackend(-1), flatten=True)
+        ev.ingest_message(inst)
+        ev.ingest_message(wit)
+        ev.ingest_message(rel)            # the error latches like any evaluation error (evaluator.rs:213-221)
+        assert "nested too deep" in (ev.backend.pending_error() or "")
+
+
+def test_huge_wire_ids_cost_memory_proportional_to_the_work_not_to_the_id():
+    """a 1 KB relation naming wire 2^28-1 inside four nested AnonCalls took 4 GiB when scopes were dense tables"""
+    import resource
+    from oracle import ir
+    z = zkb()
+    h = fx.example_header()
+    big = (1 << 28) - 1
+    g = ("Constant", big, b"\x01")
+    body = [g, ("Free", big, None)]
+    for _ in range(4):
+        body = [("Constant", big, b"\x02"), ("AnonCall", [], [], 0, 0, body), ("Free", big, None)]
+    far = [("Constant", (1 << 40) + 5, b"\x03"), ("Copy", 1 << 33, (1 << 40) + 5), ("Free", 1 << 33, None)]
+    rel = F.write_message(ir.Relation(h, ir.ARITH, ir.FOR_FUNCTION_SWITCH, [], body + far))
+    before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    for mk in (lambda: z.Evaluator(z.GpuBackend(-1), flatten=True), lambda: z.Validator(True)):
+        c = mk()
+        c.ingest_message(rel)
+        if isinstance(c, z.Validator):
+            assert c.get_violations() == ["The variable 1099511627781 is still live"] or len(c.get_violations()) <= 2
+    after = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+    assert after - before < 200 * 1024, (before, after)      # KiB
+
+
+def test_shared_subtables_cannot_expand_a_small_message_into_millions_of_gates():
+    """FlatBuffers offsets may point every entry of a vector at one shared table: 8 entries per level, 9 levels deep is
+    2^27 AnonCall gates out of ~2 KB; the reader charges every table view against the message length"""
+    import struct
+    from oracle import ir
+    z = zkb()
+
+    def shared_vec(k, child):
+        def th(w):
+            w.align(4)
+            pos = len(w.b)
+            w.b += struct.pack("<I", k) + bytes(4 * k)
+            c = child(w)
+            for i in range(k):
+                struct.pack_into("<I", w.b, pos + 4 + 4 * i, c - (pos + 4 + 4 * i))
+            return pos
+        return th
+
+    def anon(depth):
+        body = shared_vec(8, anon(depth - 1)) if depth else F._w_gates([])
+        sub = lambda w: w.table([(4, "ref", F._w_wirelist([])), (10, "ref", body)])
+        return lambda w: w.table([(4, "u8", F.DS_ID["AnonCall"]),
+                                  (6, "ref", lambda w2: w2.table([(4, "ref", F._w_wirelist([])), (6, "ref", sub)]))])
+
+    h = fx.example_header()
+    w = F._W()
+    w.b += bytes(12)
+    w.b[8:12] = b"siev"
+    body = lambda w2: w2.table([(4, "ref", F._w_header(h)), (6, "ref", F._w_str("arithmetic")),
+                                (8, "ref", F._w_str("@for,@function,@switch")),
+                                (10, "ref", lambda w3: w3.table_vec([])), (12, "ref", shared_vec(8, anon(8)))])
+    root = w.table([(4, "u8", F.MSG_RELATION), (6, "ref", body)])
+    w.align(4)
+    struct.pack_into("<I", w.b, 4, root - 4)
+    struct.pack_into("<I", w.b, 0, len(w.b) - 4)
+    buf = bytes(w.b)
+    assert len(buf) < 4096
+    for consume in (lambda: z.Validator(True).ingest_message(buf), lambda: z.Stats().ingest_message(buf),
+                    lambda: z.Evaluator(z.GpuBackend(-1)).ingest_message(buf), lambda: z.GpuBackend(-1).rewrite_message(buf)):
+        with pytest.raises(z.ZkbError) as e:
+            consume()
+        assert e.value.code == z.ZKB_E_FORMAT and "more tables" in str(e.value)
+
+
+def test_input_arrays_smaller_than_the_batch_are_refused_before_the_c_side_reads_them():
+    z = zkb()
+    b = z.GpuBackend(-1)
+    b.set_field(101)
+    g = np.zeros(3, dtype=z.GATE_DTYPE)
+    g["op"] = [z.G_INSTANCE, z.G_WITNESS, z.G_WITNESS]
+    g["out"] = [0, 1, 2]
+    b.push_gates(g)
+    b.finalize()
+    one = np.zeros((1, 4), np.uint8)
+    two = np.zeros((2, 4), np.uint8)
+    with pytest.raises(z.ZkbError) as e:
+        b.evaluate(one, one, 1)                    # one witness value, the program consumes two: the reference panics
+    assert e.value.code == z.ZKB_E_FATAL and "Missing witness value" in str(e.value)
+    with pytest.raises(z.ZkbError) as e:
+        b.evaluate(np.zeros((0, 4), np.uint8), two, 1)
+    assert e.value.code == z.ZKB_E_SEMANTIC and str(e.value) == "Not enough instance to consume"
+    with pytest.raises(z.ZkbError) as e:
+        b.evaluate(one, np.zeros((3, 2, 4), np.uint8), 5)   # three value sets for a batch of five
+    assert e.value.code == z.ZKB_E_ARG
+    with pytest.raises(z.ZkbError) as e:
+        b.evaluate(one, two, 1)                    # well-formed: only the missing device is left to complain about
+    assert e.value.code == z.ZKB_E_CUDA

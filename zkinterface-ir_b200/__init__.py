@@ -324,24 +324,36 @@ class GpuBackend:
             return x, 0, x.shape[1]
         return x, x.shape[1] * x.shape[2], x.shape[2]
 
-    def _strides(self, instances, witnesses):
+    def _strides(self, instances, witnesses, n_batch):
         inst, iss, istr = self._pack_inputs(instances)
         wit, wss, wstr = self._pack_inputs(witnesses)
         stride = wstr or istr or 1
         if istr and wstr and istr != wstr:
             raise ValueError("instance and witness value strides differ")
+        # the C side reads n_batch sets of n_instance / n_witness values through these pointers: the arrays must hold them
+        st = self.stats()
+        for x, need, short in ((inst, st["n_instance"], (ZKB_E_SEMANTIC, "Not enough instance to consume")),          # evaluator.rs:420-427
+                               (wit, st["n_witness"], (ZKB_E_FATAL, "Missing witness value for PlaintextBackend"))):  # :944-946
+            if x is None:
+                continue
+            if x.ndim == 3 and x.shape[0] < n_batch:
+                raise ZkbError(ZKB_E_ARG, f"input array holds {x.shape[0]} value sets, n_batch is {n_batch}")
+            if x.ndim not in (2, 3):
+                raise ZkbError(ZKB_E_ARG, "inputs must be [n_values, stride] or [n_batch, n_values, stride] uint8 arrays")
+            if x.shape[-2] < need:
+                raise ZkbError(*short)
         return inst, iss, wit, wss, stride
 
     def evaluate(self, instances, witnesses, n_batch: int) -> np.ndarray:
         """End-to-end: host buffers in, verdicts out (VERDICT_DTYPE array)."""
-        inst, iss, wit, wss, stride = self._strides(instances, witnesses)
+        inst, iss, wit, wss, stride = self._strides(instances, witnesses, n_batch)
         out = np.zeros(n_batch, dtype=VERDICT_DTYPE)
         self._chk(_lib.zkb_evaluate(self._c, _buf(inst), iss, _buf(wit), wss, stride, n_batch, _buf(out)))
         self._n_batch = n_batch          # the inputs stay resident: run() re-evaluates them
         return out
 
     def upload_inputs(self, instances, witnesses, n_batch: int):
-        inst, iss, wit, wss, stride = self._strides(instances, witnesses)
+        inst, iss, wit, wss, stride = self._strides(instances, witnesses, n_batch)
         self._chk(_lib.zkb_upload_inputs(self._c, _buf(inst), iss, _buf(wit), wss, stride, n_batch))
         self._n_batch = n_batch
 

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/zkb.h"
@@ -12,60 +13,83 @@
 
 namespace zkb {
 
-// wire id -> SSA value map of one scope: dense vector for small ids, hash map beyond
+// wire id -> SSA value map of one scope (HashMap<WireId, B::Wire>, evaluator.rs:158-160).  Ids that stay within a small
+// multiple of the number of insertions made so far (sequentially numbered wires: every builder-produced relation) live in
+// a dense vector; anything else goes to a hash map, so memory is proportional to the work done in the scope, never to the
+// largest wire id a (possibly hostile) gate names.
 class Scope {
 public:
     static constexpr uint32_t kNone = 0xFFFFFFFFu;
-    static constexpr uint64_t kDenseLimit = 1ull << 28;
+    static constexpr uint64_t kDenseLimit = 1ull << 32;
     std::vector<uint32_t> dense;
     std::unordered_map<uint64_t, uint32_t> sparse;
     uint64_t live = 0;
+    uint64_t n_sets = 0;              // insertions since the last clear(): bounds the dense part
+    bool track = false;               // pooled scopes remember the dense ids they touched, so clear() is O(touched)
+    std::vector<uint32_t> touched;
 
     // operand ids of a gate a few iterations ahead: random circuits read the map all over, so the loads are started early
     void prefetch(uint64_t id) const {
         if (id < dense.size()) __builtin_prefetch(&dense[id]);
     }
     uint32_t get(uint64_t id) const {
-        if (id < dense.size()) return dense[id];
-        if (id < kDenseLimit) return kNone;
+        if (id < dense.size() && dense[id] != kNone) return dense[id];
+        if (sparse.empty()) return kNone;
         auto it = sparse.find(id);
         return it == sparse.end() ? kNone : it->second;
     }
     // returns false if the id already had a value (the new value is stored anyway, like HashMap::insert)
     bool set(uint64_t id, uint32_t v) {
-        if (id < kDenseLimit) {
-            if (id >= dense.size()) {
-                size_t n = dense.size() ? dense.size() : 16;
-                while (n <= id) n *= 2;
-                dense.resize(n, kNone);
-            }
-            bool fresh = dense[id] == kNone;
+        if (id < dense.size() && dense[id] != kNone) {
             dense[id] = v;
-            if (fresh) live++;
-            return fresh;
+            return false;
         }
-        auto r = sparse.insert({id, v});
-        if (!r.second) r.first->second = v;
-        else live++;
-        return r.second;
+        if (!sparse.empty()) {
+            auto it = sparse.find(id);
+            if (it != sparse.end()) {
+                it->second = v;
+                return false;
+            }
+        }
+        n_sets++;
+        live++;
+        if (id >= dense.size() && id < kDenseLimit && id <= 4 * (n_sets + 1024)) {
+            size_t n = dense.size() ? dense.size() : 16;
+            while (n <= id) n *= 2;
+            dense.resize(n, kNone);
+        }
+        if (id < dense.size()) {
+            dense[id] = v;
+            if (track) touched.push_back((uint32_t)id);
+        } else {
+            sparse.emplace(id, v);
+        }
+        return true;
     }
     bool remove(uint64_t id) {
-        if (id < kDenseLimit) {
-            if (id >= dense.size() || dense[id] == kNone) return false;
+        if (id < dense.size() && dense[id] != kNone) {
             dense[id] = kNone;
             live--;
             return true;
         }
-        if (sparse.erase(id)) {
+        if (!sparse.empty() && sparse.erase(id)) {
             live--;
             return true;
         }
         return false;
     }
     void clear() {
-        std::fill(dense.begin(), dense.end(), kNone);
+        if (dense.size() > (1u << 20)) {  // a pooled scope does not keep a large table alive
+            std::vector<uint32_t>().swap(dense);
+        } else if (track && touched.size() < dense.size() / 8) {
+            for (uint32_t id : touched) dense[id] = kNone;
+        } else {
+            std::fill(dense.begin(), dense.end(), kNone);
+        }
+        touched.clear();
         sparse.clear();
         live = 0;
+        n_sets = 0;
     }
     template <class F>
     void for_each(F f) const {

@@ -110,6 +110,9 @@ struct zkb_evaluator {
 
     Program& prog() { return c->prog; }
 
+    static constexpr uint64_t kMaxDepth = 512;  // nested ingest_subcircuit calls (Call / AnonCall / For / Switch bodies)
+    uint64_t depth = 0;
+
     // work accounting against zkb_set_limits (not in the reference, which would run until memory is exhausted)
     uint64_t steps = 0;
     void step(uint64_t n = 1) {
@@ -118,7 +121,11 @@ struct zkb_evaluator {
     }
 
     Scope* new_scope() {
-        if (scope_pool.empty()) return new Scope();
+        if (scope_pool.empty()) {
+            Scope* s = new Scope();
+            s->track = true;
+            return s;
+        }
         Scope* s = scope_pool.back();
         scope_pool.pop_back();
         return s;
@@ -355,15 +362,22 @@ struct zkb_evaluator {
     void ingest_subcircuit(const std::vector<ir::Gate>& sub, const std::vector<std::vector<uint8_t>>& consts,
                            const std::vector<uint64_t>& outs, const std::vector<uint64_t>& ins, Scope& scope, Iters& iters,
                            Queue& instances, Queue& witnesses, const uint32_t* weight) {
+        // Function bodies may call themselves (directly or through each other): the reference recurses until its stack
+        // overflows.  The reader caps syntactic nesting at 512; the same bound on dynamic nesting turns that abort into
+        // a latched evaluation error.
+        if (depth >= kMaxDepth) throw EvalErr{"zkb: calls nested too deep (limit " + u64s(kMaxDepth) + ")"};
         Scope* ns = new_scope();
+        depth++;
         try {
             for (size_t idx = 0; idx < ins.size(); idx++) set(*ns, idx + outs.size(), prog().copy(get(scope, ins[idx])));
             for (const auto& g : sub) ingest_gate(g, consts, *ns, iters, instances, witnesses, weight);
             for (size_t idx = 0; idx < outs.size(); idx++) set(scope, outs[idx], prog().copy(get(*ns, idx)));
         } catch (...) {
+            depth--;
             release_scope(ns);
             throw;
         }
+        depth--;
         release_scope(ns);
     }
 
@@ -623,6 +637,7 @@ struct zkb_evaluator {
             found_error = e.msg;
             ctx_latch(c, e.msg);
         } catch (const Fatal& f) {
+            if (assertion_fails_before(f)) return ZKB_OK;
             fatal = true;
             return fail(ZKB_E_FATAL, f.msg);
         } catch (const Program::ProgramPanic& f) {  // ExpandDefinable's panics (exp_definable.rs:62-64, ...)
@@ -648,6 +663,71 @@ struct zkb_evaluator {
         return code;
     }
 
+    // The deferred evaluation: levelize + upload the recorded program (once), run it for the queued instance / witness
+    // values (a batch of one), and rebuild the reference's text for the first failing assertion (:357-362).
+    int evaluate_recorded(bool& have_error, std::string& first_error) {
+        have_error = false;
+        Program& p = prog();
+        const bool timing = getenv("ZKB_TIMING") != nullptr;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_begin = now();
+        if (!p.field_set || p.n_values() == 0) return ZKB_OK;
+        if (!c->finalized) {
+            c->live_values.clear();
+            values.for_each([&](uint64_t, uint32_t v) { c->live_values.push_back(v); });
+            int rc = ctx_finalize(c, 0);
+            if (rc != ZKB_OK) return fail(rc, c->err);
+        }
+        if (timing) fprintf(stderr, "finish: live wires + levelize + program upload %.3f s\n", now() - t_begin);
+        // pack the queued streams: one statement = batch of 1
+        size_t stride = (size_t)p.nlimb * 4;
+        auto widen = [&](const std::vector<std::vector<uint8_t>>& vals) {
+            for (const auto& v : vals) {
+                size_t n = v.size();
+                while (n > 0 && v[n - 1] == 0) n--;
+                stride = std::max(stride, (n + 3) / 4 * 4);
+            }
+        };
+        widen(instance_values);
+        widen(witness_values);
+        auto pack = [&](const std::vector<std::vector<uint8_t>>& vals, uint32_t need) {
+            std::vector<uint8_t> out((size_t)std::max<uint32_t>(need, 1) * stride, 0);
+            for (uint32_t i = 0; i < need && i < vals.size(); i++) {
+                size_t n = vals[i].size();
+                while (n > 0 && vals[i][n - 1] == 0) n--;
+                memcpy(out.data() + (size_t)i * stride, vals[i].data(), n);
+            }
+            return out;
+        };
+        std::vector<uint8_t> ib = pack(instance_values, p.n_instance), wb = pack(witness_values, p.n_witness);
+        zkb_verdict v;
+        const double t_eval = now();
+        int rc = zkb_evaluate(c, ib.data(), 0, wb.data(), 0, (uint32_t)stride, 1, &v);
+        if (rc != ZKB_OK) return fail(rc, c->err);
+        if (timing) fprintf(stderr, "finish: zkb_evaluate (allocations, input upload, kernels, verdict) %.3f s\n", now() - t_eval);
+        if (v.first_fail_seq != UINT64_MAX) {
+            uint64_t w = p.asserts[v.first_fail_seq].src_wire;
+            first_error = "Wire_" + u64s(w) + " (may be weighted) should be 0, while it is not";  // :357-362
+            have_error = true;
+        }
+        return ZKB_OK;
+    }
+
+    // A condition on which the reference panics was met while recording.  The reference evaluates as it goes: had an
+    // assertion recorded BEFORE this point failed, its error would have latched (:213-221) and the panic would never have
+    // been reached.  So the recorded prefix is evaluated now; true = an assertion fails, the statement is decided.
+    bool assertion_fails_before(const Fatal&) {
+        Program& p = prog();
+        if (!c->has_gpu || p.keep_copies || !p.field_set || p.asserts.empty() || c->finalized) return false;
+        bool have = false;
+        std::string msg;
+        if (evaluate_recorded(have, msg) != ZKB_OK || !have) return false;
+        has_error = true;
+        found_error = msg;
+        ctx_latch(c, msg);
+        return true;
+    }
+
     // ---- get_violations, :199-208, with the deferred evaluation in the middle -------------------------
     int finish() {
         if (evaluated) return ZKB_OK;
@@ -656,50 +736,8 @@ struct zkb_evaluator {
         if (!verified_at_least_one_gate) violations.push_back("Did not receive any gate to verify.");
         std::string first_error;
         bool have_error = false;
-        Program& p = prog();
-        const bool timing = getenv("ZKB_TIMING") != nullptr;
-        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        const double t_begin = now();
-        if (p.field_set && p.n_values() > 0) {
-            if (!c->finalized) {
-                c->live_values.clear();
-                values.for_each([&](uint64_t, uint32_t v) { c->live_values.push_back(v); });
-                int rc = ctx_finalize(c, 0);
-                if (rc != ZKB_OK) return fail(rc, c->err);
-            }
-            if (timing) fprintf(stderr, "finish: live wires + levelize + program upload %.3f s\n", now() - t_begin);
-            // pack the queued streams: one statement = batch of 1
-            size_t stride = (size_t)p.nlimb * 4;
-            auto widen = [&](const std::vector<std::vector<uint8_t>>& vals) {
-                for (const auto& v : vals) {
-                    size_t n = v.size();
-                    while (n > 0 && v[n - 1] == 0) n--;
-                    stride = std::max(stride, (n + 3) / 4 * 4);
-                }
-            };
-            widen(instance_values);
-            widen(witness_values);
-            auto pack = [&](const std::vector<std::vector<uint8_t>>& vals, uint32_t need) {
-                std::vector<uint8_t> out((size_t)std::max<uint32_t>(need, 1) * stride, 0);
-                for (uint32_t i = 0; i < need && i < vals.size(); i++) {
-                    size_t n = vals[i].size();
-                    while (n > 0 && vals[i][n - 1] == 0) n--;
-                    memcpy(out.data() + (size_t)i * stride, vals[i].data(), n);
-                }
-                return out;
-            };
-            std::vector<uint8_t> ib = pack(instance_values, p.n_instance), wb = pack(witness_values, p.n_witness);
-            zkb_verdict v;
-            const double t_eval = now();
-            int rc = zkb_evaluate(c, ib.data(), 0, wb.data(), 0, (uint32_t)stride, 1, &v);
-            if (rc != ZKB_OK) return fail(rc, c->err);
-            if (timing) fprintf(stderr, "finish: zkb_evaluate (allocations, input upload, kernels, verdict) %.3f s\n", now() - t_eval);
-            if (v.first_fail_seq != UINT64_MAX) {
-                uint64_t w = p.asserts[v.first_fail_seq].src_wire;
-                first_error = "Wire_" + u64s(w) + " (may be weighted) should be 0, while it is not";  // :357-362
-                have_error = true;
-            }
-        }
+        int rc = evaluate_recorded(have_error, first_error);
+        if (rc != ZKB_OK) return rc;
         if (!have_error && has_error) {
             first_error = found_error;
             have_error = true;

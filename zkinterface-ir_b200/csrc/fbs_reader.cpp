@@ -26,6 +26,14 @@ struct Buf {
     int32_t i32(size_t pos) const { need(pos, 4); int32_t v; memcpy(&v, p + pos, 4); return v; }
     uint64_t u64(size_t pos) const { need(pos, 8); uint64_t v; memcpy(&v, p + pos, 8); return v; }
     uint8_t u8(size_t pos) const { need(pos, 1); return p[pos]; }
+    // FlatBuffers offsets may point many vector entries at ONE shared sub-table, which may again hold a vector of shared
+    // entries: a few KB then decode to width^depth owned structs.  Every table view is charged against a budget tied to
+    // the message length (a well-formed gate costs ~5 views per ~45 bytes; the budget allows 8 per byte).
+    mutable uint64_t views = 0;
+    void charge() const {
+        if (++views > 8 * (uint64_t)n + 4096)
+            throw ParseError("zkb: message decodes to more tables than its size allows (shared sub-tables)");
+    }
 };
 
 // A table view.  Field slot k of the vtable holds the offset of the field inside the table
@@ -38,6 +46,7 @@ struct Table {
 
     Table() {}
     Table(const Buf* buf, size_t at) : b(buf), pos(at), ok(true) {
+        b->charge();
         int64_t v = (int64_t)at - (int64_t)b->i32(at);
         if (v < 0 || (size_t)v > b->n) throw ParseError("malformed FlatBuffers message (vtable out of bounds)");
         vt = (size_t)v;

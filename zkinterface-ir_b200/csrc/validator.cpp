@@ -135,28 +135,28 @@ bool is_probably_prime(const std::vector<uint8_t>& value) {  // structs/value.rs
 }
 
 // BTreeSet<WireId>: dense bitmap for small ids, hash set beyond
-class LiveSet {
+class LiveSet {  // HashSet<WireId> (validator.rs:74): a bitmap while ids stay within 64 x the insertions made, a hash set beyond,
+                 // so memory follows the work done and not the largest id a gate names
 public:
-    static constexpr uint64_t kDense = 1ull << 30;
+    static constexpr uint64_t kDense = 1ull << 36;
     bool contains(uint64_t id) const {
-        if (id < kDense) return (id >> 6) < bits_.size() && ((bits_[id >> 6] >> (id & 63)) & 1);
-        return sparse_.count(id) != 0;
+        if ((id >> 6) < bits_.size() && ((bits_[id >> 6] >> (id & 63)) & 1)) return true;
+        return !sparse_.empty() && sparse_.count(id) != 0;
     }
     void insert(uint64_t id) {
-        if (id < kDense) {
-            if ((id >> 6) >= bits_.size()) bits_.resize(std::max<size_t>((id >> 6) + 1, bits_.size() * 2), 0);
-            bits_[id >> 6] |= 1ull << (id & 63);
-        } else {
-            sparse_.insert(id);
-        }
+        if (contains(id)) return;
+        inserts_++;
+        if ((id >> 6) >= bits_.size() && id < kDense && id <= 64 * (inserts_ + 1024))
+            bits_.resize(std::max<size_t>((id >> 6) + 1, bits_.size() * 2), 0);
+        if ((id >> 6) < bits_.size()) bits_[id >> 6] |= 1ull << (id & 63);
+        else sparse_.insert(id);
     }
     bool erase(uint64_t id) {
-        if (id < kDense) {
-            if (!contains(id)) return false;
+        if ((id >> 6) < bits_.size() && ((bits_[id >> 6] >> (id & 63)) & 1)) {
             bits_[id >> 6] &= ~(1ull << (id & 63));
             return true;
         }
-        return sparse_.erase(id) != 0;
+        return !sparse_.empty() && sparse_.erase(id) != 0;
     }
     size_t count() const {
         size_t n = sparse_.size();
@@ -167,6 +167,7 @@ public:
 private:
     std::vector<uint64_t> bits_;
     std::unordered_set<uint64_t> sparse_;
+    uint64_t inserts_ = 0;
 };
 
 struct FnSig {
