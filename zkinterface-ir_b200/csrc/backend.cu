@@ -48,14 +48,6 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
     if (c->prog.keep_copies) return c->fail(ZKB_E_ARG, "this context records in flatten mode: the program can be written out, not evaluated");
     const bool keep_all = keep_values == 1;
-    // a bitwise gate on a constant >= p would need the unreduced integer (evaluator.rs:924-930): refuse up front
-    for (uint32_t v = 0; v < c->prog.n_values() && !c->prog.binary; v++) {
-        uint8_t k = c->prog.kind[v];
-        if (k != V_AND && k != V_XOR) continue;
-        for (uint32_t o : {c->prog.opa[v], c->prog.opb[v]})
-            if (c->prog.kind[o] == V_CONST && c->prog.const_unreduced[c->prog.opb[o]])
-                return c->fail(ZKB_E_UNSUPPORTED, "zkb: a constant >= p feeds a bitwise gate directly (unreduced-integer semantics)");
-    }
     // observable values: whatever is still bound in the flat scope, plus the Evaluator's live wires
     std::vector<uint32_t> live;
     if (keep_values != 2) {
@@ -63,12 +55,16 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
         c->flat_scope.for_each([&](uint64_t, uint32_t v) { live.push_back(v); });
     }
     if (const char* e = getenv("ZKB_SLOT_REUSE")) c->plan.slot_reuse = atoi(e) != 0;
-    c->plan.build(c->prog, keep_all, &live);
+    {
+        NvtxRange r("zkb:levelize");
+        c->plan.build(c->prog, keep_all, &live);
+    }
     c->keep_all = keep_all;
     c->finalized = true;
     c->resident_tile = -1;
     c->inputs_uploaded = false;
     if (!c->has_gpu) return ZKB_OK;  // host-only context: plan can be inspected, not run
+    NvtxRange r_up("zkb:program_upload");
     int rc;
     if ((rc = upload_vec(c, c->d_ops, c->plan.ops)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_aseq, c->plan.op_assert_seq)) != ZKB_OK) return rc;
@@ -76,6 +72,20 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     if ((rc = upload_vec(c, c->d_consts, c->prog.const_limbs)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_level_off, c->plan.level_off)) != ZKB_OK) return rc;
     if (c->plan.n_raw_ops > 0 && (rc = upload_vec(c, c->d_const_flags, c->prog.const_unreduced)) != ZKB_OK) return rc;
+    // raw bytes of the constants >= p, for the bitwise gates that take them unreduced (evaluator.rs:924-930)
+    c->const_raw_stride = 0;
+    if (c->plan.n_raw_ops > 0 && !c->prog.binary) {
+        size_t widest = 0;
+        for (const auto& r : c->prog.const_raw) widest = std::max(widest, r.size());
+        if (widest) {
+            c->const_raw_stride = (uint32_t)((widest + 3) / 4 * 4);
+            std::vector<uint8_t> raw((size_t)c->prog.n_consts() * c->const_raw_stride, 0);
+            for (size_t i = 0; i < c->prog.const_raw.size(); i++)
+                memcpy(&raw[i * c->const_raw_stride], c->prog.const_raw[i].data(), c->prog.const_raw[i].size());
+            if ((rc = upload_vec(c, c->d_const_raw, raw)) != ZKB_OK) return rc;
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // `raw` is pageable and about to go out of scope
+        }
+    }
     if (!c->prog.binary) launch_to_mont(c->prog.nlimb, c->d_consts, c->prog.n_consts(), c->prog.fp, c->stream);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ZKB_OK;
@@ -125,6 +135,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_consts);
         cudaFree(c->d_level_off);
         cudaFree(c->d_const_flags);
+        cudaFree(c->d_const_raw);
         cudaFree(c->d_rawflag);
         cudaFree(c->d_store);
         cudaFree(c->d_inst);
@@ -244,6 +255,7 @@ extern "C" int zkb_push_gates(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gate
                               uint64_t n_consts) {
     REC_PROLOGUE(c);
     if (c->has_pending) return c->fail(ZKB_E_SEMANTIC, c->pending_error);  // evaluator.rs:214-216: latched
+    NvtxRange r_rec("zkb:record_gates");
     Program& p = c->prog;
     Scope& sc = c->flat_scope;
     char buf[96];
@@ -422,6 +434,7 @@ extern "C" int zkb_upload_inputs(zkb_ctx* c, const uint8_t* inst, uint64_t inst_
     if (wit_set_stride != 0 && wit_set_stride < (uint64_t)p.n_witness * value_stride)
         return c->fail(ZKB_E_FATAL, "Missing witness value for PlaintextBackend");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    NvtxRange r_h2d("zkb:h2d_inputs");
     int rc = choose_tile(c, n_batch);
     if (rc != ZKB_OK) return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
@@ -462,12 +475,19 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     g.n_valid = std::min<uint32_t>(wt, c->n_batch - g.batch0);
     g.pad = 0;
     uint8_t* rawflag = pl.n_raw_ops > 0 ? c->d_rawflag : nullptr;
+    RawCtx rawctx;
+    rawctx.rawflag = rawflag;
+    rawctx.loads = c->d_loads;
+    rawctx.const_raw = c->const_raw_stride ? c->d_const_raw : nullptr;
+    rawctx.const_raw_stride = c->const_raw_stride;
+    rawctx.pad = 0;
+    rawctx.in = c->in;
     if (p.binary)
         launch_bool_load_inputs(c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, rawflag,
-                                c->d_const_flags, c->stream);
+                                c->d_const_flags, c->sm_count, c->stream);
     else
         launch_load_inputs(p.nlimb, c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, rawflag,
-                           c->d_const_flags, p.fp, c->stream);
+                           c->d_const_flags, p.fp, c->sm_count, c->stream);
     (*launches)++;
     const bool timed = level_launches != nullptr && d_fail == c->d_first_fail;
     if (timed) {
@@ -503,7 +523,7 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
             uint64_t widest = 0;
             while (e < pl.n_levels && narrow[e] == narrow[l]) widest = std::max(widest, items(e++));
             cudaError_t err = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off + l, e - l, c->d_store, c->d_consts, d_fail,
-                                                 rawflag, g, p.fp, c->sm_count, narrow[l] ? widest : std::max(widest, kClusterItems + 1),
+                                                 rawctx, g, p.fp, c->sm_count, narrow[l] ? widest : std::max(widest, kClusterItems + 1),
                                                  c->stream);
             if (err != cudaSuccess) {
                 if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: cooperative launch failed: %s\n", cudaGetErrorString(err));
@@ -534,13 +554,13 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
             continue;
         }
         if (mid > lo) {
-            launch_level(p.nlimb, c->d_ops + lo, c->d_aseq + lo, mid - lo, c->d_store, c->d_consts, d_fail, rawflag, g, p.fp, c->sm_count, false,
+            launch_level(p.nlimb, c->d_ops + lo, c->d_aseq + lo, mid - lo, c->d_store, c->d_consts, d_fail, rawctx, g, p.fp, c->sm_count, false,
                          c->stream);
             (*launches)++;
             (*level_launches)++;
         }
         if (hi > mid) {
-            launch_level(p.nlimb, c->d_ops + mid, c->d_aseq + mid, hi - mid, c->d_store, c->d_consts, d_fail, rawflag, g, p.fp, c->sm_count, true,
+            launch_level(p.nlimb, c->d_ops + mid, c->d_aseq + mid, hi - mid, c->d_store, c->d_consts, d_fail, rawctx, g, p.fp, c->sm_count, true,
                          c->stream);
             (*launches)++;
             (*level_launches)++;
@@ -550,28 +570,11 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     c->resident_tile = tile;
 }
 
-// SURVEY.md §8a trap 1: values >= p stay RAW in the reference.  The device works on residues, which is exact
-// for add/mul (the reference reduces their results).  The raw-sensitive consumers of an input value are
-// resolved ON THE DEVICE: k_load_inputs writes a per-(input, witness) "raw integer >= p" flag, and the
-// assert / not gates that read an input directly (F_RAW) treat a flagged operand as the non-zero integer it
-// is.  What the device cannot reproduce is a bitwise gate on the unreduced integer itself: refused loudly.
-static int check_unreduced_supported(zkb_ctx* c) {
-    const Program& p = c->prog;
-    if (p.binary) return ZKB_OK;  // mod 2 the bitwise gates only see the low bit: residues are exact
-    for (uint32_t v = 0; v < p.n_values(); v++) {
-        uint8_t k = p.kind[v];
-        if (k == V_AND || k == V_XOR) {
-            bool direct = p.kind[p.opa[v]] == V_INSTANCE || p.kind[p.opa[v]] == V_WITNESS || p.kind[p.opb[v]] == V_INSTANCE ||
-                          p.kind[p.opb[v]] == V_WITNESS;
-            if (direct)
-                return c->fail(ZKB_E_UNSUPPORTED,
-                               "zkb: an instance/witness value >= p feeds a bitwise gate directly; the reference evaluates that on the "
-                               "unreduced integer, which the device path does not hold");
-        }
-    }
-    return ZKB_OK;
-}
-
+// SURVEY.md §8a trap 1: values >= p stay RAW in the reference.  The device works on residues, which is exact for add / mul
+// (the reference reduces their results).  The raw-sensitive consumers of an input value are resolved ON THE DEVICE:
+// k_load_inputs writes a per-(input, witness) "raw integer >= p" flag; the assert / not gates that read an input directly
+// (F_RAW) treat a flagged operand as the non-zero integer it is, and an and / xor gate with a flagged operand re-reads its
+// raw bytes (still resident in d_inst / d_wit / the raw constant table) and works on the unreduced integer (bitwise_raw).
 extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
     if (!c->finalized) return c->fail(ZKB_E_ARG, "zkb_finalize must be called before evaluation");
     if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
@@ -581,10 +584,14 @@ extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
     const uint32_t n_tiles = (c->n_batch + wt - 1) / wt;
     uint64_t launches = 0, level_launches = 0;
     CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-    launch_fill_u32(c->d_first_fail, 0xFFFFFFFFu, c->n_batch, c->stream);
+    launch_fill_u32(c->d_first_fail, 0xFFFFFFFFu, c->n_batch, c->sm_count, c->stream);
     CUDA_TRY(c, cudaMemsetAsync(c->d_unreduced, 0, 4, c->stream));
     launches++;
-    for (uint32_t t = 0; t < n_tiles; t++) run_tile(c, t, c->d_first_fail, &launches, &level_launches);
+    {
+        NvtxRange r_lv("zkb:levels");
+        for (uint32_t t = 0; t < n_tiles; t++) run_tile(c, t, c->d_first_fail, &launches, &level_launches);
+    }
+    NvtxRange r_d2h("zkb:verdict_d2h");
     c->h_first_fail.resize(c->n_batch);
     uint32_t unreduced = 0;
     CUDA_TRY(c, cudaMemcpyAsync(c->h_first_fail.data(), c->d_first_fail, (size_t)c->n_batch * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -606,10 +613,7 @@ extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
     c->timing.load_ms = ms - lv;    // input conversion, verdict fill/copy, gaps
     c->timing.level_launches = level_launches;
     c->timing.kernel_launches = launches;
-    if (unreduced) {
-        int rc = check_unreduced_supported(c);
-        if (rc != ZKB_OK) return rc;
-    }
+    c->n_unreduced_inputs = unreduced;
     if (out)
         for (uint32_t j = 0; j < c->n_batch; j++) {
             uint32_t f = c->h_first_fail[j];
@@ -650,7 +654,7 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
     uint32_t tile = batch_idx >> c->log2_wt;
     if (c->resident_tile != (int64_t)tile) {
         uint64_t a = 0, b = 0;
-        launch_fill_u32(c->d_scratch_fail, 0xFFFFFFFFu, c->n_batch, c->stream);
+        launch_fill_u32(c->d_scratch_fail, 0xFFFFFFFFu, c->n_batch, c->sm_count, c->stream);
         run_tile(c, tile, c->d_scratch_fail, &a, &b);
     }
     std::vector<uint32_t> slots(n);

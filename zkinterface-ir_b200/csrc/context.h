@@ -1,6 +1,7 @@
 // Internal: the context behind zkb_ctx (one host thread + one device).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <string>
@@ -101,6 +102,15 @@ public:
 
 struct R1csDev;  // r1cs.cu
 
+// NVTX range over a phase of the path (host flatten / levelize / H2D / levels / D2H): shows up on the Nsight Systems and
+// ncu timelines; costs a predicted-not-taken branch when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 }  // namespace zkb
 
 struct zkb_ctx {
@@ -131,6 +141,9 @@ struct zkb_ctx {
     uint32_t* d_consts = nullptr;
     uint64_t* d_level_off = nullptr;
     uint8_t* d_const_flags = nullptr;   // per constant: raw value >= p
+    uint8_t* d_const_raw = nullptr;     // raw bytes of the constants (const_raw_stride each), when a bitwise gate may need them
+    uint32_t const_raw_stride = 0;
+    uint32_t n_unreduced_inputs = 0;    // instance / witness values >= p seen by the last run
     uint8_t* d_rawflag = nullptr;       // per (input load, lane): raw value >= p (only when plan.n_raw_ops > 0)
     size_t rawflag_bytes = 0;
     bool coop_supported = false;

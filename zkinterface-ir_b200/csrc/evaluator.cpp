@@ -1075,6 +1075,7 @@ static unsigned parse_threads() {
 }
 
 extern "C" int zkb_evaluator_ingest_buffer(zkb_evaluator* ev, const uint8_t* buf, size_t len) {
+    NvtxRange r_ing("zkb:host_parse_flatten");
     std::vector<std::pair<size_t, size_t>> msgs;
     ir::split_messages(buf, len, msgs);
     const unsigned T = parse_threads();

@@ -81,10 +81,78 @@ k_load_inputs(const InputLoad* __restrict__ loads, uint32_t n_loads, uint32_t* _
 //   AND / XOR act on canonical residues (evaluator.rs:924-930): leave Montgomery form, operate, re-enter.
 //   NOT is (a == 0) ? 1 : 0 (evaluator.rs:932-938); zero is zero in Montgomery form too.
 //   ASSERT passes the operand through so the caller tests it.
+// and / xor with an operand the reference holds UNREDUCED (an instance / witness / constant value >= p feeding the gate
+// directly): (a & b) % m and (a ^ b) % m on the raw integers (evaluator.rs:924-930).  The raw bytes are still resident
+// (d_inst / d_wit, the raw constant table); the other operand is its canonical residue.  The result is reduced by Horner
+// over element-sized chunks from the top, like the input kernel does for wide values.  Rare: kept out of line.
 template <int N>
-__device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const uint32_t* b, uint32_t opc, const FieldParams& fp,
-                                          bool raw_nonzero) {
+__device__ __noinline__ void bitwise_raw(uint32_t* r, const uint32_t* a, const uint32_t* b, bool is_and, bool fa, bool fb, uint32_t slot_a,
+                                         uint32_t slot_b, uint32_t widx, const RawCtx& rc, const FieldParams& fp) {
+    const uint8_t* src[2] = {nullptr, nullptr};
+    uint32_t len[2] = {0, 0};
+    const uint32_t slot[2] = {slot_a, slot_b};
+    const bool flagged[2] = {fa, fb};
+    uint32_t canon[2][N], one[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) one[k] = (k == 0);
+    uint32_t n_chunks = 1;
+    for (int o = 0; o < 2; o++) {
+        if (flagged[o]) {
+            const InputLoad ld = rc.loads[slot[o]];
+            if (ld.kind == V_CONST) {
+                src[o] = rc.const_raw + (size_t)ld.index * rc.const_raw_stride;
+                len[o] = rc.const_raw_stride;
+            } else {
+                src[o] = (ld.kind == V_INSTANCE ? rc.in.inst + (uint64_t)widx * rc.in.inst_set_stride
+                                                : rc.in.wit + (uint64_t)widx * rc.in.wit_set_stride) + (uint64_t)ld.index * rc.in.stride;
+                len[o] = rc.in.stride;
+            }
+            n_chunks = max(n_chunks, (len[o] + 4 * N - 1) / (4 * N));
+        } else {
+            fe_mont_mul<N>(canon[o], o == 0 ? a : b, one, fp.p, fp.n0inv);
+        }
+    }
+    uint32_t acc[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) acc[k] = 0;
+    for (uint32_t c = n_chunks; c-- > 0;) {
+        uint32_t v[2][N];
+        for (int o = 0; o < 2; o++) {
+#pragma unroll
+            for (int k = 0; k < N; k++) v[o][k] = (!flagged[o] && c == 0) ? canon[o][k] : 0u;
+            if (flagged[o]) {
+                const uint32_t b0 = c * 4 * N;
+                for (uint32_t q = 0; q < 4 * N && b0 + q < len[o]; q++) v[o][q >> 2] |= (uint32_t)src[o][b0 + q] << (8 * (q & 3));
+            }
+        }
+        uint32_t x[N], m[N], t[N];
+#pragma unroll
+        for (int k = 0; k < N; k++) x[k] = is_and ? (v[0][k] & v[1][k]) : (v[0][k] ^ v[1][k]);
+        fe_mont_mul<N>(m, x, fp.r2, fp.p, fp.n0inv);  // x * R mod p, for any N-limb x
+        if (c + 1 < n_chunks) {
+            fe_mont_mul<N>(t, acc, fp.r2, fp.p, fp.n0inv);
+            fe_add<N>(acc, t, m, fp.p);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; k++) acc[k] = m[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) r[k] = acc[k];
+}
+
+template <int N>
+__device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint4& d, uint32_t lane, const TileGeom& g,
+                                          const RawCtx& rc, const FieldParams& fp) {
+    const uint32_t opc = d.w & 0xff;
+    // the "raw integer >= p" flags of the operands that are input values (F_RAW: a, F_RAWB: b)
+    const bool fa = (d.w & F_RAW) && rc.rawflag != nullptr && rc.rawflag[((size_t)d.x << g.log2_wt) + lane] != 0;
     if (opc == D_AND || opc == D_XOR) {
+        const bool fb = (d.w & F_RAWB) && rc.rawflag != nullptr && rc.rawflag[((size_t)d.y << g.log2_wt) + lane] != 0;
+        if (fa || fb) {
+            bitwise_raw<N>(r, a, b, opc == D_AND, fa, fb, d.x, d.y, g.batch0 + lane, rc, fp);
+            return;
+        }
         uint32_t one[N], ca[N], cb[N], x[N];
 #pragma unroll
         for (int k = 0; k < N; k++) one[k] = (k == 0);
@@ -94,13 +162,13 @@ __device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const 
         else fe_xor_canon<N>(x, ca, cb, fp.p);
         fe_mont_mul<N>(r, x, fp.r2, fp.p, fp.n0inv);
     } else if (opc == D_NOT) {
-        bool z = fe_is_zero<N>(a) && !raw_nonzero;  // an input >= p is a non-zero integer even when it is 0 mod p
+        bool z = fe_is_zero<N>(a) && !fa;  // an input >= p is a non-zero integer even when it is 0 mod p
 #pragma unroll
         for (int k = 0; k < N; k++) r[k] = z ? fp.one[k] : 0u;
     } else {  // standalone assertion on an input: report non-zero when the raw integer is (evaluator.rs:900-906)
 #pragma unroll
         for (int k = 0; k < N; k++) r[k] = a[k];
-        if (raw_nonzero) r[0] |= 1u;
+        if (fa) r[0] |= 1u;
     }
 }
 
@@ -112,8 +180,7 @@ __device__ __forceinline__ void rare_gate(uint32_t* r, const uint32_t* a, const 
 template <int N, bool RARE>
 __global__ void __launch_bounds__(256)
 k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
-        const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag,
-        TileGeom g, FieldParams fp) {
+        const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, RawCtx rc, TileGeom g, FieldParams fp) {
     const uint64_t total = n_ops << g.log2_wt;
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
@@ -142,8 +209,7 @@ k_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint6
 #pragma unroll
                 for (int k = 0; k < N; k++) b[k] = 0;
             }
-            const bool raw_nonzero = (raw.w & F_RAW) && rawflag != nullptr && rawflag[((size_t)raw.x << g.log2_wt) + lane] != 0;
-            rare_gate<N>(r, a, b, opc, fp, raw_nonzero);
+            rare_gate<N>(r, a, b, raw, lane, g, rc, fp);
         }
         if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
         if (raw.w & F_ASSERT) {
@@ -248,7 +314,7 @@ template <int N, bool CLUSTER>
 __global__ void __launch_bounds__(CLUSTER ? 512 : 256)
 k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
               uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
-              const uint8_t* __restrict__ rawflag, TileGeom g, FieldParams fp) {
+              RawCtx rc, TileGeom g, FieldParams fp) {
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // CLUSTER: the grid is exactly one cluster
@@ -285,10 +351,7 @@ k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq,
             }
             if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
             else if (opc == D_MUL || opc == D_MULC) fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
-            else {
-                const bool raw_nonzero = (raw.w & F_RAW) && rawflag != nullptr && rawflag[((size_t)raw.x << g.log2_wt) + lane] != 0;
-                rare_gate<N>(r, a, b, opc, fp, raw_nonzero);
-            }
+            else rare_gate<N>(r, a, b, raw, lane, g, rc, fp);
             if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
             if (raw.w & F_ASSERT) {
                 bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
@@ -490,15 +553,15 @@ void launch_to_mont(int nlimb, uint32_t* consts, uint32_t n, const FieldParams& 
 
 void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* consts_mont,
                         InputDesc in, TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags,
-                        const FieldParams& fp, cudaStream_t s) {
+                        const FieldParams& fp, int sm_count, cudaStream_t s) {
     if (n_loads == 0) return;
-    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 256);
+    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, sm_count, 256);
     ZKB_DISPATCH_N(nlimb, (k_load_inputs<N><<<grid, 256, 0, s>>>(loads, n_loads, store, consts_mont, in, g, unreduced_count, rawflag,
                                                                  const_flags, fp)));
 }
 
 void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
-                  const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, const FieldParams& fp,
+                  const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g, const FieldParams& fp,
                   int sm_count, bool rare, cudaStream_t s) {
     if (n_ops == 0) return;
     // grid: a whole number of CTAs per SM (multiple of the SM count), grid-stride inside.  Measured on B200
@@ -521,19 +584,19 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
                 ZKB_DISPATCH_N(nlimb, (k_level_pipe<N, 1><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
             }
         } else {
-            ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rawflag, g, fp)));
+            ZKB_DISPATCH_N(nlimb, (k_level<N, false><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rc, g, fp)));
         }
     } else {
-        ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rawflag, g, fp)));
+        ZKB_DISPATCH_N(nlimb, (k_level<N, true><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, rc, g, fp)));
     }
 }
 
 template <int N>
 static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
-                                 const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, FieldParams fp,
+                                 const uint32_t* consts_mont, uint32_t* first_fail, RawCtx rc, TileGeom g, FieldParams fp,
                                  int sm_count, uint64_t max_level_items, cudaStream_t s) {
     void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
-                    (void*)&first_fail, (void*)&rawflag, (void*)&g, (void*)&fp};
+                    (void*)&first_fail, (void*)&rc, (void*)&g, (void*)&fp};
     // a wavefront that fits one cluster of 8 x 512 threads (two items per thread at most): cluster barrier
     static const bool no_cluster = getenv("ZKB_NO_CLUSTER") != nullptr;
     static bool cluster_ok = true;
@@ -569,10 +632,10 @@ static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const 
 }
 
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
-                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g,
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
                                const FieldParams& fp, int sm_count, uint64_t max_level_items, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
-    ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rawflag, g, fp, sm_count,
+    ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count,
                                                 max_level_items, s)));
     return e;
 }
@@ -584,9 +647,10 @@ void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint
 }
 
 void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* const_bits, InputDesc in,
-                             TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags, cudaStream_t s) {
+                             TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags, int sm_count,
+                             cudaStream_t s) {
     if (n_loads == 0) return;
-    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, 148, 256);
+    unsigned grid = grid_for((uint64_t)n_loads << g.log2_wt, sm_count, 256);
     k_bool_load_inputs<<<grid, 256, 0, s>>>(loads, n_loads, store, const_bits, in, g, unreduced_count, rawflag, const_flags);
 }
 
@@ -608,9 +672,9 @@ void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* 
     k_bool_read_values<<<(n + 127) / 128, 128, 0, s>>>(slots, n, store, lane, log2_wt, out);
 }
 
-void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s) {
+void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, int sm_count, cudaStream_t s) {
     if (n == 0) return;
-    k_fill_u32<<<grid_for(n, 148, 8), 256, 0, s>>>(p, v, n);
+    k_fill_u32<<<grid_for(n, sm_count, 8), 256, 0, s>>>(p, v, n);
 }
 
 }  // namespace zkb

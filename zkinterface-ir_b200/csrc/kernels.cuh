@@ -29,29 +29,41 @@ struct InputDesc {
     uint32_t pad;
 };
 
+// What the gates that must see an input's RAW integer need (SURVEY.md section 8a trap 1: constant / instance / witness
+// values >= p stay unreduced in the reference; assert_zero and not test the raw integer, and / xor operate on it).
+struct RawCtx {
+    const uint8_t* rawflag;     // per (input load, lane): raw value >= p; nullptr when no gate of the program needs it
+    const InputLoad* loads;     // input slot -> (kind, stream index): input slots are the load indices
+    const uint8_t* const_raw;   // raw little-endian bytes of the constants, const_raw_stride each (nullptr: none is >= p)
+    uint32_t const_raw_stride;
+    uint32_t pad;
+    InputDesc in;
+};
+
 // arithmetic fields (odd p, Montgomery form)
 void launch_to_mont(int nlimb, uint32_t* consts, uint32_t n, const FieldParams& fp, cudaStream_t s);
 void launch_load_inputs(int nlimb, const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* consts_mont,
                         InputDesc in, TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags,
-                        const FieldParams& fp, cudaStream_t s);
+                        const FieldParams& fp, int sm_count, cudaStream_t s);
 void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store,
-                  const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, const FieldParams& fp,
+                  const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g, const FieldParams& fp,
                   int sm_count, bool rare, cudaStream_t s);
 // every wavefront in one cooperative launch (grid barrier between levels); for launch-bound programs
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
-                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g,
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
                                const FieldParams& fp, int sm_count, uint64_t max_level_items, cudaStream_t s);
 void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                         uint32_t* out, const FieldParams& fp, cudaStream_t s);
 
 // p = 2: bit-sliced, one uint32 word = 32 witnesses
 void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t* store, const uint32_t* const_bits, InputDesc in,
-                             TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags, cudaStream_t s);
+                             TileGeom g, uint32_t* unreduced_count, uint8_t* rawflag, const uint8_t* const_flags, int sm_count,
+                             cudaStream_t s);
 void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
                        uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, int sm_count, cudaStream_t s);
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                              uint32_t* out, cudaStream_t s);
 
-void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, cudaStream_t s);
+void launch_fill_u32(uint32_t* p, uint32_t v, uint64_t n, int sm_count, cudaStream_t s);
 
 }  // namespace zkb

@@ -474,6 +474,13 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                     g.meta |= F_RAW;
                     dc[D_OPS]++;
                 }
+                // and / xor act on the integers the reference holds: an input operand >= p takes part unreduced
+                // (evaluator.rs:924-930).  Mod 2 only the low bit matters, residues are exact there.
+                if ((k == V_AND || k == V_XOR) && !prog.binary && (kind[opa[v]] <= V_WITNESS || kind[opb[v]] <= V_WITNESS)) {
+                    if (kind[opa[v]] <= V_WITNESS) g.meta |= F_RAW;
+                    if (kind[opb[v]] <= V_WITNESS) g.meta |= F_RAWB;
+                    dc[D_OPS]++;
+                }
                 ops[i] = g;
                 op_assert_seq[i] = aseq[v];
                 dc[g.meta & 0xff]++;

@@ -47,6 +47,7 @@ enum DevOp : uint32_t { D_ADD = 0, D_MUL, D_ADDC, D_MULC, D_AND, D_XOR, D_NOT, D
 constexpr uint32_t F_ASSERT = 1u << 8;    // result must be zero; assert seq in Plan::op_assert_seq
 constexpr uint32_t F_NOSTORE = 1u << 9;   // value is consumed by nothing but the fused assert
 constexpr uint32_t F_RAW = 1u << 10;      // operand a is an input value: consult its "raw value >= p" flag (trap 1)
+constexpr uint32_t F_RAWB = 1u << 11;     // operand b (of And / Xor) is an input value: likewise
 constexpr uint32_t kNoSeq = 0xFFFFFFFFu;
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 

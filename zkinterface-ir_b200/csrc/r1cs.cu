@@ -478,7 +478,7 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
     const uint32_t n_tiles = (r->n_batch + wt - 1) / wt;
     uint64_t launches = 0;
     CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-    launch_fill_u32(r->d_first_fail, 0xFFFFFFFFu, r->n_batch, c->stream);
+    launch_fill_u32(r->d_first_fail, 0xFFFFFFFFu, r->n_batch, c->sm_count, c->stream);
     CUDA_TRY(c, cudaMemsetAsync(c->d_unreduced, 0, 4, c->stream));
     launches++;
     while (c->tile_ev.size() < 2 * (size_t)n_tiles) {
