@@ -333,6 +333,49 @@ int zkb_debug_write_flat_relation(zkb_ctx* ctx, const uint8_t* modulus_le, size_
                                   uint64_t n_consts, const uint8_t** out, size_t* out_len);
 int zkb_debug_r1cs_layout(zkb_ctx* ctx, int kind, uint64_t counts[3], uint32_t* slices, uint32_t* terms, uint32_t* row_ids);
 
+/* ------------------------------------------------------------------ 7. multi-GPU (witness-batch sharding)
+ * The reference is single-threaded (evaluator.rs:191-230 checks one witness at a time); the path shards over independent
+ * witnesses: ONE levelized program, replicated on every device; rank r evaluates a contiguous block
+ * of the batch; the only exchange is one MIN all-reduce (NCCL over NVLink) of the per-witness first-failing-assertion
+ * vector, i.e. an AND of the verdict bits.  A rank is a context.  The relation is recorded and finalized on ONE rank (the
+ * root); zkb_comm_broadcast_program ships its device plan to the others with ncclBroadcast — they never see the relation.
+ *
+ *   one process, N devices   ctxs[i] = zkb_create(dev_i);  zkb_comm_init(ctxs, N);  record + zkb_finalize on ctxs[0];
+ *                            zkb_evaluate_sharded(ctxs, N, ...)           (one host thread per device inside the call)
+ *   one process per device   rank 0: zkb_comm_unique_id(&id), hand it to the peers (the launcher's job: MPI, a file, torchrun's
+ *                            store); every rank: zkb_comm_init_rank(ctx, &id, N, rank); rank 0 records + finalizes;
+ *                            every rank: zkb_comm_broadcast_program(ctx, 0), then zkb_comm_evaluate / zkb_comm_run per batch.
+ *
+ * The zkb_comm_* calls marked COLLECTIVE must be made by every rank of the communicator; an argument error is reported
+ * before anything is exchanged, a CUDA / NCCL failure on one rank inside a collective leaves the others waiting (as with
+ * NCCL itself).  NCCL is bound at run time from libnccl.so.2; contexts of ONE process that share a device (a test set-up:
+ * NCCL refuses duplicate GPUs) exchange through peer copies on their own streams instead. */
+typedef struct {
+    uint8_t bytes[128]; /* ncclUniqueId */
+} zkb_comm_id;
+int zkb_comm_unique_id(zkb_comm_id* out);
+int zkb_comm_init_rank(zkb_ctx* ctx, const zkb_comm_id* id, int n_ranks, int rank); /* COLLECTIVE */
+/* the contexts of one process form a communicator, rank i = ctxs[i]. */
+int zkb_comm_init(zkb_ctx** ctxs, int n);
+/* transport: 0 single rank, 1 NCCL, 2 in-process peer copies; nccl_version as ncclGetVersion reports it (0 if unused) */
+int zkb_comm_info(zkb_ctx* ctx, int* rank, int* n_ranks, int* transport, int* nccl_version);
+/* COLLECTIVE.  The root's finalized program -> every other rank (which must not hold a program of its own).  The peers can
+ * then evaluate, read values back (zkb_read_values) and answer zkb_assert_info / zkb_get_stats; they cannot record. */
+int zkb_comm_broadcast_program(zkb_ctx* ctx, int root);
+/* COLLECTIVE.  This rank evaluates witnesses [first, first + n_local) of a batch of n_total (host buffers as in zkb_evaluate,
+ * holding this rank's n_local pairs); out[n_total] receives the verdicts of the WHOLE batch on every rank. */
+int zkb_comm_evaluate(zkb_ctx* ctx, const uint8_t* instances_le, uint64_t instance_set_stride, const uint8_t* witnesses_le,
+                      uint64_t witness_set_stride, uint32_t value_stride, uint32_t n_local, uint32_t first, uint32_t n_total,
+                      zkb_verdict* out);
+/* COLLECTIVE.  The same over the inputs already resident on this rank (zkb_upload_inputs / a previous zkb_comm_evaluate). */
+int zkb_comm_run(zkb_ctx* ctx, uint32_t first, uint32_t n_total, zkb_verdict* out);
+/* One process, N devices: zkb_evaluate over a batch split into N contiguous blocks, witness j on rank j*N/n_batch.
+ * The program finalized on ctxs[0] is broadcast on first use.  Buffers hold the whole batch; out[n_batch]. */
+int zkb_evaluate_sharded(zkb_ctx** ctxs, int n, const uint8_t* instances_le, uint64_t instance_set_stride,
+                         const uint8_t* witnesses_le, uint64_t witness_set_stride, uint32_t value_stride, uint32_t n_batch,
+                         zkb_verdict* out);
+int zkb_run_sharded(zkb_ctx** ctxs, int n, uint32_t n_batch, zkb_verdict* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,8 @@ EXPORTED = [
     "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_metrics_create", "zkb_metrics_destroy", "zkb_metrics_ingest_message",
     "zkb_metrics_ingest_buffer", "zkb_metrics_ingest_paths", "zkb_metrics_json", "zkb_metrics_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
     "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_plan_hash", "zkb_debug_write_flat_relation",
+    "zkb_comm_unique_id", "zkb_comm_init_rank", "zkb_comm_init", "zkb_comm_info", "zkb_comm_broadcast_program", "zkb_comm_evaluate",
+    "zkb_comm_run", "zkb_evaluate_sharded", "zkb_run_sharded",
 ]
 
 _vp, _u8p, _sz, _u64, _u32, _i = C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
@@ -166,6 +168,15 @@ _sig("zkb_debug_plan_hash", _i, _vp, _u64p)
 _sig("zkb_debug_rewrite_message", _i, _vp, _u8p, _sz, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
 _sig("zkb_debug_write_flat_relation", _i, _vp, _u8p, _sz, _i, _vp, _u64, _u8p, _sz, _u64, C.POINTER(C.c_void_p),
      C.POINTER(C.c_size_t))
+_sig("zkb_comm_unique_id", _i, _vp)
+_sig("zkb_comm_init_rank", _i, _vp, _vp, _i, _i)
+_sig("zkb_comm_init", _i, C.POINTER(C.c_void_p), _i)
+_sig("zkb_comm_info", _i, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int))
+_sig("zkb_comm_broadcast_program", _i, _vp, _i)
+_sig("zkb_comm_evaluate", _i, _vp, _u8p, _u64, _u8p, _u64, _u32, _u32, _u32, _u32, _vp)
+_sig("zkb_comm_run", _i, _vp, _u32, _u32, _vp)
+_sig("zkb_evaluate_sharded", _i, C.POINTER(C.c_void_p), _i, _u8p, _u64, _u8p, _u64, _u32, _u32, _vp)
+_sig("zkb_run_sharded", _i, C.POINTER(C.c_void_p), _i, _u32, _vp)
 
 
 class ZkbError(Exception):
@@ -421,6 +432,38 @@ class GpuBackend:
         self._chk(_lib.zkb_get_timing(self._c, C.byref(t)))
         return {k: getattr(t, k) for k, _ in ZkbTiming._fields_}
 
+    # ---- multi-GPU: one context per process (zkb.h section 7) ---------------------
+    def comm_init_rank(self, comm_id: bytes, n_ranks: int, rank: int):
+        """COLLECTIVE: join the communicator rank 0 created with comm_unique_id()"""
+        cid = bytes(comm_id)
+        if len(cid) != 128:
+            raise ZkbError(ZKB_E_ARG, "comm id must be the 128 bytes of comm_unique_id()")
+        self._chk(_lib.zkb_comm_init_rank(self._c, _buf(cid), n_ranks, rank))
+
+    def comm_info(self) -> dict:
+        r, n, t, v = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._chk(_lib.zkb_comm_info(self._c, C.byref(r), C.byref(n), C.byref(t), C.byref(v)))
+        return {"rank": r.value, "n_ranks": n.value, "transport": {0: "single", 1: "nccl", 2: "in-process"}[t.value],
+                "nccl_version": v.value}
+
+    def comm_broadcast_program(self, root: int = 0):
+        """COLLECTIVE: the root's finalized program -> this rank (device plan over NCCL, no re-levelization)"""
+        self._chk(_lib.zkb_comm_broadcast_program(self._c, root))
+
+    def comm_evaluate(self, instances, witnesses, n_local: int, first: int, n_total: int) -> np.ndarray:
+        """COLLECTIVE: this rank's witnesses [first, first + n_local) of a batch of n_total; verdicts of the whole batch"""
+        inst, iss, wit, wss, stride = self._strides(instances, witnesses, n_local)
+        out = np.zeros(n_total, dtype=VERDICT_DTYPE)
+        self._chk(_lib.zkb_comm_evaluate(self._c, _buf(inst), iss, _buf(wit), wss, stride, n_local, first, n_total, _buf(out)))
+        self._n_batch = n_local
+        return out
+
+    def comm_run(self, first: int, n_total: int) -> np.ndarray:
+        """COLLECTIVE: the same over the resident inputs"""
+        out = np.zeros(n_total, dtype=VERDICT_DTYPE)
+        self._chk(_lib.zkb_comm_run(self._c, first, n_total, _buf(out)))
+        return out
+
     # ---- debug / measurement ---------------------------------------------------
     def debug_field_ops(self, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint32)
@@ -498,6 +541,60 @@ class GpuBackend:
     def r1cs_run(self) -> np.ndarray:
         out = np.zeros(self._n_batch, dtype=VERDICT_DTYPE)
         self._chk(_lib.zkb_r1cs_run(self._c, _buf(out)))
+        return out
+
+
+def comm_unique_id() -> bytes:
+    """rank 0 of a one-process-per-GPU job: the id every rank passes to GpuBackend.comm_init_rank (zkb.h section 7)"""
+    out = C.create_string_buffer(128)
+    rc = _lib.zkb_comm_unique_id(C.cast(out, C.c_void_p))
+    if rc != ZKB_OK:
+        raise ZkbError(rc, "zkb_comm_unique_id failed (NCCL not available?)")
+    return out.raw
+
+
+class ShardedBackend:
+    """One process, N devices (zkb.h section 7): `backends[0]` records and finalizes the relation, the others receive its
+    device plan on first use; a batch is split into N contiguous blocks, the verdicts MIN-reduced over NCCL."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.backends = [GpuBackend(d) for d in devices]
+        self._arr = (C.c_void_p * len(self.backends))(*[b._c for b in self.backends])
+        rc = _lib.zkb_comm_init(self._arr, len(self.backends))
+        if rc != ZKB_OK:
+            msg = _lib.zkb_last_error(self.backends[0]._c).decode("utf-8", "replace")
+            self.close()
+            raise ZkbError(rc, msg)
+        self.root = self.backends[0]
+        self._n_batch = 0
+
+    def close(self):
+        for b in getattr(self, "backends", []):
+            b.close()
+
+    def shard_of(self, rank: int, n_batch: int):
+        n = len(self.backends)
+        return n_batch * rank // n, n_batch * (rank + 1) // n
+
+    def owner(self, j: int, n_batch: int):
+        """(backend holding witness j, its index there)"""
+        for r, b in enumerate(self.backends):
+            lo, hi = self.shard_of(r, n_batch)
+            if lo <= j < hi:
+                return b, j - lo
+        raise IndexError(j)
+
+    def evaluate(self, instances, witnesses, n_batch: int) -> np.ndarray:
+        inst, iss, wit, wss, stride = self.root._strides(instances, witnesses, n_batch)
+        out = np.zeros(n_batch, dtype=VERDICT_DTYPE)
+        self.root._chk(_lib.zkb_evaluate_sharded(self._arr, len(self.backends), _buf(inst), iss, _buf(wit), wss, stride, n_batch,
+                                                 _buf(out)))
+        self._n_batch = n_batch
+        return out
+
+    def run(self) -> np.ndarray:
+        out = np.zeros(self._n_batch, dtype=VERDICT_DTYPE)
+        self.root._chk(_lib.zkb_run_sharded(self._arr, len(self.backends), self._n_batch, _buf(out)))
         return out
 
 

@@ -32,6 +32,8 @@ void ctx_latch(zkb_ctx* c, const std::string& msg) {
     }
 }
 
+static int ensure_fail_vectors(zkb_ctx* c, uint32_t n);
+
 template <class T>
 static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
     if (dptr) {
@@ -144,6 +146,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_scratch_fail);
         cudaFree(c->d_unreduced);
         r1cs_free(c);
+        comm_free(c);
         for (int i = 0; i < 4; i++)
             if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         for (auto e : c->tile_ev) cudaEventDestroy(e);
@@ -184,6 +187,7 @@ extern "C" int zkb_minus_one(zkb_ctx* c, uint8_t* out, size_t cap, size_t* len) 
 }
 
 #define REC_PROLOGUE(c)                                                                         \
+    if ((c)->is_replica) return (c)->fail(ZKB_E_ARG, "this context holds a replica of another rank's program: nothing can be recorded here"); \
     if (!(c)->prog.field_set) return (c)->fail(ZKB_E_ARG, "set_field must be called before recording"); \
     if ((c)->finalized) return (c)->fail(ZKB_E_ARG, "program already finalized");               \
     if ((c)->prog.n_values() >= (c)->max_values) return (c)->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)")
@@ -451,14 +455,7 @@ extern "C" int zkb_upload_inputs(zkb_ctx* c, const uint8_t* inst, uint64_t inst_
     c->in.wit_set_stride = wit_set_stride;
     c->in.stride = value_stride;
     c->n_batch = n_batch;
-    if (n_batch > c->first_fail_cap) {
-        if (c->d_first_fail) cudaFree(c->d_first_fail);
-        if (c->d_scratch_fail) cudaFree(c->d_scratch_fail);
-        c->d_first_fail = c->d_scratch_fail = nullptr;
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_first_fail, (size_t)n_batch * 4));
-        CUDA_TRY(c, cudaMalloc((void**)&c->d_scratch_fail, (size_t)n_batch * 4));
-        c->first_fail_cap = n_batch;
-    }
+    if ((rc = ensure_fail_vectors(c, n_batch)) != ZKB_OK) return rc;
     c->inputs_uploaded = true;
     c->resident_tile = -1;
     return ZKB_OK;
@@ -489,7 +486,7 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         launch_load_inputs(p.nlimb, c->d_loads, (uint32_t)pl.loads.size(), c->d_store, c->d_consts, c->in, g, c->d_unreduced, rawflag,
                            c->d_const_flags, p.fp, c->sm_count, c->stream);
     (*launches)++;
-    const bool timed = level_launches != nullptr && d_fail == c->d_first_fail;
+    const bool timed = level_launches != nullptr && d_fail != c->d_scratch_fail;
     if (timed) {
         while (c->tile_ev.size() < 2 * (size_t)(tile + 1)) {
             cudaEvent_t e;
@@ -575,26 +572,51 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
 // k_load_inputs writes a per-(input, witness) "raw integer >= p" flag; the assert / not gates that read an input directly
 // (F_RAW) treat a flagged operand as the non-zero integer it is, and an and / xor gate with a flagged operand re-reads its
 // raw bytes (still resident in d_inst / d_wit / the raw constant table) and works on the unreduced integer (bitwise_raw).
-extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
+namespace zkb {
+
+static int ensure_fail_vectors(zkb_ctx* c, uint32_t n) {
+    if (n <= c->first_fail_cap) return ZKB_OK;
+    if (c->d_first_fail) cudaFree(c->d_first_fail);
+    if (c->d_scratch_fail) cudaFree(c->d_scratch_fail);
+    c->d_first_fail = c->d_scratch_fail = nullptr;
+    c->first_fail_cap = 0;
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_first_fail, (size_t)n * 4));
+    CUDA_TRY(c, cudaMalloc((void**)&c->d_scratch_fail, (size_t)n * 4));
+    c->first_fail_cap = n;
+    return ZKB_OK;
+}
+
+// One pass over the resident inputs.  `first` / `n_total`: this context's witnesses are [first, first + n_batch) of a batch
+// of n_total sharded over the contexts of a communicator (comm.cu); the verdict vector is then MIN-reduced over the ranks
+// (the path's only collective) and `out` holds all n_total verdicts on every rank.  A plain run is
+// first = 0, n_total = n_batch, collective = false.
+int ctx_run(zkb_ctx* c, zkb_verdict* out, uint32_t first, uint32_t n_total, bool collective) {
     if (!c->finalized) return c->fail(ZKB_E_ARG, "zkb_finalize must be called before evaluation");
     if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
     if (!c->inputs_uploaded) return c->fail(ZKB_E_ARG, "zkb_upload_inputs must be called before zkb_run");
+    if ((uint64_t)first + c->n_batch > n_total) return c->fail(ZKB_E_ARG, "this rank's witnesses do not fit in the batch");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = ensure_fail_vectors(c, n_total);
+    if (rc != ZKB_OK) return rc;
     const uint32_t wt = 1u << c->log2_wt;
     const uint32_t n_tiles = (c->n_batch + wt - 1) / wt;
     uint64_t launches = 0, level_launches = 0;
     CUDA_TRY(c, cudaEventRecord(c->ev[2], c->stream));
-    launch_fill_u32(c->d_first_fail, 0xFFFFFFFFu, c->n_batch, c->sm_count, c->stream);
+    launch_fill_u32(c->d_first_fail, 0xFFFFFFFFu, n_total, c->sm_count, c->stream);
     CUDA_TRY(c, cudaMemsetAsync(c->d_unreduced, 0, 4, c->stream));
     launches++;
     {
         NvtxRange r_lv("zkb:levels");
-        for (uint32_t t = 0; t < n_tiles; t++) run_tile(c, t, c->d_first_fail, &launches, &level_launches);
+        for (uint32_t t = 0; t < n_tiles; t++) run_tile(c, t, c->d_first_fail + first, &launches, &level_launches);
+    }
+    if (collective) {
+        NvtxRange r_ar("zkb:verdict_allreduce");
+        if ((rc = comm_allreduce_min_u32(c, c->d_first_fail, n_total)) != ZKB_OK) return rc;
     }
     NvtxRange r_d2h("zkb:verdict_d2h");
-    c->h_first_fail.resize(c->n_batch);
+    c->h_first_fail.resize(n_total);
     uint32_t unreduced = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_first_fail.data(), c->d_first_fail, (size_t)c->n_batch * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_first_fail.data(), c->d_first_fail, (size_t)n_total * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(&unreduced, c->d_unreduced, 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -610,12 +632,12 @@ extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
         lv += x;
     }
     c->timing.levels_ms = lv;       // level kernels only, summed over tiles
-    c->timing.load_ms = ms - lv;    // input conversion, verdict fill/copy, gaps
+    c->timing.load_ms = ms - lv;    // input conversion, verdict fill / all-reduce / copy, gaps
     c->timing.level_launches = level_launches;
     c->timing.kernel_launches = launches;
     c->n_unreduced_inputs = unreduced;
     if (out)
-        for (uint32_t j = 0; j < c->n_batch; j++) {
+        for (uint32_t j = 0; j < n_total; j++) {
             uint32_t f = c->h_first_fail[j];
             memset(&out[j], 0, sizeof(zkb_verdict));
             out[j].ok = (f == 0xFFFFFFFFu) && !c->has_pending;
@@ -624,17 +646,25 @@ extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) {
     return ZKB_OK;
 }
 
+void ctx_finish_e2e_timing(zkb_ctx* c) {
+    float h2d = 0, total = 0;
+    cudaEventElapsedTime(&h2d, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&total, c->ev[0], c->ev[3]);
+    c->timing.h2d_ms = h2d;
+    c->timing.total_ms = total;
+}
+
+}  // namespace zkb
+
+extern "C" int zkb_run(zkb_ctx* c, zkb_verdict* out) { return ctx_run(c, out, 0, c->n_batch, false); }
+
 extern "C" int zkb_evaluate(zkb_ctx* c, const uint8_t* inst, uint64_t inst_set_stride, const uint8_t* wit, uint64_t wit_set_stride,
                             uint32_t value_stride, uint32_t n_batch, zkb_verdict* out) {
     int rc = zkb_upload_inputs(c, inst, inst_set_stride, wit, wit_set_stride, value_stride, n_batch);
     if (rc != ZKB_OK) return rc;
     rc = zkb_run(c, out);
     if (rc != ZKB_OK) return rc;
-    float h2d = 0, total = 0;
-    cudaEventElapsedTime(&h2d, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&total, c->ev[0], c->ev[3]);
-    c->timing.h2d_ms = h2d;
-    c->timing.total_ms = total;
+    ctx_finish_e2e_timing(c);
     return ZKB_OK;
 }
 
@@ -716,6 +746,7 @@ extern "C" int zkb_set_limits(zkb_ctx* c, uint64_t max_values, uint64_t max_step
 // same program must be identical whatever the number of host threads that built them
 extern "C" int zkb_debug_plan_hash(zkb_ctx* c, uint64_t* out) {
     if (!c->finalized) return c->fail(ZKB_E_ARG, "zkb_finalize must be called first");
+    if (c->is_replica) return c->fail(ZKB_E_ARG, "replica context: the host copy of the plan lives on the root rank");
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](const void* p, size_t n) {
         const uint8_t* b = (const uint8_t*)p;
@@ -754,7 +785,7 @@ extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
     if (c->finalized) {
         s->n_slots = c->plan.n_slots;
         s->n_levels = c->plan.n_levels;
-        s->n_device_ops = c->plan.ops.size();
+        s->n_device_ops = c->is_replica ? c->replica_n_ops : c->plan.ops.size();
         s->algo_bytes_per_witness = c->plan.algo_bytes_per_witness;
     }
     if (c->inputs_uploaded) {
@@ -771,6 +802,7 @@ extern "C" int zkb_get_timing(zkb_ctx* c, zkb_timing* t) {
 
 extern "C" int zkb_get_program(zkb_ctx* c, uint64_t first, uint64_t n, uint8_t* kinds, uint32_t* a, uint32_t* b) {
     const Program& p = c->prog;
+    if (c->is_replica) return c->fail(ZKB_E_ARG, "replica context: the recorded program lives on the root rank");
     if (first + n > p.n_values()) return c->fail(ZKB_E_ARG, "program range out of bounds");
     for (uint64_t i = 0; i < n; i++) {
         kinds[i] = p.kind[first + i];
@@ -798,6 +830,7 @@ extern "C" int zkb_assert_value(zkb_ctx* c, uint64_t seq, zkb_wire* value) {
 
 extern "C" int zkb_level_info(zkb_ctx* c, uint64_t level, uint64_t out[5]) {
     if (!c->finalized || level >= c->plan.n_levels) return c->fail(ZKB_E_ARG, "level out of range");
+    if (c->is_replica) return c->fail(ZKB_E_ARG, "replica context: the host copy of the plan lives on the root rank");
     const Plan& pl = c->plan;
     const uint64_t E = c->prog.binary ? 1 : (uint64_t)c->prog.nlimb * 4;
     uint64_t lo = pl.level_off[level], hi = pl.level_off[level + 1];

@@ -100,7 +100,8 @@ public:
     }
 };
 
-struct R1csDev;  // r1cs.cu
+struct R1csDev;    // r1cs.cu
+struct CommState;  // comm.cu
 
 // NVTX range over a phase of the path (host flatten / levelize / H2D / levels / D2H): shows up on the Nsight Systems and
 // ncu timelines; costs a predicted-not-taken branch when no tool is attached.
@@ -168,6 +169,12 @@ struct zkb_ctx {
 
     zkb::R1csDev* r1cs = nullptr;
 
+    // multi-GPU (include/zkb.h section 7): this context's rank in a communicator, and whether its program is a replica
+    // received from the root rank (device plan + the host tables evaluation and read-back need; nothing was recorded here)
+    zkb::CommState* comm = nullptr;
+    bool is_replica = false;
+    uint64_t replica_n_ops = 0;
+
     int fail(int code, const std::string& msg) {
         err = msg;
         return code;
@@ -180,4 +187,9 @@ int ctx_finalize(zkb_ctx* c, int keep_values);  // 0 live wires, 1 all values, 2
 bool ctx_record_ok(zkb_ctx* c);  // false when a recording error is latched
 void ctx_latch(zkb_ctx* c, const std::string& msg);
 void r1cs_free(zkb_ctx* c);
+int ctx_run(zkb_ctx* c, zkb_verdict* out, uint32_t first, uint32_t n_total, bool collective);
+void ctx_finish_e2e_timing(zkb_ctx* c);
+// comm.cu
+int comm_allreduce_min_u32(zkb_ctx* c, uint32_t* d_buf, size_t n);  // in place, on c->stream
+void comm_free(zkb_ctx* c);
 }  // namespace zkb
