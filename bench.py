@@ -224,15 +224,30 @@ def main():
     circ_mod = importlib.import_module("zkir_b200.circuits")
 
     # ---- one-off preparation: relation -> levelized device program ---------------------------
+    # N > 1: the relation is recorded and levelized ONCE, on rank 0; the other ranks receive the device plan over NCCL
+    # (zkb_comm_broadcast_program, include/zkb.h section 7) and never see the relation.
     t0 = time.perf_counter()
     circuit = circ_mod.random_circuit(n_gates, args.inputs, p, SEED)
     t_gen = time.perf_counter() - t0
-    t0 = time.perf_counter()
     be = z.GpuBackend(local_rank)
-    be.set_field(p)
-    be.push_gates(circuit.gates, circuit.const_pool)
-    be.finalize(keep_all_values=False, verdicts_only=args.verdicts_only)
+    if world > 1:
+        cid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            cid.copy_(torch.frombuffer(bytearray(z.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(cid, 0)                       # plumbing: the id reaches the peers through the launcher's group
+        be.comm_init_rank(bytes(cid.cpu().numpy().tobytes()), world, rank)
+        dist.barrier()
+    t0 = time.perf_counter()
+    if rank == 0:
+        be.set_field(p)
+        be.push_gates(circuit.gates, circuit.const_pool)
+        be.finalize(keep_all_values=False, verdicts_only=args.verdicts_only)
     t_prep = time.perf_counter() - t0
+    t_bcast = 0.0
+    if world > 1:
+        t0 = time.perf_counter()
+        be.comm_broadcast_program(0)
+        t_bcast = time.perf_counter() - t0
     st = be.stats()
 
     # ---- this rank's shard of the witness batch (contiguous block) ---------------------------
@@ -252,9 +267,8 @@ def main():
     w_host = w_pinned.numpy()
     expected = circ_mod.expected_first_fail(circuit, n_local, corrupt_local)
 
-    def verdict_allreduce(v):
-        """the path's only collective: MIN-reduce of first_fail over the whole batch (NCCL over NVLink)"""
-        return shard.allreduce_first_fail(shard.first_fail_vector(v), lo, hi, total_w)
+    def first_fail_vector(v):
+        return np.where(v["ok"] == 1, np.int64(1) << 40, v["first_fail_seq"].astype(np.int64))
 
     def check(ff_local):
         got = np.where(ff_local >= (1 << 40), -1, ff_local)[:n_local]
@@ -269,42 +283,41 @@ def main():
     gate_evals_total = circuit.n_gates * total_w
 
     def timed(fn, steps):
-        """device time of a step = the library's CUDA events (its own stream: H2D, kernels, verdict D2H)
-        + CUDA events around the verdict all-reduce (torch's stream); max over ranks."""
+        """device time of a step = the library's CUDA events on its own stream: (H2D,) kernels, the verdict MIN all-reduce
+        (ncclAllReduce inside libzkb, the path's only collective), verdict D2H; max over ranks."""
         barrier()
         dev_ms = 0.0
         lv_ms = 0.0
-        ar = []
         t0 = time.perf_counter()
         for _ in range(steps):
             v = fn()
             tm = be.timing()
             dev_ms += tm["total_ms"]
             lv_ms += tm["levels_ms"]
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ff = verdict_allreduce(v)
-            e1.record()
-            ar.append((e0, e1))
         barrier()
         wall = time.perf_counter() - t0
-        if world > 1:
-            dev_ms += sum(a.elapsed_time(b) for a, b in ar)
         t = torch.tensor([dev_ms, wall * 1e3, lv_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t[0].item(), t[1].item(), t[2].item(), ff, v
+        return t[0].item(), t[1].item(), t[2].item(), first_fail_vector(v), v
+
+    if world > 1:       # every rank receives the verdicts of the WHOLE batch
+        run_resident = lambda: be.comm_run(lo, total_w)                                   # noqa: E731
+        run_e2e = lambda: be.comm_evaluate(None, w_host, n_local, lo, total_w)            # noqa: E731
+    else:
+        run_resident = be.run
+        run_e2e = lambda: be.evaluate(None, w_host, n_local)                              # noqa: E731
 
     # ---- value: inputs resident in HBM -----------------------------------------------------------
     be.upload_inputs(None, w_host, n_local)
     st = be.stats()
     for _ in range(args.warmup):
-        v = be.run()
-    check(np.where(v["ok"] == 1, np.int64(1) << 40, v["first_fail_seq"].astype(np.int64)))
+        v = run_resident()
+    check(first_fail_vector(v)[lo:hi])
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev_ms, wall_ms, lv_ms, ff, v = timed(be.run, args.steps)
+    dev_ms, wall_ms, lv_ms, ff, v = timed(run_resident, args.steps)
     launches = be.timing()["kernel_launches"] * args.steps
     level_launches = be.timing()["level_launches"]
     ms_per_step = dev_ms / args.steps
@@ -312,12 +325,12 @@ def main():
 
     # ---- e2e: host buffers through the C ABI --------------------------------------------------------
     for _ in range(min(args.warmup, 2)):
-        be.evaluate(None, w_host, n_local)
-    e_dev_ms, e_wall_ms, _, ff2, v2 = timed(lambda: be.evaluate(None, w_host, n_local), args.steps)
+        run_e2e()
+    e_dev_ms, e_wall_ms, _, ff2, v2 = timed(run_e2e, args.steps)
     sampler.stop_flag = True
     e2e_ms = max(e_dev_ms, 0.0) / args.steps
     e2e_value = gate_evals_total / (e2e_ms * 1e-3)
-    check(np.where(v2["ok"] == 1, np.int64(1) << 40, v2["first_fail_seq"].astype(np.int64)))
+    check(ff2[lo:hi])
     if world > 1:
         n_false = int((ff2 < (1 << 40)).sum())
         assert n_false == len(corrupt_global), (n_false, len(corrupt_global))
@@ -420,12 +433,13 @@ def main():
                        "l2": "working set (wire store) is >> L2, no flush needed", "parallelism": f"witness-shard x{world}",
                        "wires_kept_readable": "none (verdicts only)" if args.verdicts_only else "all live top-scope wires"},
             "e2e": {"value": e2e_value, "unit": "gate-evals/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(w_host.nbytes) * world, "d2h_bytes_per_step": 4 * total_w + 4 * world},
+                    "h2d_bytes_per_step": int(w_host.nbytes) * world, "d2h_bytes_per_step": (4 * total_w + 4) * world},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(),
-            "prep_s": {"generate_circuit": t_gen, "flatten_levelize_upload": t_prep},
+            "prep_s": {"generate_circuit": t_gen, "flatten_levelize_upload": t_prep, "program_broadcast": t_bcast,
+                       "note": "levelized once on rank 0; the peers receive the device plan over NCCL (zkb_comm_broadcast_program)"},
             "wall_ms_per_step": wall_ms / args.steps,
             "verdicts": {"true": int((ff >= (1 << 40)).sum()), "false": int((ff < (1 << 40)).sum()),
                          "checked": "all, against the generator's expectation (1 % corrupted, first failing assertion known)"},

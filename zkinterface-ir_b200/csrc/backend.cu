@@ -145,6 +145,10 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_first_fail);
         cudaFree(c->d_scratch_fail);
         cudaFree(c->d_unreduced);
+        cudaFree(c->d_tab_slot);
+        cudaFree(c->d_tab_opb);
+        cudaFree(c->d_tab_readable);
+        cudaFree(c->d_tab_kind);
         r1cs_free(c);
         comm_free(c);
         for (int i = 0; i < 4; i++)
@@ -674,6 +678,23 @@ extern "C" int zkb_assert_info(zkb_ctx* c, uint64_t seq, uint64_t* src_wire_id) 
     return ZKB_OK;
 }
 
+// replica contexts keep the value tables on the device (comm.cu): fetch the entries of the requested handles
+__global__ void k_gather_value_tables(const uint64_t* __restrict__ handles, uint32_t n, uint64_t n_values, const uint32_t* __restrict__ t_slot,
+                                      const uint32_t* __restrict__ t_opb, const uint8_t* __restrict__ t_read, const uint8_t* __restrict__ t_kind,
+                                      uint32_t* __restrict__ out) {  // out: 4 x uint32 per handle {slot, opb, readable, kind}
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = handles[i];
+    if (v >= n_values) {
+        out[4 * i + 3] = 0xFFFFFFFFu;  // unknown handle
+        return;
+    }
+    out[4 * i] = t_slot[v];
+    out[4 * i + 1] = t_opb[v];
+    out[4 * i + 2] = t_read[v];
+    out[4 * i + 3] = t_kind[v];
+}
+
 extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* values, uint64_t n, uint8_t* out, size_t stride) {
     if (!c->finalized || !c->inputs_uploaded) return c->fail(ZKB_E_ARG, "nothing has been evaluated yet");
     if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
@@ -687,14 +708,38 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
         launch_fill_u32(c->d_scratch_fail, 0xFFFFFFFFu, c->n_batch, c->sm_count, c->stream);
         run_tile(c, tile, c->d_scratch_fail, &a, &b);
     }
-    std::vector<uint32_t> slots(n);
-    for (uint64_t i = 0; i < n; i++) {
-        if (values[i] >= p.n_values()) return c->fail(ZKB_E_ARG, "unknown wire handle");
-        uint32_t s = c->plan.slot_of_value[values[i]];
-        if (s == kNoSlot || !c->plan.readable[values[i]])
-            return c->fail(ZKB_E_ARG, "value was not kept on device (finalize with keep_all_values = 1 to read every value)");
-        slots[i] = s;
+    // per requested value: its slot, kind and operand b (constant-pool index / stream position of an input)
+    std::vector<uint32_t> slots(n), kinds(n), opbs(n);
+    if (c->is_replica) {
+        uint64_t* d_h = nullptr;
+        uint32_t* d_t = nullptr;
+        std::vector<uint32_t> t(4 * std::max<size_t>(n, 1));
+        CUDA_TRY(c, cudaMalloc((void**)&d_h, std::max<size_t>(n, 1) * 8));
+        CUDA_TRY(c, cudaMalloc((void**)&d_t, t.size() * 4));
+        CUDA_TRY(c, cudaMemcpyAsync(d_h, values, n * 8, cudaMemcpyHostToDevice, c->stream));
+        if (n) k_gather_value_tables<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_h, (uint32_t)n, c->replica_n_values, c->d_tab_slot, c->d_tab_opb,
+                                                                                       c->d_tab_readable, c->d_tab_kind, d_t);
+        CUDA_TRY(c, cudaMemcpyAsync(t.data(), d_t, n * 16, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d_h);
+        cudaFree(d_t);
+        for (uint64_t i = 0; i < n; i++) {
+            if (t[4 * i + 3] == 0xFFFFFFFFu) return c->fail(ZKB_E_ARG, "unknown wire handle");
+            slots[i] = t[4 * i + 2] ? t[4 * i] : kNoSlot;
+            opbs[i] = t[4 * i + 1];
+            kinds[i] = t[4 * i + 3];
+        }
+    } else {
+        for (uint64_t i = 0; i < n; i++) {
+            if (values[i] >= p.n_values()) return c->fail(ZKB_E_ARG, "unknown wire handle");
+            slots[i] = c->plan.readable[values[i]] ? c->plan.slot_of_value[values[i]] : kNoSlot;
+            kinds[i] = p.kind[values[i]];
+            opbs[i] = p.opb[values[i]];
+        }
     }
+    for (uint64_t i = 0; i < n; i++)
+        if (slots[i] == kNoSlot)
+            return c->fail(ZKB_E_ARG, "value was not kept on device (finalize with keep_all_values = 1 to read every value)");
     uint32_t *d_slots = nullptr, *d_out = nullptr;
     CUDA_TRY(c, cudaMalloc((void**)&d_slots, std::max<size_t>(n, 1) * 4));
     CUDA_TRY(c, cudaMalloc((void**)&d_out, std::max<size_t>(n, 1) * eb));
@@ -714,14 +759,13 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
         memset(dst, 0, stride);
         const uint8_t* src = host.data() + i * eb;
         size_t nb = eb;
-        uint32_t v = (uint32_t)values[i];
         std::vector<uint8_t> tmp;
-        if (p.kind[v] == V_CONST && p.const_unreduced[p.opb[v]]) {
-            src = p.const_raw[p.opb[v]].data();
-            nb = p.const_raw[p.opb[v]].size();
-        } else if (p.kind[v] == V_INSTANCE || p.kind[v] == V_WITNESS) {
-            bool is_inst = p.kind[v] == V_INSTANCE;
-            size_t off = (size_t)batch_idx * (is_inst ? c->in.inst_set_stride : c->in.wit_set_stride) + (size_t)p.opb[v] * c->in.stride;
+        if (kinds[i] == V_CONST && p.const_unreduced[opbs[i]]) {
+            src = p.const_raw[opbs[i]].data();
+            nb = p.const_raw[opbs[i]].size();
+        } else if (kinds[i] == V_INSTANCE || kinds[i] == V_WITNESS) {
+            bool is_inst = kinds[i] == V_INSTANCE;
+            size_t off = (size_t)batch_idx * (is_inst ? c->in.inst_set_stride : c->in.wit_set_stride) + (size_t)opbs[i] * c->in.stride;
             tmp.resize(c->in.stride);
             CUDA_TRY(c, cudaMemcpy(tmp.data(), (is_inst ? c->d_inst : c->d_wit) + off, c->in.stride, cudaMemcpyDeviceToHost));
             raw_in.swap(tmp);
@@ -773,7 +817,7 @@ extern "C" int zkb_debug_plan_hash(zkb_ctx* c, uint64_t* out) {
 extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
     memset(s, 0, sizeof(*s));
     const Program& p = c->prog;
-    s->n_values = p.n_values();
+    s->n_values = c->is_replica ? c->replica_n_values : p.n_values();
     s->n_asserts = p.asserts.size();
     s->n_instance = p.n_instance;
     s->n_witness = p.n_witness;

@@ -6,8 +6,8 @@
 // (TRUE = 0xFFFFFFFF), i.e. an AND of the verdict bits.
 //
 //   * the program is levelized ONCE, on the root rank; zkb_comm_broadcast_program ships the device plan (gate descriptors,
-//     assertion table, input loads, Montgomery constants, level offsets) device-to-device with ncclBroadcast, plus a small
-//     host table (level offsets, slot map, assertion wire ids) that the peers need to launch and to read values back;
+//     assertion table, input loads, Montgomery constants, level offsets, the value -> slot tables read-back consults)
+//     device-to-device with ncclBroadcast, plus a small host table (level offsets, input loads, assertion wire ids);
 //   * ranks are contexts: N contexts of one process (zkb_comm_init: ncclCommInitAll, one host thread per device in
 //     zkb_evaluate_sharded) or one context per process (zkb_comm_unique_id + zkb_comm_init_rank: torchrun / MPI style);
 //   * NCCL is bound at run time from libnccl.so.2 (the copy the process already holds, e.g. PyTorch's, else the system
@@ -17,8 +17,10 @@
 //     path is testable on a one-GPU box; distinct devices always go through NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -198,6 +200,19 @@ int comm_allreduce_min_u32(zkb_ctx* c, uint32_t* d_buf, size_t n) {
     return ZKB_OK;
 }
 
+static int comm_warm_up(zkb_ctx* c) {
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    uint32_t* d = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&d, 256));
+    CUDA_TRY(c, cudaMemsetAsync(d, 0xFF, 256, c->stream));
+    int rc = comm_allreduce_min_u32(c, d, 64);
+    if (rc == ZKB_OK) rc = comm_broadcast(c, d, 256, 0);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (rc == ZKB_OK && e != cudaSuccess) return c->fail(ZKB_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------------- program replica
 // What a peer needs on the HOST to launch the plan, to answer zkb_assert_info / zkb_get_stats and to read values back.
 struct ReplicaHeader {
@@ -245,6 +260,14 @@ static int broadcast_program(zkb_ctx* c, int root) {
         return c->fail(ZKB_E_ARG, "zkb_comm_broadcast_program: this context holds a program of its own");
     CUDA_TRY(c, cudaSetDevice(c->device));
     NvtxRange r_b("zkb:program_broadcast");
+    const bool dbg = getenv("ZKB_DEBUG") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!dbg) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "zkb: rank %d broadcast %-14s %8.2f ms\n", cm->rank, what, std::chrono::duration<double, std::milli>(now - t_start).count());
+        t_start = now;
+    };
     Program& p = c->prog;
     Plan& pl = c->plan;
     ReplicaHeader h;
@@ -256,7 +279,7 @@ static int broadcast_program(zkb_ctx* c, int root) {
         h.n_ops = c->is_replica ? c->replica_n_ops : pl.ops.size();
         h.n_loads = pl.loads.size();
         h.n_consts = p.n_consts();
-        h.n_values = p.kind.size();
+        h.n_values = c->is_replica ? c->replica_n_values : p.kind.size();
         h.n_asserts = p.asserts.size();
         h.n_levels = pl.n_levels;
         h.n_raw_ops = pl.n_raw_ops;
@@ -290,10 +313,6 @@ static int broadcast_program(zkb_ctx* c, int root) {
         put(blob, pl.level_rare.data(), pl.level_rare.size());
         put(blob, pl.loads.data(), pl.loads.size());
         put(blob, p.asserts.data(), p.asserts.size());
-        put(blob, pl.slot_of_value.data(), pl.slot_of_value.size());
-        put(blob, pl.readable.data(), pl.readable.size());
-        put(blob, p.kind.data(), p.kind.size());
-        put(blob, p.opb.data(), p.opb.size());
         put(blob, p.const_limbs.data(), p.const_limbs.size());
         put(blob, p.const_unreduced.data(), p.const_unreduced.size());
         put(blob, const_raw_flat.data(), const_raw_flat.size());
@@ -316,6 +335,7 @@ static int broadcast_program(zkb_ctx* c, int root) {
     }
     cudaFree(d_stage);
     if (rc != ZKB_OK) return rc;
+    lap("header");
     // 2. the host tables, staged through device memory
     uint8_t* d_blob = nullptr;
     CUDA_TRY(c, cudaMalloc((void**)&d_blob, std::max<size_t>(h.blob_bytes, 16)));
@@ -331,6 +351,7 @@ static int broadcast_program(zkb_ctx* c, int root) {
     }
     cudaFree(d_blob);
     if (rc != ZKB_OK) return rc;
+    lap("host tables");
     if (!is_root) {
         p = Program();
         pl = Plan();
@@ -339,10 +360,6 @@ static int broadcast_program(zkb_ctx* c, int root) {
         get(cur, pl.level_rare, h.n_levels);
         get(cur, pl.loads, h.n_loads);
         get(cur, p.asserts, h.n_asserts);
-        get(cur, pl.slot_of_value, h.n_values);
-        get(cur, pl.readable, h.n_values);
-        get(cur, p.kind, h.n_values);
-        get(cur, p.opb, h.n_values);
         get(cur, p.const_limbs, h.n_consts * h.nlimb);
         get(cur, p.const_unreduced, h.n_consts);
         get(cur, const_raw_flat, h.const_raw_bytes);
@@ -379,12 +396,14 @@ static int broadcast_program(zkb_ctx* c, int root) {
         c->keep_all = h.keep_all != 0;
         c->const_raw_stride = h.const_raw_stride;
         c->replica_n_ops = h.n_ops;
+        c->replica_n_values = h.n_values;
         c->is_replica = true;
         c->finalized = true;
         c->inputs_uploaded = false;
         c->resident_tile = -1;
         c->flat_scope.clear();
     }
+    lap("unpack");
     // 3. the device plan, device to device
     if ((rc = bcast_array(c, c->d_ops, h.n_ops, root, is_root)) != ZKB_OK) return rc;
     if ((rc = bcast_array(c, c->d_aseq, h.n_ops, root, is_root)) != ZKB_OK) return rc;
@@ -394,6 +413,46 @@ static int broadcast_program(zkb_ctx* c, int root) {
     if ((rc = bcast_array(c, c->d_const_flags, h.has_const_flags ? h.n_consts : 0, root, is_root)) != ZKB_OK) return rc;
     if ((rc = bcast_array(c, c->d_const_raw, (size_t)h.const_raw_stride * h.n_consts, root, is_root)) != ZKB_OK) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    lap("device plan");
+    // the per-value tables (value -> slot / readable / kind / operand b) stay ON THE DEVICE of a replica: zkb_read_values
+    // gathers the few entries a request names, so no peer pays a device-to-host copy of tables as long as the program
+    {
+        uint32_t *t_slot = c->d_tab_slot, *t_opb = c->d_tab_opb;
+        uint8_t *t_read = c->d_tab_readable, *t_kind = c->d_tab_kind;
+        const bool own = is_root && !c->is_replica;  // a recording root uploads its host tables for the duration of the broadcast
+        if (own) {
+            t_slot = t_opb = nullptr;
+            t_read = t_kind = nullptr;
+            const size_t n = h.n_values;
+            if (n) {
+                CUDA_TRY(c, cudaMalloc((void**)&t_slot, n * 4));
+                CUDA_TRY(c, cudaMalloc((void**)&t_opb, n * 4));
+                CUDA_TRY(c, cudaMalloc((void**)&t_read, n));
+                CUDA_TRY(c, cudaMalloc((void**)&t_kind, n));
+                CUDA_TRY(c, cudaMemcpyAsync(t_slot, pl.slot_of_value.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(t_opb, p.opb.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(t_read, pl.readable.data(), n, cudaMemcpyHostToDevice, c->stream));
+                CUDA_TRY(c, cudaMemcpyAsync(t_kind, p.kind.data(), n, cudaMemcpyHostToDevice, c->stream));
+            }
+        }
+        if ((rc = bcast_array(c, t_slot, h.n_values, root, is_root)) != ZKB_OK) return rc;
+        if ((rc = bcast_array(c, t_opb, h.n_values, root, is_root)) != ZKB_OK) return rc;
+        if ((rc = bcast_array(c, t_read, h.n_values, root, is_root)) != ZKB_OK) return rc;
+        if ((rc = bcast_array(c, t_kind, h.n_values, root, is_root)) != ZKB_OK) return rc;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (own) {
+            cudaFree(t_slot);
+            cudaFree(t_opb);
+            cudaFree(t_read);
+            cudaFree(t_kind);
+        } else {
+            c->d_tab_slot = t_slot;
+            c->d_tab_opb = t_opb;
+            c->d_tab_readable = t_read;
+            c->d_tab_kind = t_kind;
+        }
+    }
+    lap("value tables");
     cm->program_generation++;
     return ZKB_OK;
 }
@@ -428,7 +487,8 @@ extern "C" int zkb_comm_init_rank(zkb_ctx* c, const zkb_comm_id* id, int n_ranks
     c->comm->rank = rank;
     c->comm->size = n_ranks;
     c->comm->nccl = comm;
-    return ZKB_OK;
+    // NCCL connects lazily: the first collective pays for the channels.  Pay here, where the communicator is made.
+    return comm_warm_up(c);
 }
 
 extern "C" int zkb_comm_init(zkb_ctx** ctxs, int n) {
@@ -464,6 +524,15 @@ extern "C" int zkb_comm_init(zkb_ctx** ctxs, int n) {
         ctxs[i]->comm->size = n;
         ctxs[i]->comm->nccl = comms[i];
         ctxs[i]->comm->local = local;
+    }
+    if (comms[0]) {  // connect the channels now (one thread per rank: a collective blocks until every rank has joined it)
+        std::vector<int> rcs(n, ZKB_OK);
+        std::vector<std::thread> th;
+        for (int i = 1; i < n; i++) th.emplace_back([&, i] { rcs[i] = comm_warm_up(ctxs[i]); });
+        rcs[0] = comm_warm_up(ctxs[0]);
+        for (auto& t : th) t.join();
+        for (int i = 0; i < n; i++)
+            if (rcs[i] != ZKB_OK) return i ? c0->fail(rcs[i], "rank " + std::to_string(i) + ": " + ctxs[i]->err) : rcs[i];
     }
     return ZKB_OK;
 }

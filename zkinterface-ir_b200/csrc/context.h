@@ -173,7 +173,9 @@ struct zkb_ctx {
     // received from the root rank (device plan + the host tables evaluation and read-back need; nothing was recorded here)
     zkb::CommState* comm = nullptr;
     bool is_replica = false;
-    uint64_t replica_n_ops = 0;
+    uint64_t replica_n_ops = 0, replica_n_values = 0;
+    uint32_t *d_tab_slot = nullptr, *d_tab_opb = nullptr;      // replica: value -> slot / operand b, on the device
+    uint8_t *d_tab_readable = nullptr, *d_tab_kind = nullptr;  // replica: value -> readable / kind
 
     int fail(int code, const std::string& msg) {
         err = msg;
