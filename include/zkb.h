@@ -315,6 +315,9 @@ int zkb_r1cs_run(zkb_ctx* ctx, zkb_verdict* out);
  * field_throughput: register-resident dependent chains of `iters` operations per thread -> operations/s. */
 int zkb_debug_field_ops(zkb_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint64_t n);
 int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops_per_second);
+/* random 32-byte gathers (8 in flight per thread, L2-only loads) from a table of table_bytes: bytes gathered per second —
+ * the ceiling of the one-assignment R1CS check, whose traffic is z[col] look-ups in a vector larger than L2 */
+int zkb_debug_gather_throughput(zkb_ctx* ctx, uint64_t table_bytes, uint32_t iters, double* bytes_per_second);
 /* Device layout of kind 0 (tiles of fewer than 32 assignments: ones and general terms in separate classes) or 1 (wider
  * tiles: one class per matrix, ones tagged inside it), host-only contexts: counts = {slices, term groups, rows}; slices: 4 x uint32 per slice
  * {first group, A ones | A general << 16, B ones | B general << 16, C ones | C general << 16} (group counts per term

@@ -94,7 +94,15 @@ def c4(log2_rows, log2_free, batch):
     tot, lv = timed_runs(b.r1cs_run, b.timing)
     algo = c.r1cs_algorithmic_bytes(r) * batch
     ge = c.r1cs_gate_equivalent(r)
-    return {"config": f"C4 R1CS 2^{log2_rows} constraints, BN254, batch {batch}", "constraints_per_s": r.n_rows * batch / (lv * 1e-3),
+    # ceiling of the z look-ups: random 32-byte gathers from a table of z's size (one assignment), measured here
+    gather = b.debug_gather_throughput(max(r.n_vars * 32, 1 << 20)) / 1e9 if batch == 1 else None
+    z_bytes = 32 * r.nnz * batch
+    extra = {}
+    if gather:
+        # the gathered sectors at the gather ceiling + the streamed descriptors at the copy peak
+        floor_ms = (z_bytes / gather + (algo - z_bytes) / PEAK) / 1e9 * 1e3
+        extra = {"random_gather_GBps": gather, "gather_bound_ms": floor_ms, "frac_of_gather_bound": floor_ms / lv}
+    return {**extra, "config": f"C4 R1CS 2^{log2_rows} constraints, BN254, batch {batch}", "constraints_per_s": r.n_rows * batch / (lv * 1e-3),
             "gate_equivalent_per_s": ge * batch / (lv * 1e-3), "check_kernel_ms": lv, "total_ms_incl_z_conversion": tot, "nnz": r.nnz,
             "n_vars": r.n_vars, "algo_GBps": algo / (lv * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (lv * 1e-3) / 1e9 / PEAK,
             "assignment_gen_s": gen}

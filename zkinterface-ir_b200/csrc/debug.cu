@@ -1,6 +1,7 @@
 // Debug / measurement entry points (not on the product path):
 //   zkb_debug_field_ops         element-wise field ops on the device, both the PTX carry-chain product and the
 //                               portable CIOS product, so tests can compare them with Python integers
+//   zkb_debug_gather_throughput random 32-byte gathers per second from a table larger than L2: the ceiling of the R1CS check
 //   zkb_debug_field_throughput  register-resident Montgomery products / modular additions per second: the
 //                               integer-pipe ceiling of the level kernel
 #include <algorithm>
@@ -60,6 +61,31 @@ __global__ void __launch_bounds__(256) k_field_throughput(int op, uint32_t iters
     if (acc == 0x12345678u) sink[0] = acc;  // keep the chain alive
 }
 
+// random 32-byte gathers (two 16-byte loads of one sector) from a table far larger than L2, 8 independent gathers in
+// flight per thread: the ceiling of any kernel whose traffic is z[col] look-ups (k_r1cs_check with one assignment)
+__global__ void __launch_bounds__(256) k_gather_throughput(const uint4* __restrict__ table, uint64_t n_elems, uint32_t iters, uint32_t* sink) {
+    uint64_t x = (blockIdx.x * 256ull + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = 0; i < iters; i++) {
+        uint4 v[16];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            const uint64_t e = (uint64_t)(((x >> 32) * n_elems) >> 32);
+            v[2 * k] = __ldcg(table + 2 * e);
+            v[2 * k + 1] = __ldcg(table + 2 * e + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            acc.x ^= v[k].x;
+            acc.y ^= v[k].y;
+            acc.z ^= v[k].z;
+            acc.w ^= v[k].w;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) sink[0] = acc.x;
+}
+
 }  // namespace
 
 #define DISPATCH_N(nlimb, CALL)                        \
@@ -113,5 +139,31 @@ extern "C" int zkb_debug_field_throughput(zkb_ctx* c, int op, uint32_t iters, do
     }
     cudaFree(sink);
     *ops_per_second = (double)grid * 256.0 * iters / (best * 1e-3);
+    return ZKB_OK;
+}
+
+extern "C" int zkb_debug_gather_throughput(zkb_ctx* c, uint64_t table_bytes, uint32_t iters, double* bytes_per_second) {
+    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
+    if (table_bytes < 64 || iters == 0) return c->fail(ZKB_E_ARG, "table_bytes >= 64 and iters > 0");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    uint4* table = nullptr;
+    uint32_t* sink = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&table, table_bytes));
+    CUDA_TRY(c, cudaMalloc((void**)&sink, 4));
+    CUDA_TRY(c, cudaMemsetAsync(table, 0x5A, table_bytes, c->stream));
+    const unsigned grid = (unsigned)c->sm_count * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+        k_gather_throughput<<<grid, 256, 0, c->stream>>>(table, table_bytes / 32, iters, sink);
+        CUDA_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaFree(table);
+    cudaFree(sink);
+    *bytes_per_second = (double)grid * 256.0 * iters * 8.0 * 32.0 / (best * 1e-3);
     return ZKB_OK;
 }

@@ -10,6 +10,7 @@
 // dot products in Montgomery form and the row test, with the first violated row reported per
 // witness (= the first failing AssertZero of the gate expansion, which emits one per row in order).
 // No tensor cores: the matrices are ~3 nnz/row sparse, nothing here is a dense contraction.
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -117,117 +118,226 @@ k_r1cs_load_z(const uint8_t* __restrict__ zraw, uint64_t set_stride, uint32_t st
     }
 }
 
-// The term stream of one (row, assignment lane): terms are consumed in storage order (A ones, A general, B ..., C ...).
-// Loads in flight per thread: the {col, coef} pair three terms ahead and the z limbs of the next kZDepth terms in
-// registers while the current term's integer chain runs (the gathers are random 32-byte sectors of a z that does not
-// fit in L2: their latency is what the kernel waits on, `long_scoreboard` in ncu).  `prefetch.global.L2` of later
-// terms was measured and made things worse at every distance (scripts/ab_r1cs_prefetch.sh: 0.535 ms without,
-// 0.561 / 0.629 / 0.649 / 0.662 ms at 3 / 6 / 10 / 16 terms ahead), like in the level kernel.
-#ifndef ZKB_R1CS_ZDEPTH
-#define ZKB_R1CS_ZDEPTH 1
+// ---------------------------------------------------------------------------------------------------------------------
+// k_r1cs_check: thread <-> (sorted row, assignment lane), lane fastest.
+//
+// The kernel waits on the z gathers: random 32-byte sectors of a vector far larger than L2, ~1 us away.  Keeping HBM
+// busy needs (bandwidth x latency) / 32 B ~ 1100 sectors in flight per SM; a thread that holds its operands in registers
+// keeps one or two (round 1: 2480 GB/s = 0.38 of the copy peak, long_scoreboard 5.4, occupancy 33 % at 80 registers).
+// Here NOTHING waits in registers: every thread owns two small rings in shared memory, filled by cp.async (LDGSTS),
+//     D ring: the {col, tag} descriptors of its next terms   (8-byte coalesced / broadcast loads)
+//     G ring: the z limbs those descriptors name             (16-byte gathers, L2 only: .cg)
+// and runs a three-deep software pipeline over its term stream, one commit group per term:
+//     step s:  wait until group s - GA has landed      (descriptor of term s - GA, limbs of term s - 2 GA)
+//              issue the gather of term s - GA, request the descriptor of term s, commit group s
+//              consume term s - 2 GA from shared memory (Montgomery multiply-add)
+// so GA gathers and GA descriptor loads per thread are in flight while the integer chain runs, across row boundaries
+// (the stream continues into the thread's next row), with no registers tied up.  The stream is self-describing: the top
+// two bits of a tag mark the last term of A_r, of B_r and of C_r (build_layout writes them into the device copy), so the
+// consumer needs no slice header; only the descriptor cursor reads headers, one item ahead.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t TD_MASK = 0x3FFFFFFFu;  // device tag: low 30 bits = coefficient index | TD_ONE | TD_PAD
+constexpr uint32_t TD_PAD = 0x3FFFFFFFu;
+constexpr uint32_t TD_ONE = 0x3FFFFFFEu;
+constexpr uint32_t M_END_A = 1, M_END_B = 2, M_END_C = 3;  // tag >> 30
+
+#ifndef ZKB_R1CS_GA
+#define ZKB_R1CS_GA 3
 #endif
-template <int N>
-struct TermStream {
-    static constexpr int kZDepth = ZKB_R1CS_ZDEPTH;  // 1 or 2
-    const uint2* tp;  // this row's column of the slice: term k at tp[32 * k]
-    const uint32_t* z;
-    uint32_t lane, log2_wt, k, K;
-    uint2 t0, t1, t2;
-    uint32_t z0[N], z1[N], z2[kZDepth == 2 ? N : 1];
+#ifndef ZKB_R1CS_MIN_CTAS
+#define ZKB_R1CS_MIN_CTAS 4
+#endif
+constexpr int kR1csThreads = 256;
 
-    __device__ __forceinline__ uint2 fetch(uint32_t i) const { return i < K ? __ldg(tp + (size_t)32 * i) : make_uint2(0, T_PAD); }
-    __device__ __forceinline__ void gather(uint32_t* dst, const uint2& t) const {
-#pragma unroll
-        for (int i = 0; i < N; i++) dst[i] = 0;
-        if (t.y != T_PAD) load_elem<N>(dst, z, t.x, lane, log2_wt);
-    }
-    __device__ __forceinline__ void start(const uint2* tp_, const uint32_t* z_, uint32_t lane_, uint32_t log2_wt_, uint32_t K_) {
-        tp = tp_; z = z_; lane = lane_; log2_wt = log2_wt_; k = 0; K = K_;
-        t0 = fetch(0);
-        t1 = fetch(1);
-        t2 = fetch(2);
-        gather(z0, t0);
-        if (kZDepth == 2) gather(z1, t1);
-    }
-    // issue the loads of the following terms; call before the current term's arithmetic
-    __device__ __forceinline__ void prefetch(uint2& t3) {
-        t3 = fetch(k + 3);
-        if (kZDepth == 2) gather(z2, t2);
-        else gather(z1, t1);
-    }
-    __device__ __forceinline__ void advance(const uint2& t3) {
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            z0[i] = z1[i];
-            if (kZDepth == 2) z1[i] = z2[i];
-        }
-        t0 = t1; t1 = t2; t2 = t3;
-        k++;
-    }
-};
-
-// acc = sum of the next n_one terms with coefficient one, then of the next n_gen terms with a general coefficient
-// (Montgomery residues).  The two kinds are stored apart so that the lanes of a warp never wait on a product they
-// do not need: a slice runs max(ones) additions and max(general) multiply-adds, not their union.
-template <int N>
-__device__ __forceinline__ void lc_dot(uint32_t* acc, TermStream<N>& st, uint32_t n_one, uint32_t n_gen, const uint32_t* __restrict__ coefs,
-                                       const FieldParams& fp) {
-#pragma unroll
-    for (int i = 0; i < N; i++) acc[i] = 0;
-    for (uint32_t j = 0; j < n_one; j++) {
-        uint2 t3;
-        st.prefetch(t3);
-        if (st.t0.y != T_PAD) fe_add<N>(acc, acc, st.z0, fp.p);
-        st.advance(t3);
-    }
-    for (uint32_t j = 0; j < n_gen; j++) {
-        uint2 t3;
-        st.prefetch(t3);
-        const uint32_t ci = st.t0.y;
-        if (ci == T_ONE) {  // layout kind 1 keeps the ones inside the general class (a warp-uniform branch there)
-            fe_add<N>(acc, acc, st.z0, fp.p);
-        } else if (ci != T_PAD) {
-            uint32_t t[N], cf[N];
-#pragma unroll
-            for (int i = 0; i < N; i++) cf[i] = __ldg(coefs + (size_t)ci * N + i);
-            fe_mont_mul<N>(t, st.z0, cf, fp.p, fp.n0inv);
-            fe_add<N>(acc, acc, t, fp.p);
-        }
-        st.advance(t3);
-    }
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(uint32_t smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_dst), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+template <int CW>
+__device__ __forceinline__ void lds_chunk(uint32_t* o, uint32_t a) {
+    if constexpr (CW == 4) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(a));
+    else if constexpr (CW == 2) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o[0]), "=r"(o[1]) : "r"(a));
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o[0]) : "r"(a));
+}
+template <int CW>
+__device__ __forceinline__ void sts_chunk(uint32_t a, const uint32_t* o) {
+    if constexpr (CW == 4) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+    else if constexpr (CW == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(o[0]), "r"(o[1]) : "memory");
+    else asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(o[0]) : "memory");
 }
 
-// thread <-> (sorted row, assignment lane), lane fastest
-#ifndef ZKB_R1CS_MIN_CTAS
-#define ZKB_R1CS_MIN_CTAS 3
-#endif
+// Ring sizes are powers of two so that a ring position is (step & mask): the D ring needs 2 GA + 1 entries (a descriptor
+// lives from its request to the consumption of its term), the G ring GA + 1 (limbs live from the gather to the consumption).
 template <int N>
-__global__ void __launch_bounds__(256, ZKB_R1CS_MIN_CTAS)
+struct R1csSmem {
+    static constexpr int GA = ZKB_R1CS_GA;
+    static constexpr int RD = GA <= 3 ? 8 : 16;
+    static constexpr int RG = GA <= 3 ? 4 : 8;
+    static_assert(2 * GA + 1 <= RD && GA + 1 <= RG, "rings too small for this look-ahead");
+    static constexpr int CW = Elem<N>::CW, NC = Elem<N>::NC, CB = CW * 4;       // chunk: limbs, count, bytes
+    static constexpr uint32_t d_bytes = (uint32_t)RD * kR1csThreads * 8;       // [RD][threads] x {col, tag}
+    static constexpr uint32_t g_bytes = (uint32_t)RG * NC * kR1csThreads * CB;  // [RG][NC][threads] x chunk
+    static constexpr uint32_t a_bytes = (uint32_t)NC * kR1csThreads * CB;       // [NC][threads]: A_r . z, then (A_r . z)(B_r . z), parked while the next LC runs
+    static constexpr size_t bytes = (size_t)d_bytes + g_bytes + a_bytes;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kR1csThreads, ZKB_R1CS_MIN_CTAS)
 k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, const uint32_t* __restrict__ row_ids,
              const uint32_t* __restrict__ coefs, const uint32_t* __restrict__ z, uint64_t n_rows, uint64_t n_slices,
              uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
-    const uint64_t total = (n_slices * 32) << g.log2_wt;
-    const uint32_t wt_mask = (1u << g.log2_wt) - 1;
-    const bool single = g.log2_wt == 0;
-    for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total; tid += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t lane = (uint32_t)tid & wt_mask;
-        const uint64_t srow = tid >> g.log2_wt;
-        const uint4 sl = __ldg(slices + (srow >> 5));  // {first group, A ones | A general << 16, B ..., C ...}
-        const uint32_t ka1 = sl.y & 0xFFFF, kag = sl.y >> 16, kb1 = sl.z & 0xFFFF, kbg = sl.z >> 16, kc1 = sl.w & 0xFFFF, kcg = sl.w >> 16;
-        TermStream<N> st;
-        st.start(terms + (size_t)sl.x * 32 + (srow & 31), z, lane, g.log2_wt, ka1 + kag + kb1 + kbg + kc1 + kcg);
-        uint32_t a[N], b[N], cc[N], ab[N];
-        lc_dot<N>(a, st, ka1, kag, coefs, fp);
-        lc_dot<N>(b, st, kb1, kbg, coefs, fp);
-        lc_dot<N>(cc, st, kc1, kcg, coefs, fp);
-        fe_mont_mul<N>(ab, a, b, fp.p, fp.n0inv);  // (aR)(bR)/R = abR, compared with cR
-        uint32_t diff = 0;
+    using S = R1csSmem<N>;
+    constexpr int GA = S::GA, NC = S::NC, CW = S::CW;
+    constexpr uint32_t D_STEP = kR1csThreads * 8, G_STEP = NC * kR1csThreads * S::CB, C_STEP = kR1csThreads * S::CB;
+    extern __shared__ uint4 smem_raw[];
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t d_base = smem0 + threadIdx.x * 8;
+    const uint32_t g_base = smem0 + S::d_bytes + threadIdx.x * S::CB;
+    const uint32_t a_base = smem0 + S::d_bytes + S::g_bytes + threadIdx.x * S::CB;
+    const uint2 pad_desc = make_uint2(0, TD_PAD);
 #pragma unroll
-        for (int k = 0; k < N; k++) diff |= ab[k] ^ cc[k];
-        const bool real = srow < n_rows;  // the last slice may hold padding rows
-        bool fail = diff != 0 && real && lane < g.n_valid;
-        report_fail(fail, real ? __ldg(row_ids + srow) : 0u, first_fail, g.batch0 + lane, single);
+    for (int i = 0; i < S::RD; i++) sts64(d_base + i * D_STEP, pad_desc);  // terms before the first are padding: no prologue
+
+    const uint64_t total = (n_slices * 32) << g.log2_wt;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool single = g.log2_wt == 0;
+    uint64_t d_item = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint32_t lane = (uint32_t)d_item & ((1u << g.log2_wt) - 1);  // the same for every item of this thread (stride is a multiple of the tile)
+    const uint8_t* z_lane = reinterpret_cast<const uint8_t*>(z) + (size_t)lane * S::CB;
+    const uint32_t z_elem = (uint32_t)(NC * S::CB) << g.log2_wt;   // bytes between consecutive variables
+    const uint32_t z_chunk = (uint32_t)S::CB << g.log2_wt;         // bytes between the chunks of one variable
+
+    // ---- descriptor cursor: walks this thread's items (tid, tid + stride, ...), K groups each
+    bool d_alive = d_item < total;
+    uint4 hdr = d_alive ? __ldg(slices + ((d_item >> g.log2_wt) >> 5)) : make_uint4(0, 0, 0, 0);
+    const uint2* d_ptr = terms;
+    uint32_t d_left = 0;
+    auto d_open = [&]() {  // hdr = header of d_item; afterwards hdr = header of the item after it (load in flight)
+        d_left = (hdr.y & 0xFFFF) + (hdr.y >> 16) + (hdr.z & 0xFFFF) + (hdr.z >> 16) + (hdr.w & 0xFFFF) + (hdr.w >> 16);
+        d_ptr = terms + (size_t)hdr.x * 32 + ((d_item >> g.log2_wt) & 31);
+        const uint64_t nxt = d_item + stride;
+        if (nxt < total) hdr = __ldg(slices + ((nxt >> g.log2_wt) >> 5));
+    };
+    if (d_alive) d_open();
+    uint64_t c_item = d_item;  // item the consumer is in
+    int drain = 0;
+
+    uint32_t acc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) acc[i] = 0;
+
+    for (uint32_t s = 0;; s++) {
+        cp_async_wait<GA - 1>();
+        // (1) gather the limbs of term s - GA: its descriptor has landed
+        {
+            const uint2 t = lds64(d_base + ((s - GA) & (S::RD - 1)) * D_STEP);
+            if ((t.y & TD_MASK) != TD_PAD) {
+                const uint8_t* src = z_lane + (uint64_t)t.x * z_elem;
+                const uint32_t dst = g_base + ((s - GA) & (S::RG - 1)) * G_STEP;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    if constexpr (S::CB == 16) cp_async_16(dst + c * C_STEP, src + (size_t)c * z_chunk);
+                    else cp_async_small<S::CB>(dst + c * C_STEP, src + (size_t)c * z_chunk);
+                }
+            }
+        }
+        // (2) request the descriptor of term s
+        if (d_alive) {
+            cp_async_small<8>(d_base + (s & (S::RD - 1)) * D_STEP, d_ptr);
+            d_ptr += 32;
+            if (--d_left == 0) {
+                d_item += stride;
+                d_alive = d_item < total;
+                if (d_alive) d_open();
+            }
+        } else {
+            sts64(d_base + (s & (S::RD - 1)) * D_STEP, pad_desc);  // past the last term: padding drains the pipeline
+            if (++drain > 2 * GA) break;
+        }
+        cp_async_commit();
+        // (3) consume term s - 2 GA
+        const uint2 t = lds64(d_base + ((s - 2 * GA) & (S::RD - 1)) * D_STEP);
+        const uint32_t tag = t.y & TD_MASK;
+        if (tag != TD_PAD) {
+            uint32_t zl[N];
+            const uint32_t srcs = g_base + ((s - 2 * GA) & (S::RG - 1)) * G_STEP;
+#pragma unroll
+            for (int c = 0; c < NC; c++) lds_chunk<CW>(zl + c * CW, srcs + c * C_STEP);
+            if (tag == TD_ONE) {
+                fe_add<N>(acc, acc, zl, fp.p);
+            } else {
+                uint32_t cf[N], prod[N];
+                using V = typename Vec<CW>::T;
+                const V* cv = reinterpret_cast<const V*>(coefs) + (size_t)tag * NC;  // a few KB, L1-resident (the gathers bypass L1)
+#pragma unroll
+                for (int c = 0; c < NC; c++) unpack(__ldg(cv + c), cf + c * CW);
+                fe_mont_mul<N>(prod, zl, cf, fp.p, fp.n0inv);
+                fe_add<N>(acc, acc, prod, fp.p);
+            }
+        }
+        const uint32_t mark = t.y >> 30;
+        if (mark != 0) {
+            if (mark == M_END_A) {  // park A_r . z in shared memory: the registers serve B_r
+#pragma unroll
+                for (int c = 0; c < NC; c++) sts_chunk<CW>(a_base + c * C_STEP, acc + c * CW);
+            } else if (mark == M_END_B) {  // (aR)(bR)/R = abR takes the parking place: only the accumulator lives across terms
+                uint32_t av[N], ab[N];
+#pragma unroll
+                for (int c = 0; c < NC; c++) lds_chunk<CW>(av + c * CW, a_base + c * C_STEP);
+                fe_mont_mul<N>(ab, av, acc, fp.p, fp.n0inv);
+#pragma unroll
+                for (int c = 0; c < NC; c++) sts_chunk<CW>(a_base + c * C_STEP, ab + c * CW);
+            } else {  // abR against cR
+                uint32_t ab[N];
+#pragma unroll
+                for (int c = 0; c < NC; c++) lds_chunk<CW>(ab + c * CW, a_base + c * C_STEP);
+                uint32_t diff = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) diff |= ab[i] ^ acc[i];
+                const uint64_t srow = c_item >> g.log2_wt;
+                const bool fail = diff != 0 && srow < n_rows && lane < g.n_valid;  // the last slice may hold padding rows
+                report_fail(fail, fail ? __ldg(row_ids + srow) : 0u, first_fail, g.batch0 + lane, single);
+                c_item += stride;
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++) acc[i] = 0;
+        }
     }
+    cp_async_wait<0>();
+}
+
+static unsigned grid_for(uint64_t total, int sm_count, int per_sm);
+
+// persistent grid: as many CTAs as the shared-memory rings allow, every thread streams through its rows
+template <int N>
+static void launch_r1cs_check(zkb_ctx* c, R1csDev* r, const R1csLayout& L, TileGeom g, const FieldParams& fp) {
+    const size_t smem = R1csSmem<N>::bytes;
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(k_r1cs_check<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_r1cs_check<N>, kR1csThreads, smem);
+        if (per_sm < 1) per_sm = 1;
+        if (const char* e = getenv("ZKB_R1CS_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
+        if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: k_r1cs_check<%d>: %d CTAs/SM, %zu B of shared memory per CTA\n", N, per_sm, smem);
+    }
+    unsigned grid = grid_for((L.n_slices * 32) << g.log2_wt, c->sm_count, per_sm);
+    // a thread keeps its assignment lane from row to row: the grid stride must be a multiple of the tile width
+    const unsigned m = std::max(1u, (1u << g.log2_wt) / kR1csThreads);
+    grid = std::max(m, grid / m * m);
+    k_r1cs_check<N><<<grid, kR1csThreads, smem, c->stream>>>(L.d_slices, L.d_terms, L.d_row_ids, r->d_coefs, r->d_z, r->n_rows, L.n_slices,
+                                                             r->d_first_fail, g, fp);
 }
 
 static unsigned grid_for(uint64_t total, int sm_count, int per_sm) {
@@ -255,7 +365,7 @@ extern "C" int zkb_r1cs_load(zkb_ctx* c, const zkb_csr* A, const zkb_csr* B, con
     if (A->n_rows != B->n_rows || A->n_rows != C->n_rows) return c->fail(ZKB_E_ARG, "A, B, C must have the same number of rows");
     if (A->n_rows >= 0xFFFFFFE0ull) return c->fail(ZKB_E_UNSUPPORTED, "zkb: more than 2^32 rows");
     if (n_vars == 0 || n_vars >= 0xFFFFFFFFull) return c->fail(ZKB_E_ARG, "n_vars out of range");
-    if (n_coefs >= T_ONE) return c->fail(ZKB_E_ARG, "coefficient table too large");
+    if (n_coefs >= TD_ONE) return c->fail(ZKB_E_ARG, "coefficient table too large (2^30 - 2 entries at most)");
     if (c->has_gpu) CUDA_TRY(c, cudaSetDevice(c->device));
     r1cs_free(c);
     R1csDev* r = new R1csDev();
@@ -347,6 +457,9 @@ static int build_layout(zkb_ctx* c, R1csDev* r, int kind) {
         uint32_t k[6] = {0, 0, 0, 0, 0, 0};
         for (uint64_t i = s * 32; i < std::min(nr, s * 32 + 32); i++)
             for (int q = 0; q < 6; q++) k[q] = std::max(k[q], cls_cnt[(size_t)order[i] * 6 + q]);
+        if (c->has_gpu)  // the device stream marks the end of A_r, B_r, C_r on a term: every matrix owns at least one group
+            for (int m = 0; m < 3; m++)
+                if (k[2 * m] + k[2 * m + 1] == 0) k[2 * m + 1] = 1;
         slices[s] = make_uint4((uint32_t)n_groups, k[0] | (k[1] << 16), k[2] | (k[3] << 16), k[4] | (k[5] << 16));
         for (int q = 0; q < 6; q++) n_groups += k[q];
         if (n_groups >= (1ull << 32) / 32) return c->fail(ZKB_E_UNSUPPORTED, "zkb: R1CS too large for the sliced layout");
@@ -378,6 +491,19 @@ static int build_layout(zkb_ctx* c, R1csDev* r, int kind) {
         L.h_terms = std::move(terms);
         L.h_row_ids = std::move(order);
         return ZKB_OK;
+    }
+    // device tags: 30-bit payload + end-of-A / end-of-B / end-of-C marker on the last group of each matrix
+    for (uint64_t s = 0; s < n_slices; s++) {
+        const uint32_t kA = (slices[s].y & 0xFFFF) + (slices[s].y >> 16), kB = (slices[s].z & 0xFFFF) + (slices[s].z >> 16),
+                       kC = (slices[s].w & 0xFFFF) + (slices[s].w >> 16);
+        const uint64_t g0 = slices[s].x;
+        for (uint64_t gi = g0; gi < g0 + kA + kB + kC; gi++) {
+            const uint32_t mark = gi == g0 + kA - 1 ? M_END_A : gi == g0 + kA + kB - 1 ? M_END_B : gi == g0 + kA + kB + kC - 1 ? M_END_C : 0;
+            for (int l = 0; l < 32; l++) {
+                uint32_t& t = terms[gi * 32 + l].y;
+                t = (t == T_PAD ? TD_PAD : t == T_ONE ? TD_ONE : t) | (mark << 30);
+            }
+        }
     }
     CUDA_TRY(c, cudaMalloc((void**)&L.d_slices, slices.size() * sizeof(uint4)));
     CUDA_TRY(c, cudaMalloc((void**)&L.d_terms, terms.size() * sizeof(uint2)));
@@ -497,9 +623,7 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
                                                                      c->d_unreduced, fp)));
         cudaEventRecord(c->tile_ev[2 * t], c->stream);
         const R1csLayout& L = r->layout[r->log2_wt < 5 ? 0 : 1];
-        grid = grid_for((L.n_slices * 32) << r->log2_wt, c->sm_count, 256);
-        DISPATCH_N(N, (k_r1cs_check<N><<<grid, 256, 0, c->stream>>>(L.d_slices, L.d_terms, L.d_row_ids, r->d_coefs, r->d_z, r->n_rows,
-                                                                    L.n_slices, r->d_first_fail, g, fp)));
+        DISPATCH_N(N, (launch_r1cs_check<N>(c, r, L, g, fp)));
         cudaEventRecord(c->tile_ev[2 * t + 1], c->stream);
         launches += 2;
     }
