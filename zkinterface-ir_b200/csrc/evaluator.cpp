@@ -624,6 +624,305 @@ struct zkb_evaluator {
         }
     }
 
+
+    // ---- flat relation messages, recorded in bulk straight from the FlatBuffers tables ----------------------------------
+    // A builder-produced flat relation is a run of messages of 100 000 simple gates.  For a window of such messages the
+    // serial gate loop (ingest_relation above, evaluator.rs:288-301) is replaced by three passes over the tables in place —
+    // no owned Gate structs — each spread over the parse threads, one message per task:
+    //   count   gate kinds per message (value handles, assertion and input-stream positions are prefix sums of these)
+    //   define  every value-defining gate writes its SSA row (kind, operand WIRE ids) and binds its output wire in the
+    //           scope table with a compare-and-swap: a wire that already has a value is a conflict
+    //   resolve operand wire ids -> value handles; an operand must have been bound by an EARLIER gate (smaller handle)
+    // Anything irregular — a structured gate, Copy, Free, a re-used or undefined wire, too few instance / witness values,
+    // a resource limit, a malformed table — makes the window fall back, untouched, to the serial path, which reports the
+    // error exactly where and how the reference does.  Regular windows give the state the serial path would give.
+    struct FlatCount {
+        uint64_t n_gates = 0, n_values = 0, n_asserts = 0, n_inst = 0, n_wit = 0, n_const_gates = 0, max_w0 = 0;
+        uint64_t by_type[ir::G_WITNESS + 1] = {0};
+        std::vector<std::pair<const uint8_t*, uint32_t>> consts;  // bytes of the constant-bearing gates, in order
+        ir::FlatRelationHead head;
+        bool ok = false;
+    };
+    struct FlatFill {
+        zkb_evaluator* ev;
+        uint32_t v, a, inst, wit, ci;  // running value handle / assertion index / stream cursors / constant-gate index
+        const uint32_t* cidx;          // pool index of this message's k-th constant-bearing gate
+        const uint32_t* inst_pos;
+        const uint32_t* wit_pos;
+        uint32_t v_lo, v_hi;           // undo pass: handles of the window being rolled back
+        bool conflict = false;
+    };
+    static bool flat_count_fn(void* ctx, const ir::FlatGate& g) {
+        FlatCount& k = *(FlatCount*)ctx;
+        k.n_gates++;
+        k.by_type[g.type]++;
+        if (g.type == ir::G_ASSERT_ZERO) {
+            k.n_asserts++;
+            return true;
+        }
+        k.n_values++;
+        if (g.w0 > k.max_w0) k.max_w0 = g.w0;
+        if (g.type == ir::G_INSTANCE) k.n_inst++;
+        else if (g.type == ir::G_WITNESS) k.n_wit++;
+        if (g.cbytes) k.consts.emplace_back(g.cbytes, g.clen);
+        return g.w0 < 0xFFFFFFFFull;  // operand wire ids are staged in the 32-bit operand columns
+    }
+    static bool flat_fill_fn(void* ctx, const ir::FlatGate& g) {
+        FlatFill& f = *(FlatFill*)ctx;
+        Program& p = f.ev->prog();
+        if (g.type == ir::G_ASSERT_ZERO) {
+            if (g.w0 >= 0xFFFFFFFFull) return !(f.conflict = true);
+            p.asserts[f.a++] = AssertRec{(uint32_t)g.w0, f.v, g.w0};  // value: the wire for now (resolved below)
+            return true;
+        }
+        uint8_t kind;
+        uint32_t a = 0, b = 0;
+        switch (g.type) {
+            case ir::G_CONSTANT: kind = V_CONST; b = f.cidx[f.ci++]; break;
+            case ir::G_ADD: kind = V_ADD; break;
+            case ir::G_MUL: kind = V_MUL; break;
+            case ir::G_AND: kind = V_AND; break;
+            case ir::G_XOR: kind = V_XOR; break;
+            case ir::G_NOT: kind = V_NOT; break;
+            case ir::G_ADD_CONSTANT: kind = V_ADDC; b = f.cidx[f.ci++]; break;
+            case ir::G_MUL_CONSTANT: kind = V_MULC; b = f.cidx[f.ci++]; break;
+            case ir::G_INSTANCE: kind = V_INSTANCE; b = f.inst_pos[f.inst++]; break;
+            default: kind = V_WITNESS; b = f.wit_pos[f.wit++]; break;
+        }
+        if (kind >= V_ADD) {
+            if (g.w1 >= 0xFFFFFFFFull || g.w2 >= 0xFFFFFFFFull) return !(f.conflict = true);
+            a = (uint32_t)g.w1;
+            if (kind == V_ADD || kind == V_MUL || kind == V_AND || kind == V_XOR) b = (uint32_t)g.w2;
+        }
+        p.kind[f.v] = kind;
+        p.opa[f.v] = a;
+        p.opb[f.v] = b;
+        uint32_t expect = Scope::kNone;
+        if (!__atomic_compare_exchange_n(&f.ev->values.dense[g.w0], &expect, f.v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+            return !(f.conflict = true);  // "Wire_{id} already has a value in this scope."
+        f.v++;
+        return true;
+    }
+    static bool flat_undo_fn(void* ctx, const ir::FlatGate& g) {  // unbind the wires this window bound
+        FlatFill& f = *(FlatFill*)ctx;
+        if (g.type == ir::G_ASSERT_ZERO || g.w0 >= f.ev->values.dense.size()) return true;
+        uint32_t& d = f.ev->values.dense[g.w0];
+        if (d >= f.v_lo && d < f.v_hi) d = Scope::kNone;
+        return true;
+    }
+
+    template <class F>
+    static void parallel_for(size_t n, unsigned threads, F f) {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t i; (i = next.fetch_add(1)) < n;) f(i);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads && t < n; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+
+    // Returns how many messages, from w0 on, have been recorded (a prefix of the window: the leading run of flat relation
+    // messages).  0: nothing was changed; *serial_n then says how many leading messages the serial path should take before
+    // the bulk path is tried again (the leading run of other messages, or the whole window after an irregularity).
+    size_t ingest_flat_window(const uint8_t* buf, const std::vector<std::pair<size_t, size_t>>& msgs, size_t w0, size_t w1, unsigned threads,
+                              size_t* serial_n) {
+        Program& p = prog();
+        *serial_n = w1 - w0;
+        if (fatal || evaluated || has_error || p.keep_copies || p.expand_on || !values.sparse.empty() || getenv("ZKB_NO_FLAT_INGEST")) return 0;
+        size_t nm = w1 - w0;
+        static const bool timing = getenv("ZKB_TIMING") != nullptr;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_0 = now();
+        auto lap = [&](const char* what) {
+            if (!timing) return;
+            double t = now();
+            fprintf(stderr, "  flat window: %-8s %.4f s\n", what, t - t_0);
+            t_0 = t;
+        };
+        std::vector<FlatCount> cnt(nm);
+        parallel_for(nm, threads, [&](size_t i) {
+            std::string e;
+            cnt[i].ok = ir::walk_flat_relation(buf + msgs[w0 + i].first, msgs[w0 + i].second, cnt[i].head, flat_count_fn, &cnt[i], false, e) == ir::FLAT_OK;
+        });
+        lap("count");
+        {
+            size_t n_ok = 0;
+            while (n_ok < nm && cnt[n_ok].ok) n_ok++;
+            if (n_ok == 0) {  // the window starts with other messages (instance / witness values, structured relations)
+                size_t n_bad = 0;
+                while (n_bad < nm && !cnt[n_bad].ok) n_bad++;
+                *serial_n = n_bad;
+                return 0;
+            }
+            nm = n_ok;
+            w1 = w0 + nm;
+            cnt.resize(nm);
+        }
+        uint64_t tv = 0, ta = 0, ti = 0, tw = 0, tg = 0, max_w0 = 0;
+        for (auto& k : cnt) {
+            tv += k.n_values; ta += k.n_asserts; ti += k.n_inst; tw += k.n_wit; tg += k.n_gates;
+            max_w0 = std::max(max_w0, k.max_w0);
+        }
+        const uint64_t v0 = p.n_values(), a0 = p.asserts.size();
+        if (tv == 0 || v0 + tv >= c->max_values || steps + tg > c->max_steps || a0 + ta >= 0xFFFFFFF0ull) return 0;
+        if (ti > instance_queue.size() || tw > witness_queue.size()) return 0;  // the serial path reports where the stream runs dry
+        // the scope stays a dense table only while ids are within a small multiple of the values bound (context.h)
+        if (max_w0 >= Scope::kDenseLimit || max_w0 > 4 * (values.n_sets + tv + 1024)) return 0;
+        // header / field of every message, as ingest_relation does (:262-267); any change of field goes the serial way
+        for (auto& k : cnt) {
+            if (p.field_set && k.head.header.field_characteristic != p.modulus_le) return 0;
+            std::string e;
+            if (!p.set_field(k.head.header.field_characteristic.data(), k.head.header.field_characteristic.size(), k.head.header.field_degree, e))
+                return 0;
+        }
+        // ---- point of no return for the cheap part: constants are interned (harmless if the window falls back later)
+        std::vector<std::vector<uint32_t>> cidx(nm);
+        for (size_t i = 0; i < nm; i++) {
+            cidx[i].reserve(cnt[i].consts.size());
+            for (auto& cb : cnt[i].consts) cidx[i].push_back(p.intern_const(cb.first, cb.second));
+        }
+        std::vector<uint32_t> inst_pos(instance_queue.begin(), instance_queue.begin() + ti), wit_pos(witness_queue.begin(), witness_queue.begin() + tw);
+        // Room for the whole buffer at once, sized from its length (a flat gate takes >= 56 bytes of tables), with the fresh
+        // pages touched by all threads: growing 9 bytes per value window by window would copy the columns again and again
+        // and take every page fault on this thread.
+        const uint64_t est = v0 + std::max<uint64_t>(tv, (msgs.back().first + msgs.back().second - msgs[w0].first) / 56);
+        if (p.kind.capacity() < v0 + tv) {
+            p.kind.reserve(est);
+            p.opa.reserve(est);
+            p.opb.reserve(est);
+            const uint64_t a_est = a0 + std::max<uint64_t>(ta, (est - v0) * (ta + 1) / (tv + 1) * 5 / 4);
+            p.asserts.reserve(a_est);
+            struct Span { uint8_t* lo; uint8_t* hi; };
+            const Span spans[4] = {{(uint8_t*)p.kind.data() + v0, (uint8_t*)p.kind.data() + p.kind.capacity()},
+                                   {(uint8_t*)(p.opa.data() + v0), (uint8_t*)(p.opa.data() + p.opa.capacity())},
+                                   {(uint8_t*)(p.opb.data() + v0), (uint8_t*)(p.opb.data() + p.opb.capacity())},
+                                   {(uint8_t*)(p.asserts.data() + a0), (uint8_t*)(p.asserts.data() + p.asserts.capacity())}};
+            constexpr size_t kChunk = 4u << 20;
+            std::vector<std::pair<uint8_t*, uint8_t*>> chunks;
+            for (const Span& sp : spans)
+                for (uint8_t* q = sp.lo; q < sp.hi; q += kChunk) chunks.emplace_back(q, std::min(sp.hi, q + kChunk));
+            parallel_for(chunks.size(), threads, [&](size_t i) {
+                for (volatile uint8_t* q = chunks[i].first; q < chunks[i].second; q += 4096) *q = 0;  // capacity beyond size(): ours, unread
+            });
+        }
+        p.kind.resize(v0 + tv);
+        p.opa.resize(v0 + tv);
+        p.opb.resize(v0 + tv);
+        p.asserts.resize(a0 + ta);
+        const size_t dense0 = values.dense.size();
+        if (max_w0 >= values.dense.size()) {
+            // wires of a flat relation are numbered as they are defined: the table the rest of the buffer needs, in one step
+            uint64_t want = std::max<uint64_t>(max_w0 + 1, std::min<uint64_t>(values.n_sets + (est - v0), 4 * (values.n_sets + tv + 1024)));
+            size_t n = values.dense.size() ? values.dense.size() : 16;
+            while (n < want) n *= 2;
+            const size_t old = values.dense.size();
+            values.dense.reserve(n);
+            constexpr size_t kChunk = 1u << 20;  // entries
+            const size_t nch = (n - old + kChunk - 1) / kChunk;
+            uint32_t* d = values.dense.data();
+            parallel_for(nch, threads, [&](size_t i) {  // first touch + fill by all threads; resize() below then runs over resident pages
+                const size_t lo = old + i * kChunk, hi = std::min(n, lo + kChunk);
+                for (size_t k = lo; k < hi; k++) ((volatile uint32_t*)d)[k] = Scope::kNone;
+            });
+            values.dense.resize(n, Scope::kNone);
+        }
+        std::vector<FlatFill> fill(nm);
+        {
+            uint64_t v = v0, a = a0, ii = 0, ww = 0;
+            for (size_t i = 0; i < nm; i++) {
+                fill[i] = FlatFill{this, (uint32_t)v, (uint32_t)a, 0, 0, 0, cidx[i].data(), inst_pos.data() + ii, wit_pos.data() + ww,
+                                   (uint32_t)v0, (uint32_t)(v0 + tv), false};
+                v += cnt[i].n_values; a += cnt[i].n_asserts; ii += cnt[i].n_inst; ww += cnt[i].n_wit;
+            }
+        }
+        lap("prepare");
+        std::atomic<bool> bad{false};
+        parallel_for(nm, threads, [&](size_t i) {
+            std::string e;
+            ir::FlatRelationHead h;
+            int rc = ir::walk_flat_relation(buf + msgs[w0 + i].first, msgs[w0 + i].second, h, flat_fill_fn, &fill[i], true, e);
+            if (rc != ir::FLAT_OK || fill[i].conflict) bad = true;
+        });
+        lap("define");
+        // resolve: operand wires -> handles of values bound EARLIER in program order
+        if (!bad) {
+            const uint32_t* dense = values.dense.data();
+            const size_t dn = values.dense.size();
+            const size_t chunks = (tv + 65535) / 65536, achunks = (ta + 65535) / 65536;
+            parallel_for(chunks + achunks, threads, [&](size_t ch) {
+                if (ch < chunks) {
+                    const uint64_t lo = v0 + ch * 65536, hi = std::min<uint64_t>(v0 + tv, lo + 65536);
+                    for (uint64_t v = lo; v < hi; v++) {
+                        const uint8_t k = p.kind[v];
+                        if (k < V_ADD) continue;
+                        const uint32_t wa = p.opa[v];
+                        const uint32_t ra = wa < dn ? dense[wa] : Scope::kNone;
+                        if (ra >= v) { bad = true; return; }  // undefined (kNone) or bound later: "No value given for wire_{id}"
+                        p.opa[v] = ra;
+                        if (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR) {
+                            const uint32_t wb = p.opb[v];
+                            const uint32_t rb = wb < dn ? dense[wb] : Scope::kNone;
+                            if (rb >= v) { bad = true; return; }
+                            p.opb[v] = rb;
+                        }
+                    }
+                } else {
+                    const uint64_t lo = a0 + (ch - chunks) * 65536, hi = std::min<uint64_t>(a0 + ta, lo + 65536);
+                    for (uint64_t a = lo; a < hi; a++) {
+                        AssertRec& r = p.asserts[a];
+                        const uint32_t rv = r.value < dn ? dense[r.value] : Scope::kNone;
+                        if (rv >= r.pos) { bad = true; return; }
+                        r.value = rv;
+                    }
+                }
+            });
+        }
+        lap("resolve");
+        if (bad) {  // undo: the window is replayed gate by gate by the serial path
+            parallel_for(nm, threads, [&](size_t i) {
+                std::string e;
+                ir::FlatRelationHead h;
+                ir::walk_flat_relation(buf + msgs[w0 + i].first, msgs[w0 + i].second, h, flat_undo_fn, &fill[i], false, e);
+            });
+            (void)dense0;  // a grown table stays grown: kNone entries are indistinguishable from absent ones
+            p.kind.resize(v0);
+            p.opa.resize(v0);
+            p.opb.resize(v0);
+            p.asserts.resize(a0);
+            return 0;
+        }
+        // commit the bookkeeping the serial loop does gate by gate
+        for (auto& k : cnt) {
+            modulus_le = k.head.header.field_characteristic;
+            is_boolean = (k.head.gate_mask & ir::M_BOOL) == ir::M_BOOL;
+            if (k.n_gates) verified_at_least_one_gate = true;
+            p.cb_count[CB_CONSTANT] += k.by_type[ir::G_CONSTANT];
+            p.cb_count[CB_ADD] += k.by_type[ir::G_ADD];
+            p.cb_count[CB_MUL] += k.by_type[ir::G_MUL];
+            p.cb_count[CB_ADDC] += k.by_type[ir::G_ADD_CONSTANT];
+            p.cb_count[CB_MULC] += k.by_type[ir::G_MUL_CONSTANT];
+            p.cb_count[CB_AND] += k.by_type[ir::G_AND];
+            p.cb_count[CB_XOR] += k.by_type[ir::G_XOR];
+            p.cb_count[CB_NOT] += k.by_type[ir::G_NOT];
+            p.cb_count[CB_INSTANCE] += k.by_type[ir::G_INSTANCE];
+            p.cb_count[CB_WITNESS] += k.by_type[ir::G_WITNESS];
+            p.cb_count[CB_COPY] += k.by_type[ir::G_ASSERT_ZERO];  // an unweighted assertion tests a copy (:355)
+            p.cb_count[CB_ASSERT_ZERO] += k.by_type[ir::G_ASSERT_ZERO];
+            p.ir_gates += k.n_gates - k.by_type[ir::G_CONSTANT] - k.by_type[ir::G_INSTANCE] - k.by_type[ir::G_WITNESS];
+        }
+        c->is_boolean = is_boolean;
+        steps += tg;
+        values.n_sets += tv;
+        values.live += tv;
+        for (uint64_t k = 0; k < ti; k++) p.n_instance = std::max(p.n_instance, inst_pos[k] + 1);
+        for (uint64_t k = 0; k < tw; k++) p.n_witness = std::max(p.n_witness, wit_pos[k] + 1);
+        instance_queue.erase(instance_queue.begin(), instance_queue.begin() + ti);
+        witness_queue.erase(witness_queue.begin(), witness_queue.begin() + tw);
+        return nm;
+    }
+
     // Evaluator::ingest_message, :213-230: errors latch, later messages are skipped
     int ingest_parsed(ir::Message& m) {
         if (fatal) return fail(ZKB_E_FATAL, err);
@@ -1079,19 +1378,32 @@ extern "C" int zkb_evaluator_ingest_buffer(zkb_evaluator* ev, const uint8_t* buf
     std::vector<std::pair<size_t, size_t>> msgs;
     ir::split_messages(buf, len, msgs);
     const unsigned T = parse_threads();
-    if (T < 2 || msgs.size() < 2 || len < ((size_t)1 << 20)) {
+    static const size_t min_bytes = getenv("ZKB_PARALLEL_INGEST_MIN_BYTES") ? (size_t)atoll(getenv("ZKB_PARALLEL_INGEST_MIN_BYTES")) : ((size_t)1 << 20);
+    if (T < 2 || msgs.size() < 2 || len < min_bytes) {
         for (auto& m : msgs) {
             int rc = ev->ingest_bytes(buf + m.first, m.second);
             if (rc != ZKB_OK) return rc;
         }
         return ZKB_OK;
     }
-    const size_t window = (size_t)T * 2;
+    const size_t window = (size_t)T * 4;
     double t_parse = 0, t_ing = 0;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    for (size_t w0 = 0; w0 < msgs.size(); w0 += window) {
+    double t_flat = 0;
+    size_t n_flat = 0;
+    for (size_t w0 = 0, next_w0 = 0; w0 < msgs.size(); w0 = next_w0) {
         double ta = now();
-        const size_t w1 = std::min(msgs.size(), w0 + window);
+        size_t w1 = std::min(msgs.size(), w0 + window);
+        size_t serial_n = 0;
+        const size_t done = ev->ingest_flat_window(buf, msgs, w0, w1, T, &serial_n);  // flat relation messages: from the tables in place
+        if (done) {
+            t_flat += now() - ta;
+            n_flat += done;
+            next_w0 = w0 + done;
+            continue;
+        }
+        w1 = w0 + serial_n;
+        next_w0 = w1;
         std::vector<ir::Message> parsed(w1 - w0);
         std::vector<std::string> errs(w1 - w0);
         std::vector<char> ok(w1 - w0, 0);
@@ -1117,7 +1429,7 @@ extern "C" int zkb_evaluator_ingest_buffer(zkb_evaluator* ev, const uint8_t* buf
         }
         t_ing += now() - tb;
     }
-    if (getenv("ZKB_TIMING")) fprintf(stderr, "parse %.3f s ingest %.3f s\n", t_parse, t_ing);
+    if (getenv("ZKB_TIMING")) fprintf(stderr, "flat windows %.3f s (%zu of %zu messages), parse %.3f s ingest %.3f s\n", t_flat, n_flat, msgs.size(), t_parse, t_ing);
     return ZKB_OK;
 }
 

@@ -441,6 +441,65 @@ void split_messages(const uint8_t* buf, size_t len, std::vector<std::pair<size_t
     }
 }
 
+// Flat view of a relation message: the same tables read_message decodes, visited in place (structs/gates.rs:60-259 without
+// the owned `Gate` values).  Every access is bounds-checked like in read_message.
+int walk_flat_relation(const uint8_t* buf, size_t len, FlatRelationHead& head, FlatGateFn fn, void* ctx, bool wires, std::string& err) {
+    try {
+        if (len < 12) return FLAT_OTHER;
+        Buf b{buf, len};
+        Table root(&b, 4 + (size_t)b.u32(4));
+        if (root.u8(4) != MSG_RELATION) return FLAT_OTHER;
+        Table m = root.table(6);
+        if (!m || !m.has(12)) return FLAT_OTHER;      // the owned-struct reader produces the reference's error text
+        size_t at; uint32_t n;
+        if (m.vec(10, at, n) && n != 0) return FLAT_OTHER;  // functions
+        read_header(m.table(4), head.header);
+        std::string gs, ft;
+        if (!m.string(6, gs) || !m.string(8, ft)) return FLAT_OTHER;
+        if (!parse_gate_set(gs, head.gate_mask, err) || !parse_feature_toggle(ft, head.feat_mask, err)) return FLAT_OTHER;
+        if (!m.vec(12, at, n)) return FLAT_OTHER;
+        head.n_gates = n;
+        FlatGate g;
+        for (uint32_t i = 0; i < n; i++) {
+            Table d = m.vec_at(at, i);
+            const uint8_t ty = d.u8(4);
+            if (ty < G_CONSTANT || ty > G_WITNESS || ty == G_COPY) return FLAT_OTHER;  // Copy aliases, Free re-uses ids, the rest is structured
+            Table t = d.table(6);
+            if (!t) return FLAT_OTHER;
+            g.type = ty;
+            g.cbytes = nullptr;
+            g.clen = 0;
+            g.w1 = g.w2 = 0;
+            Table w = t.table(4);
+            if (!w) return FLAT_OTHER;
+            g.w0 = w.u64(4);
+            if (ty == G_CONSTANT || ty == G_ADD_CONSTANT || ty == G_MUL_CONSTANT) {
+                const int slot = ty == G_CONSTANT ? 6 : 8;
+                if (!t.has(slot)) return FLAT_OTHER;
+                size_t cat = t.indirect(slot);
+                uint32_t clen = b.u32(cat);
+                b.need(cat + 4, clen);
+                g.cbytes = b.p + cat + 4;
+                g.clen = clen;
+            }
+            if (wires && ty != G_CONSTANT && ty != G_ASSERT_ZERO && ty != G_INSTANCE && ty != G_WITNESS) {
+                Table w1 = t.table(6);
+                if (!w1) return FLAT_OTHER;
+                g.w1 = w1.u64(4);
+                if (ty == G_ADD || ty == G_MUL || ty == G_AND || ty == G_XOR) {
+                    Table w2 = t.table(8);
+                    if (!w2) return FLAT_OTHER;
+                    g.w2 = w2.u64(4);
+                }
+            }
+            if (!fn(ctx, g)) return FLAT_STOPPED;
+        }
+        return FLAT_OK;
+    } catch (const ParseError&) {
+        return FLAT_OTHER;  // malformed: read_message reports it with the reference's wording when the message is reached
+    }
+}
+
 bool read_message(const uint8_t* buf, size_t len, Message& out, std::string& err) {
     try {
         REQ(len >= 12, "malformed FlatBuffers message (too short)");

@@ -117,6 +117,27 @@ struct Message {
 // Returns false and sets err (the reference's "Missing ..." texts) on malformed input.
 bool read_message(const uint8_t* buf, size_t len, Message& out, std::string& err);
 
+// A relation message made of simple, value-defining gates only (what a GateBuilder emits for a flat circuit: one message
+// per 100 000 gates) can be visited IN PLACE, without owned structs: head = header / gate set / features, fn is called once
+// per top-level gate with the wire ids (and, for Constant / AddConstant / MulConstant, a pointer to the constant's bytes
+// inside buf).  wires = false skips the input-wire tables (a counting pass).  Returns FLAT_OK, FLAT_STOPPED (fn returned
+// false) or FLAT_OTHER: anything else — another message type, functions, a structured gate, Copy, Free, or a malformed
+// table — is left to read_message, which also produces the reference's error texts.
+struct FlatRelationHead {
+    Header header;
+    uint16_t gate_mask = 0, feat_mask = 0;
+    uint32_t n_gates = 0;
+};
+struct FlatGate {
+    uint8_t type;
+    uint64_t w0, w1, w2;
+    const uint8_t* cbytes;
+    uint32_t clen;
+};
+typedef bool (*FlatGateFn)(void* ctx, const FlatGate& g);
+enum { FLAT_OK = 0, FLAT_STOPPED = 1, FLAT_OTHER = 2 };
+int walk_flat_relation(const uint8_t* buf, size_t len, FlatRelationHead& head, FlatGateFn fn, void* ctx, bool wires, std::string& err);
+
 // Size-prefixed framing, consumers/utils.rs:6-41: offsets/lengths of the messages in a stream.
 // A message running past the end of the buffer stops the split (the reference's read_exact fails).
 void split_messages(const uint8_t* buf, size_t len, std::vector<std::pair<size_t, size_t>>& out);
