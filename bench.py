@@ -346,7 +346,10 @@ def main():
     algo_bytes_step = st["algo_bytes_per_witness"] * n_local            # this rank
     lv_ms_step = lv_ms / args.steps
     achieved = algo_bytes_step / (lv_ms_step * 1e-3) / 1e9 if lv_ms_step > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_level_pipe<8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # launch_level's rule (csrc/kernels.cu): full 256-lane tiles of an 8-limb field take the bulk-copy ring kernel
+    tma = eb == 32 and st["tile_witnesses"] == 256 and os.environ.get("ZKB_LEVEL_TMA", "1") != "0"
+    kernel_name = "k_level_tma<8>" if tma else f"k_level_pipe<{max(1, eb // 4)}>"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes_step / max(level_launches, 1),
                 "avg_launch_ms": lv_ms_step / max(level_launches, 1), "launches_per_step": level_launches,
@@ -354,13 +357,14 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            ratio = json.load(open(prof))["traffic_over_algorithmic"]
+            tj = json.load(open(prof))
+            ratio = tj["traffic_over_algorithmic"]
             roofline["traffic"] = ratio * roofline["algorithmic_bytes_per_launch"]
-            roofline["traffic_source"] = ("profiles/traffic.json: dram__bytes_read+write of 3 captured k_level launches = "
-                                          f"{ratio:.3f} x their algorithmic bytes, scaled to the average launch")
+            roofline["traffic_source"] = (f"profiles/traffic.json ({tj.get('capture', '?')}): dram__bytes_read+write of 3 captured "
+                                          f"level launches = {ratio:.3f} x their algorithmic bytes, scaled to the average launch")
             roofline["dram_frac"] = roofline["frac"] * ratio
             roofline["note"] = ("frac counts ALGORITHMIC bytes (3E per two-input gate, E per assertion) and can exceed 1: "
-                                f"{(1 - ratio) * 100:.1f} % of them never reach DRAM (operands shared inside a wavefront hit L2, "
+                                f"{(1 - ratio) * 100:.1f} % of them never reach DRAM (operands read twice inside a wavefront hit L2, "
                                 "fused-assert-only values are not stored); dram_frac = measured DRAM traffic / copy peak")
         except Exception:
             pass

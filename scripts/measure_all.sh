@@ -13,7 +13,7 @@ python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 python bench.py --witnesses 256 --steps 1 --warmup 1 --no-cpu-baseline --no-value-check > $out/${tag}_plain256.json 2>/dev/null && {
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
       python bench.py --witnesses 256 --steps 1 --warmup 1 --no-cpu-baseline --no-value-check > $out/${tag}_ncu_list.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:k_level_pipe -s 20 -c 3 -o $out/${tag}_prof_level \
+  ncu --set full --clock-control none --import-source on -k regex:k_level_tma -s 20 -c 3 -o $out/${tag}_prof_level \
       python bench.py --witnesses 256 --steps 1 --warmup 1 --no-cpu-baseline --no-value-check > $out/${tag}_ncu_full.log 2>&1
 }
 # secondary configs (parity checked in the same run) and the R1CS kernel capture

@@ -202,6 +202,8 @@ if __name__ == "__main__":
         print(json.dumps(c4(14 if a.small else 18, 12 if a.small else 16, 64)), flush=True)
     if "c3s" in todo:
         print(json.dumps(c3_sieve(14 if a.small else 22)), flush=True)
+    if "c3s24" in todo:      # the headline relation as a statement: 168 messages of 100 000 gates
+        print(json.dumps(c3_sieve(14 if a.small else 24)), flush=True)
     if "c5" in todo:
         print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 1)), flush=True)
         print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 64)), flush=True)

@@ -262,3 +262,27 @@ def test_narrow_fields_packed_lanes(name, n_batch):
         exp = c.expected_first_fail(circ, n_batch, corrupt)
         for j in range(n_batch):
             assert (int(v[j]["first_fail_seq"]) if not v[j]["ok"] else -1) == exp[j]
+
+
+@pytest.mark.parametrize("tma", ["1", "0"])
+@pytest.mark.parametrize("name,tile_log2", [("bls381", "8"), ("p256full", "8"), ("bls381", "9"), ("bn254", "10")])
+def test_full_tiles_bulk_copy_ring_and_vector_loads(name, tile_log2, tma, monkeypatch):
+    """Tiles of >= 256 lanes of an 8-limb field run k_level_tma (operand rows through cp.async.bulk + an mbarrier ring);
+    ZKB_LEVEL_TMA=0 keeps them on k_level_pipe.  Full tiles and a ragged last one (lanes past the batch are masked), every
+    arithmetic gate kind (constants are not bulk-copied), wire re-use, failing witnesses in each tile; wavefronts with more
+    gates than the ring has stages and with fewer."""
+    monkeypatch.setenv("ZKB_LEVEL_TMA", tma)
+    monkeypatch.setenv("ZKB_TILE_LOG2", tile_log2)
+    c = circuits()
+    p = FIELDS[name]
+    n_batch = 256 * 2 + 45
+    circ = c.random_circuit(2500, 40, p, seed=77, n_tracked=5)
+    corrupt = {0: 0, 255: 2, 256: 4, 511: 1, 512: 3, n_batch - 1: 0}
+    w = c.make_witnesses(circ, n_batch, seed=8, corrupt=corrupt)
+    v, _, st = _check(c, circ.gates, circ.const_pool, p, None, w, n_batch, circ.n_wires, sample=(1, 254, 257, 510, 513, n_batch - 2))
+    assert st["tile_witnesses"] == 1 << int(tile_log2)
+    gates, pool, n_wires = random_flat_program(p, 900, 4, 6, seed=5, bool_ops=False)
+    rng = np.random.default_rng(12)
+    inst = c.random_field_elements(rng, (4,), p)
+    wit = c.random_field_elements(rng, (n_batch, 6), p)
+    _check(c, gates, pool, p, inst, wit, n_batch, n_wires, sample=(0, 255, 256, n_batch - 1))

@@ -115,6 +115,12 @@ extern "C" zkb_ctx* zkb_create(int device) {
     }
     c->sm_count = prop.multiProcessorCount;
     c->coop_supported = prop.cooperativeLaunch != 0;
+    if (const char* g = getenv("ZKB_L2_FETCH_GRANULARITY")) {  // experiment knob (32 / 64 / 128): DRAM bytes fetched per L2 miss
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        size_t got = 0;
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: L2 fetch granularity %zu B\n", got);
+    }
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         c->err = std::string("zkb_create: ") + cudaGetErrorString(e);

@@ -303,6 +303,149 @@ k_level_pipe(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_level_tma: the same wavefront step with the operand rows brought in by the bulk-copy engine (cp.async.bulk, 1-D TMA)
+// instead of per-thread vector loads.  In the witness-minor layout a gate's operand for a block of 256 lanes is two
+// contiguous 4 KB pieces (N = 8: one per 16-byte chunk row; adjacent, i.e. one 8 KB block, when the tile is 256 lanes
+// wide), so a CTA <-> one (gate, lane block) per iteration: one elected thread arms an mbarrier with the byte count and
+// issues the bulk copies into a ring of STAGES shared-memory stages, STAGES items ahead; all 256 threads wait on the
+// stage's mbarrier, take their two 16-byte chunks per operand from shared memory (conflict-free: consecutive lanes,
+// consecutive 16-byte words), and the stage is handed back after one block barrier.  Results leave with plain 16-byte
+// vector stores (each warp writes 512 contiguous bytes already).
+// For 8-limb fields and tiles of >= 256 lanes (the headline configuration); everything else runs k_level_pipe.
+// Measured on the headline shape (scripts/ab_level_tma*.sh, profiles/r02g_ab_level_tma*.log): 73.4-74.2 G gate-evals/s against
+// 69.3-69.6 for k_level_pipe on the same box, i.e. 1.01-1.02 x the measured copy peak; bulk STORES of the results through shared memory on top changed
+// nothing (77.6 vs 77.4 on one box, scripts/ab_level_tma3.sh at commit time) and were dropped.  ZKB_LEVEL_TMA=0 switches back to k_level_pipe.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef ZKB_TMA_STAGES
+#define ZKB_TMA_STAGES 3
+#endif
+#ifndef ZKB_TMA_MIN_CTAS
+#define ZKB_TMA_MIN_CTAS 4
+#endif
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+constexpr size_t kTmaSmemBytes = (size_t)ZKB_TMA_STAGES * 16384;
+
+template <int N>
+__global__ void __launch_bounds__(256, ZKB_TMA_MIN_CTAS)
+k_level_tma(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
+            const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail, TileGeom g, FieldParams fp) {
+    static_assert(N == 8, "two 16-byte chunks per element");
+    constexpr int S = ZKB_TMA_STAGES;
+    constexpr uint32_t ELEM = 8192, STAGE = 2 * ELEM;
+    extern __shared__ __align__(128) uint8_t tma_smem[];
+    __shared__ __align__(8) uint64_t full_bar[S];
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(tma_smem);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(full_bar);
+    const uint4* dptr = reinterpret_cast<const uint4*>(ops);
+    const uint8_t* store_b = reinterpret_cast<const uint8_t*>(store);
+    // item = (gate, block of 256 lanes): a tile of 2^log2_wt lanes holds 2^(log2_wt - 8) blocks; the two 16-byte chunks of an
+    // element are rows of 16 << log2_wt bytes, 4 KB of each belong to a block (adjacent when the tile IS one block)
+    const uint32_t log2_q = g.log2_wt - 8;
+    const uint32_t q_mask = (1u << log2_q) - 1;
+    const uint64_t n_items = n_ops << log2_q;
+    const uint32_t row = 4096u << log2_q;  // bytes between the chunk rows of one element
+    const uint64_t stride = gridDim.x;
+    uint64_t gi = blockIdx.x;
+    if (gi >= n_items) return;
+    auto issue = [&](uint32_t stage, const uint4& d, uint32_t q) {  // elected thread: arm the stage's barrier, start the copies
+        const uint32_t opc = d.w & 0xff;
+        const bool two = !(opc == D_ADDC || opc == D_MULC);
+        const uint32_t bar = bar0 + stage * 8;
+        mbar_expect_tx(bar, two ? STAGE : ELEM);
+        const uint8_t* pa = store_b + (size_t)d.x * 2 * row + (size_t)q * 4096;
+        bulk_g2s(smem0 + stage * STAGE, pa, 4096, bar);
+        bulk_g2s(smem0 + stage * STAGE + 4096, pa + row, 4096, bar);
+        if (two) {
+            const uint8_t* pb = store_b + (size_t)d.y * 2 * row + (size_t)q * 4096;
+            bulk_g2s(smem0 + stage * STAGE + ELEM, pb, 4096, bar);
+            bulk_g2s(smem0 + stage * STAGE + ELEM + 4096, pb + row, 4096, bar);
+        }
+    };
+    uint64_t gp = gi;  // producer cursor (thread 0): next gate to request
+    uint4 dp = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < S; i++) mbar_init(bar0 + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            if (gp < n_items) issue(i, __ldg(dptr + (gp >> log2_q)), (uint32_t)gp & q_mask);
+            gp += stride;
+        }
+        if (gp < n_items) dp = __ldg(dptr + (gp >> log2_q));
+    }
+    __syncthreads();
+    uint4 d0 = __ldg(dptr + (gi >> log2_q));
+    for (uint32_t it = 0;; it++) {
+        const uint64_t gn = gi + stride;
+        uint4 d1 = make_uint4(0, 0, 0, 0);
+        if (gn < n_items) d1 = __ldg(dptr + (gn >> log2_q));
+        const uint32_t lane = (((uint32_t)gi & q_mask) << 8) + threadIdx.x;
+        const uint32_t stage = it % S, parity = (it / S) & 1;
+        const uint32_t opc = d0.w & 0xff;
+        uint32_t a[N], b[N], r[N];
+        mbar_wait(bar0 + stage * 8, parity);
+        const uint32_t sa = smem0 + stage * STAGE + threadIdx.x * 16;
+        unpack(lds128(sa), a);
+        unpack(lds128(sa + 4096), a + 4);
+        if (opc == D_ADDC || opc == D_MULC) {
+#pragma unroll
+            for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)d0.y * N + k);
+        } else {
+            unpack(lds128(sa + ELEM), b);
+            unpack(lds128(sa + ELEM + 4096), b + 4);
+        }
+        __syncthreads();  // every thread holds its limbs: the stage can be refilled
+        if (threadIdx.x == 0) {
+            if (gp < n_items) {
+                issue(stage, dp, (uint32_t)gp & q_mask);
+                gp += stride;
+                if (gp < n_items) dp = __ldg(dptr + (gp >> log2_q));
+            }
+        }
+        if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
+        else fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
+        if (!(d0.w & F_NOSTORE)) store_elem<N>(store, d0.z, lane, g.log2_wt, r);
+        if (d0.w & F_ASSERT) {
+            const uint32_t seq = __ldg(aseq + (gi >> log2_q));
+            bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
+            report_fail(fail, seq, first_fail, g.batch0 + lane, false);
+        }
+        if (gn >= n_items) break;
+        d0 = d1;
+        gi = gn;
+    }
+}
+
 // All wavefronts in ONE cooperative launch, a grid barrier between levels.  For programs whose levels are
 // too small to fill the chip (single-witness statements, deep narrow circuits) the per-level launch latency
 // (~4-5 us) dominates; a grid.sync() costs ~1-2 us.  Operands are read with ld.global.cg because they were
@@ -521,6 +664,12 @@ static bool level_pipe_enabled() {
     }
     return v != 0;
 }
+// full 256-lane tiles of an 8-limb field go through k_level_tma; ZKB_LEVEL_TMA=0 keeps them on k_level_pipe (read at every
+// launch so that one process can compare the two)
+static bool level_tma_enabled() {
+    const char* e = getenv("ZKB_LEVEL_TMA");
+    return e ? atoi(e) != 0 : true;
+}
 static int grid_per_sm(int dflt) {
     static int v = -1;
     if (v < 0) {
@@ -580,6 +729,16 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
             } else if (pack && nlimb == 1 && g.log2_wt >= 7) {
                 grid = grid_for(n_ops << (g.log2_wt - 2), sm_count, grid_per_sm(256));
                 k_level_pipe<1, 4><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp);
+            } else if (nlimb == 8 && g.log2_wt >= 8 && level_tma_enabled()) {
+                static int tma_per_sm = 0;
+                constexpr size_t smem = kTmaSmemBytes;
+                if (!tma_per_sm) {
+                    cudaFuncSetAttribute(k_level_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    const char* e = getenv("ZKB_TMA_GRID_PER_SM");
+                    tma_per_sm = e ? std::max(1, atoi(e)) : 128;
+                }
+                grid = grid_for(n_ops << g.log2_wt, sm_count, tma_per_sm);
+                k_level_tma<8><<<grid, 256, smem, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp);
             } else {
                 ZKB_DISPATCH_N(nlimb, (k_level_pipe<N, 1><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp)));
             }
