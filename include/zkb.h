@@ -318,6 +318,10 @@ int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops
 /* random 32-byte gathers (8 in flight per thread, L2-only loads) from a table of table_bytes: bytes gathered per second —
  * the ceiling of the one-assignment R1CS check, whose traffic is z[col] look-ups in a vector larger than L2 */
 int zkb_debug_gather_throughput(zkb_ctx* ctx, uint64_t table_bytes, uint32_t iters, double* bytes_per_second);
+/* microseconds per barrier of a kernel that only synchronises: kind 0 cooperative_groups' grid.sync(), 1 the counter barrier
+ * the all-levels kernel uses, 2 the hardware barrier of one 8-CTA cluster; blocks CTAs of 256 threads (0: one per SM).
+ * n_levels x this is the latency floor of a single-witness statement evaluated in one launch. */
+int zkb_debug_barrier_cost(zkb_ctx* ctx, int kind, uint32_t blocks, uint32_t n_barriers, double* us_per_barrier);
 /* Device layout of kind 0 (tiles of fewer than 32 assignments: ones and general terms in separate classes) or 1 (wider
  * tiles: one class per matrix, ones tagged inside it), host-only contexts: counts = {slices, term groups, rows}; slices: 4 x uint32 per slice
  * {first group, A ones | A general << 16, B ones | B general << 16, C ones | C general << 16} (group counts per term

@@ -68,7 +68,17 @@ def c2(log2_gates, window):
     tot, lv = timed_runs(b.run, b.timing)
     st = b.stats()
     algo = 8 * 3 * (circ.hist["add"] + circ.hist["mul"]) + 8 * circ.hist["assert_zero"] + 16 * st["n_device_ops"]
-    return {"config": f"C2 2^{log2_gates}-gate Goldilocks, 1 witness, operands {'windowed ' + str(window) if window else 'global'}",
+    # the latency floor of a one-launch evaluation is n_levels x the barrier between wavefronts,
+    # measured here with kernels that only synchronise, at the CTA count the all-levels launch uses (launch_coop_n's rule)
+    widest = max(b.level_info(l)["gates"] for l in range(st["n_levels"]))
+    cluster = widest <= 8 * 512 * 2
+    blocks = max(148, -(-(-(-widest // 256)) // 148) * 148)
+    bar = {"cooperative_groups_grid_sync_us": b.debug_barrier_cost(0, blocks), "counter_barrier_us": b.debug_barrier_cost(1, blocks),
+           "cluster_barrier_us": b.debug_barrier_cost(2), "ctas": 8 if cluster else blocks}
+    used = bar["cluster_barrier_us"] if cluster else bar["counter_barrier_us"]
+    return {"barrier": bar, "barrier_floor_ms": st["n_levels"] * used * 1e-3, "frac_of_barrier_floor": st["n_levels"] * used * 1e-3 / tot,
+            "widest_level_gates": widest,
+            "config": f"C2 2^{log2_gates}-gate Goldilocks, 1 witness, operands {'windowed ' + str(window) if window else 'global'}",
             "gates_per_s": circ.n_gates / (tot * 1e-3), "ms": tot, "levels": st["n_levels"], "us_per_level": tot * 1e3 / st["n_levels"],
             "algo_GBps_incl_descriptors": algo / (tot * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (tot * 1e-3) / 1e9 / PEAK,
             "prep_s": prep, "note": "L2-resident, launch/latency bound (one launch per wavefront)"}

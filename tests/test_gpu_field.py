@@ -40,3 +40,14 @@ def test_field_throughput_reports_sane_numbers():
     mul = b.debug_field_throughput(1, 500)
     add = b.debug_field_throughput(0, 500)
     assert mul > 1e10 and add > mul
+
+
+def test_barrier_cost_microbenchmark():
+    """the three barriers the all-levels kernel can use: cooperative_groups' grid.sync, the counter barrier, one cluster"""
+    z = zkb()
+    b = z.GpuBackend(0)
+    for kind in (0, 1, 2):
+        us = b.debug_barrier_cost(kind, 0, 50)
+        assert 0.0 < us < 200.0, (kind, us)
+    # the counter keeps counting across launches: a second measurement starts where the first ended
+    assert 0.0 < b.debug_barrier_cost(1, 296, 20) < 200.0

@@ -34,6 +34,7 @@ FIELDS = {
     "m31": (1 << 31) - 1,
     "goldilocks": (1 << 64) - (1 << 32) + 1,
     "p61": (1 << 61) - 1,
+    "p64full": (1 << 64) - 59,                           # largest 64-bit prime: one-limb (u64) Montgomery path, top bit set
     "kat124": 16249742125730185677094195492597105093,   # modulus of evaluator.rs:956
     "bn254": 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001,
     "bls381": 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,

@@ -76,7 +76,7 @@ EXPORTED = [
     "zkb_validator_ingest_buffer", "zkb_validator_ingest_paths", "zkb_validator_get_violations", "zkb_validator_violation",
     "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_metrics_create", "zkb_metrics_destroy", "zkb_metrics_ingest_message",
     "zkb_metrics_ingest_buffer", "zkb_metrics_ingest_paths", "zkb_metrics_json", "zkb_metrics_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
-    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_gather_throughput", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_plan_hash", "zkb_debug_write_flat_relation",
+    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_gather_throughput", "zkb_debug_barrier_cost", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_plan_hash", "zkb_debug_write_flat_relation",
     "zkb_comm_unique_id", "zkb_comm_init_rank", "zkb_comm_init", "zkb_comm_info", "zkb_comm_broadcast_program", "zkb_comm_evaluate",
     "zkb_comm_run", "zkb_evaluate_sharded", "zkb_run_sharded",
 ]
@@ -164,6 +164,7 @@ _sig("zkb_r1cs_run", _i, _vp, _vp)
 _sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
 _sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
 _sig("zkb_debug_gather_throughput", _i, _vp, _u64, _u32, C.POINTER(C.c_double))
+_sig("zkb_debug_barrier_cost", _i, _vp, _i, _u32, _u32, C.POINTER(C.c_double))
 _sig("zkb_debug_r1cs_layout", _i, _vp, _i, _u64p, _vp, _vp, _vp)
 _sig("zkb_debug_plan_hash", _i, _vp, _u64p)
 _sig("zkb_debug_rewrite_message", _i, _vp, _u8p, _sz, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
@@ -482,6 +483,13 @@ class GpuBackend:
         """bytes / s of random 32-byte gathers from a table of table_bytes (the R1CS check's ceiling)"""
         out = C.c_double()
         self._chk(_lib.zkb_debug_gather_throughput(self._c, table_bytes, iters, C.byref(out)))
+        return out.value
+
+    def debug_barrier_cost(self, kind: int, blocks: int = 0, n_barriers: int = 200) -> float:
+        """microseconds per barrier (0: cooperative_groups grid.sync, 1: the counter barrier of the all-levels kernel,
+        2: one 8-CTA cluster's hardware barrier) with `blocks` CTAs (0: one per SM)"""
+        out = C.c_double()
+        self._chk(_lib.zkb_debug_barrier_cost(self._c, kind, blocks, n_barriers, C.byref(out)))
         return out.value
 
     # ---- R1CS -----------------------------------------------------------------

@@ -128,6 +128,8 @@ extern "C" zkb_ctx* zkb_create(int device) {
     }
     for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev[i]);
     cudaMalloc((void**)&c->d_unreduced, sizeof(uint32_t));
+    cudaMalloc((void**)&c->d_barrier, sizeof(uint32_t));  // arrival counter of the grid barrier (kernels.cu: grid_barrier)
+    cudaMemset(c->d_barrier, 0, sizeof(uint32_t));
     c->has_gpu = true;
     return c;
 }
@@ -151,6 +153,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_first_fail);
         cudaFree(c->d_scratch_fail);
         cudaFree(c->d_unreduced);
+        cudaFree(c->d_barrier);
         cudaFree(c->d_tab_slot);
         cudaFree(c->d_tab_opb);
         cudaFree(c->d_tab_readable);
@@ -531,7 +534,7 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
             while (e < pl.n_levels && narrow[e] == narrow[l]) widest = std::max(widest, items(e++));
             cudaError_t err = launch_levels_coop(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off + l, e - l, c->d_store, c->d_consts, d_fail,
                                                  rawctx, g, p.fp, c->sm_count, narrow[l] ? widest : std::max(widest, kClusterItems + 1),
-                                                 c->stream);
+                                                 c->d_barrier, &c->barrier_epoch, c->stream);
             if (err != cudaSuccess) {
                 if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: cooperative launch failed: %s\n", cudaGetErrorString(err));
                 cudaGetLastError();          // not launchable cooperatively: one launch per level from here on

@@ -160,6 +160,8 @@ struct zkb_ctx {
     uint32_t* d_scratch_fail = nullptr;
     size_t first_fail_cap = 0;
     uint32_t* d_unreduced = nullptr;
+    uint32_t* d_barrier = nullptr;   // monotonic arrival counter of the grid barrier
+    uint32_t barrier_epoch = 0;      // its value once every launch issued so far has finished
     int64_t resident_tile = -1;
     bool inputs_uploaded = false;
     std::vector<uint32_t> h_first_fail;

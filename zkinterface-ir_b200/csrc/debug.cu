@@ -9,6 +9,7 @@
 
 #include "context.h"
 #include "device_util.cuh"
+#include "kernels.cuh"
 
 using namespace zkb;
 
@@ -165,5 +166,19 @@ extern "C" int zkb_debug_gather_throughput(zkb_ctx* c, uint64_t table_bytes, uin
     cudaFree(table);
     cudaFree(sink);
     *bytes_per_second = (double)grid * 256.0 * iters * 8.0 * 32.0 / (best * 1e-3);
+    return ZKB_OK;
+}
+
+// microseconds per barrier (kind 0: cooperative_groups grid.sync(), 1: the counter barrier k_levels_coop uses, 2: the hardware
+// barrier of one 8-CTA cluster) with `blocks` CTAs of 256 threads: n_levels x this is the latency floor of a single-witness
+// statement evaluated in one launch
+extern "C" int zkb_debug_barrier_cost(zkb_ctx* c, int kind, uint32_t blocks, uint32_t n_barriers, double* us_per_barrier) {
+    if (!c->has_gpu) return c->fail(ZKB_E_CUDA, "no CUDA device in this context (there is no CPU fallback)");
+    if (kind < 0 || kind > 2 || n_barriers == 0) return c->fail(ZKB_E_ARG, "kind in 0..2 and n_barriers > 0");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (blocks == 0) blocks = (uint32_t)c->sm_count;
+    float us = 0;
+    CUDA_TRY(c, measure_barrier_cost(kind, blocks, n_barriers, c->d_barrier, &c->barrier_epoch, c->stream, c->ev[0], c->ev[1], &us));
+    *us_per_barrier = us;
     return ZKB_OK;
 }

@@ -257,9 +257,45 @@ __device__ __forceinline__ void fe_mont_mul_chain(uint32_t* r, const uint32_t* a
     fe_cond_sub_p<N>(r, t, top, p);
 }
 
+// Two-limb fields (33..64-bit moduli) as ONE 64-bit limb: the 128-bit product is mul.lo.u64 / mul.hi.u64, the Montgomery
+// step one more product pair - or, for the Goldilocks prime p = 2^64 - 2^32 + 1, no product at all: p^-1 = 1 + 2^32
+// (mod 2^64), so m = lo + (lo << 32) and m * p / 2^64 = m - (m >> 32) - [the add overflowed], all shifts and adds.
+// Same contract as the CIOS form: a * b < p * 2^64, result fully reduced.  -p^-1 mod 2^64 is rebuilt from its low half
+// (n0inv) by one Newton step; the compiler hoists that out of the gate loop (it depends on the field only).
+__device__ __forceinline__ void fe_mont_mul_u64(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t n0inv) {
+    const uint64_t A = (uint64_t)a[1] << 32 | a[0], B = (uint64_t)b[1] << 32 | b[0], P = (uint64_t)p[1] << 32 | p[0];
+    const uint64_t lo = A * B, hi = __umul64hi(A, B);
+    uint64_t res;
+    if (P == 0xFFFFFFFF00000001ull) {
+        const uint64_t m = lo + (lo << 32);
+        const uint64_t e = m < lo ? 1u : 0u;
+        const uint64_t q = m - (m >> 32) - e;     // m * p / 2^64
+        res = hi - q;
+        if (hi < q) res -= 0xFFFFFFFFull;         // + p (mod 2^64)
+        if (res >= P) res -= P;
+    } else {
+        uint64_t ninv = (uint64_t)n0inv;                 // -p^-1 mod 2^32
+        ninv = 0 - ninv;                                 // p^-1 mod 2^32 (as a 64-bit value: correct in the low half)
+        ninv *= 2 - P * ninv;                            // Newton: p^-1 mod 2^64
+        const uint64_t m = lo * (0 - ninv);
+        const uint64_t uh = __umul64hi(m, P);            // lo + low(m * P) = 0 mod 2^64: carries exactly when lo != 0
+        res = hi + uh;
+        uint64_t carry = res < hi ? 1u : 0u;
+        const uint64_t c0 = lo != 0 ? 1u : 0u;
+        res += c0;
+        carry |= res < c0 ? 1u : 0u;
+        if (carry || res >= P) res -= P;
+    }
+    r[0] = (uint32_t)res;
+    r[1] = (uint32_t)(res >> 32);
+}
+
 template <int N>
 __device__ __forceinline__ void fe_mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t n0inv) {
     if constexpr (N == 8 || N == 4) fe_mont_mul_chain<N>(r, a, b, p, n0inv);
+#ifndef ZKB_NO_U64_FIELD
+    else if constexpr (N == 2) fe_mont_mul_u64(r, a, b, p, n0inv);
+#endif
     else fe_mont_mul_portable<N>(r, a, b, p, n0inv);
 }
 

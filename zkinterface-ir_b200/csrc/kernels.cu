@@ -446,6 +446,23 @@ k_level_tma(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, u
     }
 }
 
+// Grid barrier on one monotonic counter (per context, never reset: the host hands every launch its starting value).
+// A CTA arrives with one red.release.gpu after its block barrier and polls the counter until all have.  Measured SLOWER than
+// cooperative_groups' grid.sync() (zkb_debug_barrier_cost, profiles/r02h_ab_c2.log): opt-in only (ZKB_COUNTER_BARRIER=1).
+// All CTAs must be resident: the kernel is still launched with cudaLaunchCooperativeKernel.
+__device__ __forceinline__ void grid_barrier(uint32_t* ctr, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        uint32_t v;
+        do {  // relaxed polls (an acquire load is a load plus a fence, every time round), one fence once the count is there
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while ((int32_t)(v - target) < 0);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 // All wavefronts in ONE cooperative launch, a grid barrier between levels.  For programs whose levels are
 // too small to fill the chip (single-witness statements, deep narrow circuits) the per-level launch latency
 // (~4-5 us) dominates; a grid.sync() costs ~1-2 us.  Operands are read with ld.global.cg because they were
@@ -453,29 +470,61 @@ k_level_tma(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, u
 // CLUSTER = true: the same loop for programs so narrow that ONE thread-block cluster (8 CTAs on neighbouring SMs of
 // one die) holds a whole wavefront: the barrier between levels is the hardware cluster barrier (barrier.cluster
 // arrive.release / wait.acquire, ~0.2 us) instead of a grid barrier through L2 atomics.
+#ifdef ZKB_COOP_PROFILE
+__device__ __forceinline__ long long zkb_clock() {  // clock read that memory operations are not moved across
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#endif
+// A descriptor load that stays where it is written: a plain __ldg of __restrict__ data is an invariant load, which the
+// compiler is free to sink below the barrier down to its first use, putting the memory latency back on the critical path.
+__device__ __forceinline__ uint4 ldg_pinned(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <int N, bool CLUSTER>
 __global__ void __launch_bounds__(CLUSTER ? 512 : 256)
 k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
               uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
-              RawCtx rc, TileGeom g, FieldParams fp) {
+              RawCtx rc, TileGeom g, FieldParams fp, uint32_t* barrier_ctr, uint32_t barrier_base) {
     const uint32_t wt_mask = (1u << g.log2_wt) - 1;
     const bool single = g.log2_wt == 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // CLUSTER: the grid is exactly one cluster
     const uint64_t tid0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const uint4* dptr = reinterpret_cast<const uint4*>(ops);
+    // wavefront boundaries from shared memory: the barriers flush L1, a global read of level_off[l + 2] would be one L2
+    // round trip at the top of every level, in front of the descriptor prefetch that needs it
+    constexpr uint32_t kOffCache = 2048;
+    __shared__ uint64_t s_off[kOffCache + 1];
+    for (uint32_t i = threadIdx.x; i <= n_levels && i <= kOffCache; i += blockDim.x) s_off[i] = level_off[i];
+    __syncthreads();
+    auto off = [&](uint32_t i) -> uint64_t { return i <= kOffCache ? s_off[i] : level_off[i]; };
     // the first descriptor of each level is fetched BEFORE the barrier that precedes the level (descriptors
     // do not depend on wire data), taking one memory latency off the per-level critical path
-    uint64_t lo = level_off[0], hi = n_levels ? level_off[1] : lo;
+    uint64_t lo = off(0), hi = n_levels ? off(1) : lo;
     uint4 first = make_uint4(0, 0, 0, 0);
-    if (tid0 < ((hi - lo) << g.log2_wt)) first = __ldg(dptr + lo + (tid0 >> g.log2_wt));
+    if (tid0 < ((hi - lo) << g.log2_wt)) first = ldg_pinned(dptr + lo + (tid0 >> g.log2_wt));
+#ifdef ZKB_COOP_PROFILE
+    long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
+#endif
     for (uint32_t l = 0; l < n_levels; l++) {
+#ifdef ZKB_COOP_PROFILE
+        const long long th0 = zkb_clock();
+#endif
         const uint64_t total = (hi - lo) << g.log2_wt;
         uint64_t nlo = hi, nhi = hi;
         uint4 next_first = make_uint4(0, 0, 0, 0);
         if (l + 1 < n_levels) {
-            nhi = level_off[l + 2];
-            if (tid0 < ((nhi - nlo) << g.log2_wt)) next_first = __ldg(dptr + nlo + (tid0 >> g.log2_wt));
+            nhi = off(l + 2);
+            if (tid0 < ((nhi - nlo) << g.log2_wt)) next_first = ldg_pinned(dptr + nlo + (tid0 >> g.log2_wt));
         }
+#ifdef ZKB_COOP_PROFILE
+        const long long tw0 = zkb_clock();
+        prof[0] += tw0 - th0;
+#endif
         for (uint64_t tid = tid0; tid < total; tid += stride) {
             const uint32_t lane = (uint32_t)tid & wt_mask;
             const uint64_t gi = lo + (tid >> g.log2_wt);
@@ -492,23 +541,54 @@ k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq,
 #pragma unroll
                 for (int k = 0; k < N; k++) b[k] = 0;
             }
+#ifdef ZKB_COOP_PROFILE
+            long long tq0 = zkb_clock();
+            prof[6] += tq0 - tw0;
+            if ((a[0] ^ b[0]) == 0x12345678u) tq0++;  // waits for the operands
+            const long long tq1 = zkb_clock();
+            prof[3] += tq1 - tq0;
+#endif
             if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
             else if (opc == D_MUL || opc == D_MULC) fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
             else rare_gate<N>(r, a, b, raw, lane, g, rc, fp);
+#ifdef ZKB_COOP_PROFILE
+            long long tq2 = zkb_clock();
+            if (r[0] == 0x12345679u) tq2++;
+            prof[4] += tq2 - tq1;
+#endif
             if (!(raw.w & F_NOSTORE)) store_elem<N>(store, raw.z, lane, g.log2_wt, r);
             if (raw.w & F_ASSERT) {
                 bool fail = !fe_is_zero<N>(r) && lane < g.n_valid;
                 report_fail(fail, __ldg(aseq + gi), first_fail, g.batch0 + lane, single);
             }
+#ifdef ZKB_COOP_PROFILE
+            prof[5] += zkb_clock() - tq2;
+#endif
         }
+#ifdef ZKB_COOP_PROFILE
+        prof[1] += zkb_clock() - tw0;
+#endif
         first = next_first;
         lo = nlo;
         hi = nhi;
         if (l + 1 < n_levels) {
+#ifdef ZKB_COOP_PROFILE
+            const long long tb0 = zkb_clock();
+#endif
             if (CLUSTER) cg::this_cluster().sync();
+            else if (barrier_ctr) grid_barrier(barrier_ctr, barrier_base + gridDim.x * (l + 1));
             else cg::this_grid().sync();
+#ifdef ZKB_COOP_PROFILE
+            prof[2] += zkb_clock() - tb0;
+#endif
         }
     }
+#ifdef ZKB_COOP_PROFILE
+    if ((threadIdx.x & 31) == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (threadIdx.x == 0 || threadIdx.x == blockDim.x - 32))
+        printf("coop profile cta %u warp %u: levels %u  head %lld  work %lld (issue %lld operands %lld compute %lld store+assert %lld)  barrier %lld  (cycles per level)\n",
+               blockIdx.x, threadIdx.x / 32, n_levels, prof[0] / n_levels, prof[1] / n_levels, prof[6] / n_levels, prof[3] / n_levels, prof[4] / n_levels,
+               prof[5] / n_levels, prof[2] / n_levels);
+#endif
 }
 
 template <int N>
@@ -753,9 +833,14 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
 template <int N>
 static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
                                  const uint32_t* consts_mont, uint32_t* first_fail, RawCtx rc, TileGeom g, FieldParams fp,
-                                 int sm_count, uint64_t max_level_items, cudaStream_t s) {
+                                 int sm_count, uint64_t max_level_items, uint32_t* barrier_ctr, uint32_t* barrier_epoch, cudaStream_t s) {
+    // cooperative_groups' grid.sync() measured faster than the counter barrier (1.19 vs 1.81 us at 444 CTAs, 1.18 vs 1.25 at
+    // 148; C2 4.40 vs 4.74 us per level: profiles/r02h_ab_c2.log), so it stays the default; ZKB_COUNTER_BARRIER=1 for the A/B
+    static const bool counter_barrier = getenv("ZKB_COUNTER_BARRIER") != nullptr;
+    if (!counter_barrier) barrier_ctr = nullptr;
+    uint32_t barrier_base = *barrier_epoch;
     void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
-                    (void*)&first_fail, (void*)&rc, (void*)&g, (void*)&fp};
+                    (void*)&first_fail, (void*)&rc, (void*)&g, (void*)&fp, (void*)&barrier_ctr, (void*)&barrier_base};
     // a wavefront that fits one cluster of 8 x 512 threads (two items per thread at most): cluster barrier
     static const bool no_cluster = getenv("ZKB_NO_CLUSTER") != nullptr;
     static bool cluster_ok = true;
@@ -787,15 +872,76 @@ static cudaError_t launch_coop_n(const GateOp* ops, const uint32_t* aseq, const 
     if (blocks < (uint64_t)sm_count) blocks = sm_count;
     if (blocks > (uint64_t)sm_count * per_sm) blocks = (uint64_t)sm_count * per_sm;
     if (const char* e = getenv("ZKB_COOP_BLOCKS")) blocks = (uint64_t)atoi(e);
-    return cudaLaunchCooperativeKernel((void*)k_levels_coop<N, false>, dim3((unsigned)blocks), dim3(256), args, 0, s);
+    e = cudaLaunchCooperativeKernel((void*)k_levels_coop<N, false>, dim3((unsigned)blocks), dim3(256), args, 0, s);
+    if (e == cudaSuccess && barrier_ctr && n_levels > 1) *barrier_epoch += (uint32_t)blocks * (n_levels - 1);  // arrivals this launch adds
+    return e;
+}
+
+// barrier micro-benchmark: n barriers and nothing else (zkb_debug_barrier_cost)
+template <int KIND>
+__global__ void __launch_bounds__(KIND == 2 ? 512 : 256) k_barrier_only(uint32_t n, uint32_t* ctr, uint32_t base, uint32_t* sink) {
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (KIND == 0) cg::this_grid().sync();
+        else if (KIND == 1) grid_barrier(ctr, base + gridDim.x * (i + 1));
+        else cg::this_cluster().sync();
+        acc += i;
+    }
+    if (acc == 0xFFFFFFFFu) *sink = acc;
+}
+
+cudaError_t measure_barrier_cost(int kind, unsigned blocks, unsigned n_barriers, uint32_t* barrier_ctr, uint32_t* barrier_epoch,
+                                 cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, float* us_per_barrier) {
+    uint32_t base = *barrier_epoch;
+    uint32_t* sink = barrier_ctr;  // never written
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        // the launch itself is timed too: subtract an n = 0 launch of the same shape
+        float ms[2] = {0, 0};
+        for (int pass = 0; pass < 2; pass++) {
+            uint32_t n = pass == 0 ? 0u : n_barriers;
+            base = *barrier_epoch;
+            void* args[] = {(void*)&n, (void*)&barrier_ctr, (void*)&base, (void*)&sink};
+            cudaEventRecord(ev0, s);
+            cudaError_t e;
+            if (kind == 2) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(8);
+                cfg.blockDim = dim3(512);
+                cfg.stream = s;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 8;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                e = cudaLaunchKernelExC(&cfg, (const void*)k_barrier_only<2>, args);
+            } else if (kind == 1) {
+                e = cudaLaunchCooperativeKernel((void*)k_barrier_only<1>, dim3(blocks), dim3(256), args, 0, s);
+                if (e == cudaSuccess) *barrier_epoch += blocks * n;
+            } else {
+                e = cudaLaunchCooperativeKernel((void*)k_barrier_only<0>, dim3(blocks), dim3(256), args, 0, s);
+            }
+            if (e != cudaSuccess) return e;
+            cudaEventRecord(ev1, s);
+            e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return e;
+            cudaEventElapsedTime(&ms[pass], ev0, ev1);
+        }
+        if (rep > 0) best = std::min(best, ms[1] - ms[0]);
+    }
+    *us_per_barrier = best * 1e3f / (float)n_barriers;
+    return cudaSuccess;
 }
 
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
                                uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
-                               const FieldParams& fp, int sm_count, uint64_t max_level_items, cudaStream_t s) {
+                               const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t* barrier_ctr,
+                               uint32_t* barrier_epoch, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count,
-                                                max_level_items, s)));
+                                                max_level_items, barrier_ctr, barrier_epoch, s)));
     return e;
 }
 

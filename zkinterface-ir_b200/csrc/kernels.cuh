@@ -51,7 +51,12 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
 // every wavefront in one cooperative launch (grid barrier between levels); for launch-bound programs
 cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
                                uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
-                               const FieldParams& fp, int sm_count, uint64_t max_level_items, cudaStream_t s);
+                               const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t* barrier_ctr,
+                               uint32_t* barrier_epoch, cudaStream_t s);
+// microseconds per barrier of a kernel that does nothing else (kind 0: cooperative_groups grid.sync, 1: the counter barrier of
+// k_levels_coop, 2: the hardware barrier of one 8-CTA cluster)
+cudaError_t measure_barrier_cost(int kind, unsigned blocks, unsigned n_barriers, uint32_t* barrier_ctr, uint32_t* barrier_epoch,
+                                 cudaStream_t s, cudaEvent_t ev0, cudaEvent_t ev1, float* us_per_barrier);
 void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                         uint32_t* out, const FieldParams& fp, cudaStream_t s);
 
