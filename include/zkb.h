@@ -186,12 +186,19 @@ typedef struct {
     uint32_t binary;        /* p == 2 */
     uint32_t tile_witnesses;/* witnesses resident per pass (after upload) */
     uint32_t n_tiles;
+    uint64_t n_call_groups; /* For loops over a plain function kept as ONE loop-structured descriptor each (Boolean
+                             * profile; evaluator.rs:495-559 + :441-471): the device expands them, only the calls'
+                             * outputs are SSA values (kind 11 in zkb_get_program) */
+    uint64_t n_group_calls; /* function calls those groups stand for */
+    uint64_t n_group_launches;     /* after finalize: kernel launches that expand them (one per dependency depth) */
+    uint64_t n_group_table_slots;  /* after finalize: operand slots listed explicitly (inputs whose slots are not an
+                                    * arithmetic progression over the calls) */
 } zkb_stats;
 int zkb_get_stats(zkb_ctx* ctx, zkb_stats* out);
 
 /* Inspection of the recorded SSA program (host preparation parity checks): values
  * [first, first+n) -> kind (0 const, 1 instance, 2 witness, 3 add, 4 mul, 5 addc, 6 mulc, 7 and,
- * 8 xor, 9 not), operand a (value handle), operand b (value handle, or constant-pool index for
+ * 8 xor, 9 not, 11 output of a call group: a = group, b = call * n_outputs + position), operand a (value handle), operand b (value handle, or constant-pool index for
  * const/addc/mulc, or stream position for instance/witness). */
 int zkb_get_program(zkb_ctx* ctx, uint64_t first, uint64_t n, uint8_t* kinds, uint32_t* a, uint32_t* b);
 /* canonical residue of constant-pool entry idx (little-endian) */

@@ -147,10 +147,19 @@ def c5(lo, li, batch):
     b.upload_inputs(None, W, batch)
     tot, lv = timed_runs(b.run, b.timing)
     st = b.stats()
+    # unrolled, one 16-byte GateOp + 3 operands of 1/8 byte per gate = 16.4 B/gate at one witness.
+    # Loop-structured (csrc/program.h CallGroup): a call moves its 3 inputs and 2 outputs (one 32-witness word each per tile
+    # word) and nothing else — the 8-gate body lives in registers, the 96-byte descriptor stands for 2^li calls.
+    words = max(1, st["tile_witnesses"] // 32)
+    grouped_bytes = st["n_group_calls"] * (3 + 2) * 4 * words + 96 * st["n_call_groups"] + (16 + 12 * words) * st["n_device_ops"]
     return {"config": f"C5 Boolean 2^{lo + li + 3} leaf gates (nested For 2^{lo} x 2^{li}), {batch} witness(es) bit-sliced",
-            "gates_per_s": n_leaf * batch / (tot * 1e-3), "ms": tot, "levels": st["n_levels"], "host_flatten_s": flat_s,
-            "finalize_and_first_eval_s": first_s, "values": st["n_values"],
-            "algo_GBps": (16 + 12) * st["n_device_ops"] * max(1, batch // 32) / (tot * 1e-3) / 1e9}
+            "gates_per_s": n_leaf * batch / (tot * 1e-3), "ms": tot, "levels_ms": lv, "levels": st["n_levels"], "host_flatten_s": flat_s,
+            "finalize_and_first_eval_s": first_s, "host_prep_s": flat_s + first_s, "values": st["n_values"],
+            "call_groups": st["n_call_groups"], "group_calls": st["n_group_calls"], "device_ops": st["n_device_ops"],
+            "kernel_launches": b.timing()["kernel_launches"],
+            "descriptor_form_bytes_per_gate": 16 + 3 / 8, "grouped_bytes_per_gate": grouped_bytes / n_leaf,
+            "device_GBps": grouped_bytes / (tot * 1e-3) / 1e9,
+            "descriptor_form_GBps_equivalent": (16 + 3 / 8) * n_leaf / (tot * 1e-3) / 1e9}
 
 
 def c3_sieve(log2_gates):

@@ -14,7 +14,8 @@ WS = os.path.join(ROOT, "tests", "golden", "example")
 
 
 def build():
-    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(SRC), os.path.getmtime(os.path.join(ROOT, "include", "zkb.hpp"))):
+    if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(
+            os.path.getmtime(SRC), os.path.getmtime(os.path.join(ROOT, "include", "zkb.hpp")), os.path.getmtime(os.path.join(ROOT, "include", "zkb.h"))):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-o", BIN,
                                "-L", PKG, "-lzkb", f"-Wl,-rpath,{PKG}"])
 

@@ -48,7 +48,9 @@ class ZkbStats(C.Structure):
                 ("n_witness", C.c_uint64), ("n_consts", C.c_uint64), ("ir_gates", C.c_uint64),
                 ("callbacks", C.c_uint64 * 12), ("n_slots", C.c_uint64), ("n_levels", C.c_uint64),
                 ("n_device_ops", C.c_uint64), ("algo_bytes_per_witness", C.c_uint64), ("nlimb", C.c_uint32),
-                ("binary", C.c_uint32), ("tile_witnesses", C.c_uint32), ("n_tiles", C.c_uint32)]
+                ("binary", C.c_uint32), ("tile_witnesses", C.c_uint32), ("n_tiles", C.c_uint32),
+                ("n_call_groups", C.c_uint64), ("n_group_calls", C.c_uint64),
+                ("n_group_launches", C.c_uint64), ("n_group_table_slots", C.c_uint64)]
 
 
 class ZkbTiming(C.Structure):

@@ -46,6 +46,13 @@ static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
     return ZKB_OK;
 }
 
+int ctx_upload_groups(zkb_ctx* c) {
+    int rc;
+    if ((rc = upload_vec(c, c->d_group_descs, c->plan.group_descs)) != ZKB_OK) return rc;
+    if ((rc = upload_vec(c, c->d_group_ops, c->plan.group_ops)) != ZKB_OK) return rc;
+    return upload_vec(c, c->d_group_tables, c->plan.group_tables);
+}
+
 int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (!c->prog.field_set) return c->fail(ZKB_E_ARG, "zkb_finalize: set_field was never called");
     if (c->prog.keep_copies) return c->fail(ZKB_E_ARG, "this context records in flatten mode: the program can be written out, not evaluated");
@@ -73,6 +80,7 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     if ((rc = upload_vec(c, c->d_loads, c->plan.loads)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_consts, c->prog.const_limbs)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_level_off, c->plan.level_off)) != ZKB_OK) return rc;
+    if ((rc = ctx_upload_groups(c)) != ZKB_OK) return rc;
     if (c->plan.n_raw_ops > 0 && (rc = upload_vec(c, c->d_const_flags, c->prog.const_unreduced)) != ZKB_OK) return rc;
     // raw bytes of the constants >= p, for the bitwise gates that take them unreduced (evaluator.rs:924-930)
     c->const_raw_stride = 0;
@@ -144,6 +152,9 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_loads);
         cudaFree(c->d_consts);
         cudaFree(c->d_level_off);
+        cudaFree(c->d_group_descs);
+        cudaFree(c->d_group_ops);
+        cudaFree(c->d_group_tables);
         cudaFree(c->d_const_flags);
         cudaFree(c->d_const_raw);
         cudaFree(c->d_rawflag);
@@ -203,9 +214,9 @@ extern "C" int zkb_minus_one(zkb_ctx* c, uint8_t* out, size_t cap, size_t* len) 
     if ((c)->is_replica) return (c)->fail(ZKB_E_ARG, "this context holds a replica of another rank's program: nothing can be recorded here"); \
     if (!(c)->prog.field_set) return (c)->fail(ZKB_E_ARG, "set_field must be called before recording"); \
     if ((c)->finalized) return (c)->fail(ZKB_E_ARG, "program already finalized");               \
-    if ((c)->prog.n_values() >= (c)->max_values) return (c)->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)")
+    if ((c)->prog.n_total_values() >= (c)->max_values) return (c)->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)")
 #define CHECK_WIRE(c, w) \
-    if ((w) >= (c)->prog.n_values()) return (c)->fail(ZKB_E_ARG, "unknown wire handle")
+    if (!(c)->prog.valid_handle(w)) return (c)->fail(ZKB_E_ARG, "unknown wire handle")
 
 extern "C" int zkb_copy(zkb_ctx* c, zkb_wire a, zkb_wire* out) {
     REC_PROLOGUE(c);
@@ -294,7 +305,7 @@ extern "C" int zkb_push_gates(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gate
     p.opb.reserve(p.opb.size() + n_gates);
     for (uint64_t i = 0; i < n_gates; i++) {
         const zkb_gate& g = gates[i];
-        if (p.n_values() >= c->max_values) return c->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)");
+        if (p.n_total_values() >= c->max_values) return c->fail(ZKB_E_UNSUPPORTED, "zkb: resource limit exceeded (max_values)");
         uint32_t va = 0, vb = 0, res = 0;
         switch (g.op) {
             case ZKB_G_CONSTANT:
@@ -508,6 +519,16 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         }
         cudaEventRecord(c->tile_ev[2 * tile], c->stream);
     }
+    // call groups: one launch per dependency depth, before the first wavefront (their outputs are level-0 values)
+    for (size_t d = 0; d + 1 < pl.depth_off.size(); d++) {
+        const uint32_t lo = pl.depth_off[d], hi = pl.depth_off[d + 1];
+        if (hi == lo) continue;
+        const uint64_t calls = (uint64_t)pl.group_descs[hi - 1].first_call + pl.group_descs[hi - 1].n_calls;
+        launch_bool_groups(c->d_group_descs + lo, hi - lo, calls, c->d_group_ops, c->d_group_tables, c->d_store, c->d_consts, g,
+                           pl.group_regs, c->sm_count, c->stream);
+        (*launches)++;
+        if (level_launches) (*level_launches)++;
+    }
     // launch-bound programs (levels far too small to fill the chip): all wavefronts in one cooperative launch
     bool coop = !p.binary && pl.n_levels > 1 && ((uint64_t)pl.max_level_ops << c->log2_wt) <= (uint64_t)c->sm_count * 8192;
     if (const char* e = getenv("ZKB_COOP")) coop = coop && atoi(e) != 0;
@@ -690,10 +711,18 @@ extern "C" int zkb_assert_info(zkb_ctx* c, uint64_t seq, uint64_t* src_wire_id) 
 // replica contexts keep the value tables on the device (comm.cu): fetch the entries of the requested handles
 __global__ void k_gather_value_tables(const uint64_t* __restrict__ handles, uint32_t n, uint64_t n_values, const uint32_t* __restrict__ t_slot,
                                       const uint32_t* __restrict__ t_opb, const uint8_t* __restrict__ t_read, const uint8_t* __restrict__ t_kind,
+                                      uint32_t callout_slot0, uint32_t n_callouts,
                                       uint32_t* __restrict__ out) {  // out: 4 x uint32 per handle {slot, opb, readable, kind}
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t v = handles[i];
+    if (v >= kCalloutBit && v - kCalloutBit < n_callouts) {  // output of a call group: implicit value (program.h)
+        out[4 * i] = callout_slot0 + (uint32_t)(v - kCalloutBit);
+        out[4 * i + 1] = 0;
+        out[4 * i + 2] = 1;
+        out[4 * i + 3] = V_CALLOUT;
+        return;
+    }
     if (v >= n_values) {
         out[4 * i + 3] = 0xFFFFFFFFu;  // unknown handle
         return;
@@ -727,7 +756,8 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
         CUDA_TRY(c, cudaMalloc((void**)&d_t, t.size() * 4));
         CUDA_TRY(c, cudaMemcpyAsync(d_h, values, n * 8, cudaMemcpyHostToDevice, c->stream));
         if (n) k_gather_value_tables<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_h, (uint32_t)n, c->replica_n_values, c->d_tab_slot, c->d_tab_opb,
-                                                                                       c->d_tab_readable, c->d_tab_kind, d_t);
+                                                                                       c->d_tab_readable, c->d_tab_kind, c->plan.callout_slot0,
+                                                                                       c->plan.n_callouts, d_t);
         CUDA_TRY(c, cudaMemcpyAsync(t.data(), d_t, n * 16, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         cudaFree(d_h);
@@ -740,10 +770,11 @@ extern "C" int zkb_read_values(zkb_ctx* c, uint32_t batch_idx, const zkb_wire* v
         }
     } else {
         for (uint64_t i = 0; i < n; i++) {
-            if (values[i] >= p.n_values()) return c->fail(ZKB_E_ARG, "unknown wire handle");
-            slots[i] = c->plan.readable[values[i]] ? c->plan.slot_of_value[values[i]] : kNoSlot;
-            kinds[i] = p.kind[values[i]];
-            opbs[i] = p.opb[values[i]];
+            if (!p.valid_handle(values[i])) return c->fail(ZKB_E_ARG, "unknown wire handle");
+            const uint32_t h = (uint32_t)values[i];
+            slots[i] = c->plan.is_readable(h) ? c->plan.slot_of(h) : kNoSlot;
+            kinds[i] = is_callout(h) ? (uint32_t)V_CALLOUT : p.kind[h];
+            opbs[i] = is_callout(h) ? 0 : p.opb[h];
         }
     }
     for (uint64_t i = 0; i < n; i++)
@@ -816,6 +847,11 @@ extern "C" int zkb_debug_plan_hash(zkb_ctx* c, uint64_t* out) {
     mix(pl.readable.data(), pl.readable.size());
     mix(pl.level_off.data(), pl.level_off.size() * 8);
     mix(pl.level_rare.data(), pl.level_rare.size() * 8);
+    mix(pl.group_descs.data(), pl.group_descs.size() * sizeof(GroupDesc));
+    mix(pl.group_ops.data(), pl.group_ops.size() * sizeof(TmplOp));
+    mix(pl.group_tables.data(), pl.group_tables.size() * 4);
+    mix(&pl.callout_slot0, 4);
+    mix(&pl.n_callouts, 4);
     mix(&pl.n_slots, 4);
     mix(&pl.n_reused_slots, 8);
     mix(pl.n_dev_ops, sizeof(pl.n_dev_ops));
@@ -826,7 +862,7 @@ extern "C" int zkb_debug_plan_hash(zkb_ctx* c, uint64_t* out) {
 extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
     memset(s, 0, sizeof(*s));
     const Program& p = c->prog;
-    s->n_values = c->is_replica ? c->replica_n_values : p.n_values();
+    s->n_values = c->is_replica ? c->replica_n_values + c->plan.n_callouts : p.n_total_values();
     s->n_asserts = p.asserts.size();
     s->n_instance = p.n_instance;
     s->n_witness = p.n_witness;
@@ -840,6 +876,14 @@ extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
         s->n_levels = c->plan.n_levels;
         s->n_device_ops = c->is_replica ? c->replica_n_ops : c->plan.ops.size();
         s->algo_bytes_per_witness = c->plan.algo_bytes_per_witness;
+    }
+    s->n_call_groups = c->plan.group_descs.empty() ? p.groups.size() : c->plan.group_descs.size();
+    for (const auto& g : p.groups) s->n_group_calls += g.n_calls;
+    if (p.groups.empty())
+        for (const auto& g : c->plan.group_descs) s->n_group_calls += g.n_calls;  // replica: only the plan came over
+    if (c->finalized) {
+        for (size_t d = 0; d + 1 < c->plan.depth_off.size(); d++) s->n_group_launches += c->plan.depth_off[d + 1] > c->plan.depth_off[d];
+        s->n_group_table_slots = c->plan.group_tables.size();
     }
     if (c->inputs_uploaded) {
         s->tile_witnesses = 1u << c->log2_wt;
@@ -856,7 +900,7 @@ extern "C" int zkb_get_timing(zkb_ctx* c, zkb_timing* t) {
 extern "C" int zkb_get_program(zkb_ctx* c, uint64_t first, uint64_t n, uint8_t* kinds, uint32_t* a, uint32_t* b) {
     const Program& p = c->prog;
     if (c->is_replica) return c->fail(ZKB_E_ARG, "replica context: the recorded program lives on the root rank");
-    if (first + n > p.n_values()) return c->fail(ZKB_E_ARG, "program range out of bounds");
+    if (first + n > p.n_values()) return c->fail(ZKB_E_ARG, "program range out of bounds");  // explicit values only
     for (uint64_t i = 0; i < n; i++) {
         kinds[i] = p.kind[first + i];
         a[i] = p.opa[first + i];

@@ -223,6 +223,7 @@ struct ReplicaHeader {
     uint64_t cb_count[CB_KINDS];
     uint64_t n_dev_ops[D_OPS];
     uint64_t modulus_len, pending_len, const_raw_bytes;
+    uint64_t n_group_descs, n_group_ops, n_group_tables, n_depth_off, group_regs, callout_slot0, n_callouts;  // call groups (program.h)
     uint32_t n_slots, max_level_ops, n_instance, n_witness;
     uint32_t nlimb, binary, is_boolean, has_pending, keep_all, const_raw_stride, has_const_flags, pad;
     FieldParams fp;
@@ -318,6 +319,17 @@ static int broadcast_program(zkb_ctx* c, int root) {
         put(blob, const_raw_flat.data(), const_raw_flat.size());
         put(blob, p.modulus_le.data(), p.modulus_le.size());
         put(blob, c->pending_error.data(), (size_t)h.pending_len);
+        h.n_group_descs = pl.group_descs.size();
+        h.n_group_ops = pl.group_ops.size();
+        h.n_group_tables = pl.group_tables.size();
+        h.n_depth_off = pl.depth_off.size();
+        h.group_regs = pl.group_regs;
+        h.callout_slot0 = pl.callout_slot0;
+        h.n_callouts = pl.n_callouts;
+        put(blob, pl.group_descs.data(), pl.group_descs.size());
+        put(blob, pl.group_ops.data(), pl.group_ops.size());
+        put(blob, pl.group_tables.data(), pl.group_tables.size());
+        put(blob, pl.depth_off.data(), pl.depth_off.size());
         h.blob_bytes = blob.size();
     }
     // 1. the fixed-size header
@@ -366,6 +378,13 @@ static int broadcast_program(zkb_ctx* c, int root) {
         get(cur, p.modulus_le, h.modulus_len);
         std::vector<char> pend;
         get(cur, pend, h.pending_len);
+        get(cur, pl.group_descs, h.n_group_descs);
+        get(cur, pl.group_ops, h.n_group_ops);
+        get(cur, pl.group_tables, h.n_group_tables);
+        get(cur, pl.depth_off, h.n_depth_off);
+        pl.group_regs = (uint32_t)h.group_regs;
+        pl.callout_slot0 = (uint32_t)h.callout_slot0;
+        pl.n_callouts = (uint32_t)h.n_callouts;
         const uint8_t* q = const_raw_flat.data();
         p.const_raw.resize(h.n_consts);
         for (uint64_t i = 0; i < h.n_consts && q < const_raw_flat.data() + const_raw_flat.size(); i++) {
@@ -412,6 +431,7 @@ static int broadcast_program(zkb_ctx* c, int root) {
     if ((rc = bcast_array(c, c->d_level_off, h.n_levels + 1, root, is_root)) != ZKB_OK) return rc;
     if ((rc = bcast_array(c, c->d_const_flags, h.has_const_flags ? h.n_consts : 0, root, is_root)) != ZKB_OK) return rc;
     if ((rc = bcast_array(c, c->d_const_raw, (size_t)h.const_raw_stride * h.n_consts, root, is_root)) != ZKB_OK) return rc;
+    if (!is_root && (rc = ctx_upload_groups(c)) != ZKB_OK) return rc;  // small: from the host copy that came with the tables
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     lap("device plan");
     // the per-value tables (value -> slot / readable / kind / operand b) stay ON THE DEVICE of a replica: zkb_read_values

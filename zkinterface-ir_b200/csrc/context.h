@@ -4,6 +4,7 @@
 #include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -28,6 +29,7 @@ public:
     uint64_t n_sets = 0;              // insertions since the last clear(): bounds the dense part
     bool track = false;               // pooled scopes remember the dense ids they touched, so clear() is O(touched)
     std::vector<uint32_t> touched;
+    bool touched_all = false;         // bulk insertions are not listed: clear() wipes the whole table
 
     // operand ids of a gate a few iterations ahead: random circuits read the map all over, so the loads are started early
     void prefetch(uint64_t id) const {
@@ -67,6 +69,22 @@ public:
         }
         return true;
     }
+    // bulk insertion (call groups, sub-scope plumbing): after ensure_dense(hi, n) the caller writes up to n UNBOUND ids
+    // <= hi straight into `dense` and reports how many with bulk_inserted().  The same memory bound as set().
+    bool ensure_dense(uint64_t hi, uint64_t n_new) {
+        if (hi < dense.size()) return true;
+        if (hi >= kDenseLimit || hi > 4 * (n_sets + n_new + 1024)) return false;
+        // sized for the request (a loop that announces 2^24 outputs gets 2^24 entries, not the next power of two), but never
+        // growing by less than half, so repeated requests stay amortized
+        size_t n = std::max<size_t>({(size_t)hi + 1, dense.size() + dense.size() / 2, (size_t)16});
+        dense.resize(n, kNone);
+        return true;
+    }
+    void bulk_inserted(uint64_t n) {
+        n_sets += n;
+        live += n;
+        touched_all = true;
+    }
     bool remove(uint64_t id) {
         if (id < dense.size() && dense[id] != kNone) {
             dense[id] = kNone;
@@ -82,12 +100,13 @@ public:
     void clear() {
         if (dense.size() > (1u << 20)) {  // a pooled scope does not keep a large table alive
             std::vector<uint32_t>().swap(dense);
-        } else if (track && touched.size() < dense.size() / 8) {
+        } else if (track && !touched_all && touched.size() < dense.size() / 8) {
             for (uint32_t id : touched) dense[id] = kNone;
         } else {
             std::fill(dense.begin(), dense.end(), kNone);
         }
         touched.clear();
+        touched_all = false;
         sparse.clear();
         live = 0;
         n_sets = 0;
@@ -141,6 +160,9 @@ struct zkb_ctx {
     zkb::InputLoad* d_loads = nullptr;
     uint32_t* d_consts = nullptr;
     uint64_t* d_level_off = nullptr;
+    zkb::GroupDesc* d_group_descs = nullptr;  // call groups (program.h), launch order
+    zkb::TmplOp* d_group_ops = nullptr;
+    uint32_t* d_group_tables = nullptr;
     uint8_t* d_const_flags = nullptr;   // per constant: raw value >= p
     uint8_t* d_const_raw = nullptr;     // raw bytes of the constants (const_raw_stride each), when a bitwise gate may need them
     uint32_t const_raw_stride = 0;
@@ -187,6 +209,7 @@ struct zkb_ctx {
 
 namespace zkb {
 // shared helpers implemented in backend.cu
+int ctx_upload_groups(zkb_ctx* c);  // plan.group_* -> device
 int ctx_finalize(zkb_ctx* c, int keep_values);  // 0 live wires, 1 all values, 2 verdicts only
 bool ctx_record_ok(zkb_ctx* c);  // false when a recording error is latched
 void ctx_latch(zkb_ctx* c, const std::string& msg);

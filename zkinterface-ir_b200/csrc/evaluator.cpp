@@ -11,6 +11,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <functional>
 #include <atomic>
 #include <chrono>
 #include <deque>
@@ -41,6 +42,9 @@ struct FunctionDecl {  // evaluator.rs:130-136
     // behaves identically on every invocation: it is run over a flat array of local wires instead of a Scope
     // (n_local > 0).  Anything else goes through ingest_subcircuit, which reports errors where the reference does.
     uint32_t n_local = 0;
+    // index of the body's Template in the Program (loop-structured recording, program.h), -1: not compiled yet, -2: the
+    // body does not qualify
+    mutable int tmpl = -1;
 };
 
 uint32_t simple_body_locals(const std::vector<ir::Gate>& body, uint64_t n_out, uint64_t n_in) {
@@ -239,11 +243,12 @@ struct zkb_evaluator {
             } else {
                 uint64_t b = eval_iterexpr(el.last, known);
                 if (b >= a && b - a > (1ull << 32)) throw EvalErr{"zkb: iterator range too large"};
-                if (b >= a) step(b - a);
-                for (uint64_t w = a; w <= b && b >= a; w++) {
-                    out.push_back(w);
-                    if (w == UINT64_MAX) break;
-                }
+                if (b < a) continue;
+                step(b - a);
+                const size_t o = out.size();
+                out.resize(o + (size_t)(b - a) + 1);
+                uint64_t* dst = out.data() + o;
+                for (uint64_t k = 0; k <= b - a; k++) dst[k] = a + k;
             }
         }
     }
@@ -320,7 +325,7 @@ struct zkb_evaluator {
         for (size_t idx = 0; idx < ins.size(); idx++) L[n_out + idx] = p.copy(get(scope, ins[idx]));
         const auto& consts = *f.consts;
         for (const ir::Gate& g : *f.body) {
-            if (p.n_values() >= c->max_values) throw EvalErr{"zkb: resource limit exceeded (max_values)"};
+            if (p.n_total_values() >= c->max_values) throw EvalErr{"zkb: resource limit exceeded (max_values)"};
             step();
             switch (g.type) {
                 case ir::G_CONSTANT: {
@@ -352,6 +357,240 @@ struct zkb_evaluator {
         }
         for (size_t idx = 0; idx < n_out; idx++) set(scope, outs[idx], p.copy(L[idx]));
     }
+    // ---- loop-structured recording: a For loop over a plain function becomes ONE call group (program.h) -----------------
+    // The body qualifies when every gate is a value-defining simple gate the device interpreter runs on reduced values:
+    // no AssertZero (an assertion inside a call needs a sequence number per call), no Copy (an output that aliases a raw
+    // input would carry its unreduced integer on), and no Not directly on a call input (Not tests the RAW integer of an
+    // input value, evaluator.rs:932-938; And / Xor / Add / Mul only see the low bit mod 2).  Boolean profile only.
+    int template_of(const FunctionDecl& f) {
+        if (f.tmpl != -1) return f.tmpl;
+        f.tmpl = -2;
+        Program& p = prog();
+        if (!f.n_local || f.n_local > kMaxTemplateRegs || f.body->size() > kMaxTemplateOps || f.input_count > kMaxGroupInputs ||
+            f.output_count == 0)
+            return f.tmpl;
+        Template t;
+        t.n_out = (uint32_t)f.output_count;
+        t.n_in = (uint32_t)f.input_count;
+        t.n_regs = f.n_local;
+        auto is_input = [&](uint64_t w) { return w >= f.output_count && w < f.output_count + f.input_count; };
+        for (const ir::Gate& g : *f.body) {
+            TmplOp o{};
+            o.dst = (uint8_t)g.w0;
+            o.a = (uint8_t)g.w1;
+            o.b = (uint32_t)g.w2;
+            switch (g.type) {
+                case ir::G_CONSTANT: {
+                    const auto& v = (*f.consts)[g.const_idx];
+                    o.kind = V_CONST;
+                    o.a = 0;
+                    o.b = p.intern_const(v.data(), v.size());
+                    if (p.const_unreduced[o.b]) return f.tmpl;  // a constant >= p stays a raw integer (trap 1)
+                    t.cb[CB_CONSTANT]++;
+                } break;
+                case ir::G_ADD: o.kind = V_ADD; t.cb[CB_ADD]++; t.n_two++; break;
+                case ir::G_MUL: o.kind = V_MUL; t.cb[CB_MUL]++; t.n_two++; break;
+                case ir::G_AND: o.kind = V_AND; t.cb[CB_AND]++; t.n_two++; break;
+                case ir::G_XOR: o.kind = V_XOR; t.cb[CB_XOR]++; t.n_two++; break;
+                case ir::G_ADD_CONSTANT: case ir::G_MUL_CONSTANT: {
+                    const auto& v = (*f.consts)[g.const_idx];
+                    o.kind = g.type == ir::G_ADD_CONSTANT ? V_ADDC : V_MULC;
+                    o.b = p.intern_const(v.data(), v.size());
+                    t.cb[g.type == ir::G_ADD_CONSTANT ? CB_ADDC : CB_MULC]++;
+                    t.n_one++;
+                } break;
+                case ir::G_NOT:
+                    if (is_input(g.w1)) return f.tmpl;
+                    o.kind = V_NOT;
+                    o.b = 0;
+                    t.cb[CB_NOT]++;
+                    t.n_one++;
+                    break;
+                default: return f.tmpl;  // AssertZero, Copy
+            }
+            if (g.type != ir::G_CONSTANT) t.ir_gates++;
+            t.ops.push_back(o);
+        }
+        t.cb[CB_COPY] = f.input_count + f.output_count;
+        p.templates.push_back(std::move(t));
+        f.tmpl = (int)p.templates.size() - 1;
+        return f.tmpl;
+    }
+
+    struct AffineWire {
+        uint64_t w0, stride;
+    };
+    // wires of an iterator-expression list at loop value i0, with their step per loop iteration; false: not affine
+    bool affine_wires(const ir::IterExprList& l, Iters& iters, const std::string& var, uint64_t i0, std::vector<AffineWire>& out) {
+        out.clear();
+        iters_set(iters, var, i0);
+        // value v0 at loop index i0 and step st per iteration (wrapping arithmetic, as the reference's release build); false
+        // when the expression is not linear in the loop variable (a product of two dependent sides, a DivConst of one)
+        std::function<bool(const ir::IterExpr&, uint64_t&, uint64_t&)> form = [&](const ir::IterExpr& e, uint64_t& v0, uint64_t& st) {
+            switch (e.type) {
+                case 1: v0 = e.value; st = 0; return true;
+                case 2: v0 = lookup_iter(e.name, iters); st = e.name == var ? 1 : 0; return true;
+                case 3: case 4: case 5: {
+                    uint64_t a0, sa, b0, sb;
+                    if (!form(*e.l, a0, sa) || !form(*e.r, b0, sb)) return false;
+                    if (e.type == 3) { v0 = a0 + b0; st = sa + sb; }
+                    else if (e.type == 4) { v0 = a0 - b0; st = sa - sb; }
+                    else {
+                        if (sa != 0 && sb != 0) return false;
+                        v0 = a0 * b0;
+                        st = sa * b0 + sb * a0;
+                    }
+                    return true;
+                }
+                case 6: {
+                    uint64_t a0, sa;
+                    if (e.value == 0 || !form(*e.l, a0, sa) || sa != 0) return false;
+                    v0 = a0 / e.value;
+                    st = 0;
+                    return true;
+                }
+            }
+            return false;
+        };
+        for (const auto& el : l) {
+            uint64_t a, sa;
+            if (!form(el.first, a, sa)) return false;
+            if (!el.is_range) {
+                out.push_back({a, sa});
+                continue;
+            }
+            uint64_t b, sb;
+            if (!form(el.last, b, sb) || sa != sb) return false;
+            if (b < a) continue;
+            if (b - a > 4096) return false;
+            for (uint64_t w = a;; w++) {
+                out.push_back({w, sa});
+                if (w == b) break;
+            }
+        }
+        return true;
+    }
+
+    // true: the whole loop has been recorded as one call group, with the state the gate-by-gate loop would leave (bindings,
+    // callback counts, work accounting).  false: nothing was changed; the caller runs the loop gate by gate, which also
+    // reports every error where the reference does.
+    bool try_call_group(const ir::Complex& cx, const FunctionDecl& f, Scope& scope, Iters& iters, const uint32_t* weight) {
+        Program& p = prog();
+        if (getenv("ZKB_NO_CALL_GROUPS") != nullptr || weight || p.keep_copies || p.expand_on || !p.field_set || !p.binary) return false;
+        if (cx.last < cx.first || cx.last - cx.first < 3 || cx.last - cx.first >= (1ull << 28)) return false;
+        const int ti = template_of(f);
+        if (ti < 0) return false;
+        const uint64_t n = cx.last - cx.first + 1;
+        std::vector<AffineWire> wo, wi;
+        Iters saved = iters;
+        bool ok = false;
+        try {
+            ok = affine_wires(cx.it_outputs, iters, cx.name, cx.first, wo) && affine_wires(cx.it_inputs, iters, cx.name, cx.first, wi);
+        } catch (const Fatal&) {
+        } catch (const EvalErr&) {
+        }
+        iters = saved;
+        const Template& t = p.templates[ti];
+        if (!ok || wo.size() != t.n_out || wi.size() != t.n_in) return false;
+        // outputs: every call writes its own block of unbound wires
+        const uint64_t S = wo[0].stride;
+        uint64_t lo = wo[0].w0, hi = wo[0].w0;
+        for (const auto& a : wo) {
+            if (a.stride != S) return false;
+            lo = std::min(lo, a.w0);
+            hi = std::max(hi, a.w0);
+        }
+        if (S == 0 || S >= (1ull << 32) || hi - lo >= S || hi >= (1ull << 40)) return false;
+        for (size_t a = 0; a < wo.size(); a++)
+            for (size_t b = a + 1; b < wo.size(); b++)
+                if (wo[a].w0 == wo[b].w0) return false;
+        const uint64_t n_new = n * t.n_out;
+        const uint64_t out_last = hi + S * (n - 1);
+        const bool plain_scope = scope.sparse.empty();  // every binding is in the dense table: it can be walked directly
+        {
+            const uint32_t* d = scope.dense.data();
+            const uint64_t dn = scope.dense.size();
+            if (plain_scope && out_last < dn) {  // branch-free walks: the loops pipeline
+                uint32_t all = Scope::kNone;
+                for (const auto& a : wo)
+                    for (uint64_t c = 0, w = a.w0; c < n; c++, w += S) all &= d[w];
+                if (all != Scope::kNone) return false;
+            } else {
+                for (const auto& a : wo)
+                    for (uint64_t c = 0, w = a.w0; c < n; c++, w += S)
+                        if (plain_scope ? (w < dn && d[w] != Scope::kNone) : scope.get(w) != Scope::kNone) return false;
+            }
+        }
+        // inputs: bound before the loop, level-0 values (inputs or outputs of earlier groups), handles in arithmetic progression
+        CallGroup cg;
+        cg.tmpl = (uint32_t)ti;
+        cg.n_calls = (uint32_t)n;
+        cg.n_out = t.n_out;
+        cg.depth = 0;
+        for (const auto& a : wi) {
+            if (a.w0 >= (1ull << 40) || (a.stride >= (1ull << 32) && a.stride != 0)) return false;
+            const uint32_t h0 = scope.get(a.w0);
+            if (h0 == Scope::kNone) return false;
+            uint32_t st = 0, h_last = h0;
+            if (a.stride != 0) {
+                const uint32_t h1 = scope.get(a.w0 + a.stride);
+                if (h1 == Scope::kNone || h1 <= h0) return false;
+                st = h1 - h0;
+                if ((uint64_t)h0 + (uint64_t)st * (n - 1) >= 0xFFFFFFFFull) return false;
+                h_last = h0 + st * (uint32_t)(n - 1);
+                if (is_callout(h0) != is_callout(h_last)) return false;
+                const uint32_t* d = scope.dense.data();
+                const uint64_t dn = scope.dense.size();
+                uint32_t expect = h0;
+                if (plain_scope && a.w0 + a.stride * (n - 1) < dn) {
+                    uint32_t diff = 0;
+                    for (uint64_t c = 0, w = a.w0; c < n; c++, w += a.stride, expect += st) diff |= d[w] ^ expect;
+                    if (diff) return false;
+                } else {
+                    for (uint64_t c = 0, w = a.w0; c < n; c++, w += a.stride, expect += st) {
+                        const uint32_t h = plain_scope ? (w < dn ? d[w] : Scope::kNone) : scope.get(w);
+                        if (h != expect) return false;
+                    }
+                }
+            }
+            if (is_callout(h0)) {  // outputs of the groups first .. last touched
+                const CallGroup* g0 = &p.group_of_callout(callout_index(h0));
+                const CallGroup* g1 = &p.group_of_callout(callout_index(h_last));
+                for (const CallGroup* g = g0; g <= g1; g++) cg.depth = std::max(cg.depth, g->depth + 1);
+            } else {
+                const uint8_t* kind = p.kind.data();
+                uint8_t worst = kind[h0];
+                if (st != 0)
+                    for (uint64_t c = 0, h = h0; c < n; c++, h += st) worst = std::max(worst, kind[h]);
+                if (worst > V_WITNESS) return false;
+            }
+            cg.in_base.push_back(h0);
+            cg.in_stride.push_back(st);
+        }
+        if (p.n_total_values() + n_new >= c->max_values || (uint64_t)p.n_callouts + n_new >= kMaxCallouts) return false;  // the gate-by-gate loop reports the limit
+        step(n * (1 + f.body->size()));
+        // ---- commit: the outputs are implicit values (program.h), only the scope learns about them
+        c->max_values = std::min<uint64_t>(c->max_values, kCalloutBit - 256);  // explicit handles stay below the callout space
+        cg.first_callout = p.n_callouts;
+        const uint32_t h_first = kCalloutBit | cg.first_callout;
+        if (plain_scope && scope.ensure_dense(out_last, n_new)) {
+            uint32_t* d = scope.dense.data();
+            for (uint32_t k = 0; k < t.n_out; k++) {
+                uint32_t h = h_first + k;
+                for (uint64_t c = 0, w = wo[k].w0; c < n; c++, w += S, h += t.n_out) d[w] = h;
+            }
+            scope.bulk_inserted(n_new);
+        } else {
+            for (uint64_t c = 0; c < n; c++)
+                for (uint32_t k = 0; k < t.n_out; k++) set(scope, wo[k].w0 + S * c, h_first + (uint32_t)(c * t.n_out + k));
+        }
+        p.n_callouts += (uint32_t)n_new;
+        for (int k = 0; k < CB_KINDS; k++) p.cb_count[k] += n * t.cb[k];
+        p.ir_gates += n * t.ir_gates;
+        p.groups.push_back(std::move(cg));
+        return true;
+    }
+
     void call_function(const FunctionDecl& f, const std::vector<uint64_t>& outs, const std::vector<uint64_t>& ins, Scope& scope,
                        Iters& fresh, Queue& instances, Queue& witnesses, const uint32_t* weight) {
         if (f.n_local) ingest_simple_function(f, outs, ins, scope, weight);
@@ -369,9 +608,43 @@ struct zkb_evaluator {
         Scope* ns = new_scope();
         depth++;
         try {
-            for (size_t idx = 0; idx < ins.size(); idx++) set(*ns, idx + outs.size(), prog().copy(get(scope, ins[idx])));
+            // Long input / output lists (a loop body handed a whole block of wires) are moved table to table; whatever the
+            // fast loops cannot take — an unbound input, an output that is already bound, ids outside the dense tables —
+            // is left to the one-by-one code below, which reports it as the reference does.
+            Program& p = prog();
+            const size_t n_in = ins.size(), n_out = outs.size();
+            size_t idx = 0;
+            if (n_in >= 32 && !p.keep_copies && scope.sparse.empty() && ns->ensure_dense(n_out + n_in - 1, n_in)) {
+                const uint32_t* src = scope.dense.data();
+                const uint64_t sn = scope.dense.size();
+                uint32_t* dst = ns->dense.data() + n_out;  // a fresh scope: nothing is bound
+                for (; idx < n_in; idx++) {
+                    const uint64_t id = ins[idx];
+                    if (id >= sn || src[id] == Scope::kNone) break;
+                    dst[idx] = src[id];
+                }
+                p.cb_count[CB_COPY] += idx;
+                ns->bulk_inserted(idx);
+            }
+            for (; idx < n_in; idx++) set(*ns, idx + n_out, p.copy(get(scope, ins[idx])));
             for (const auto& g : sub) ingest_gate(g, consts, *ns, iters, instances, witnesses, weight);
-            for (size_t idx = 0; idx < outs.size(); idx++) set(scope, outs[idx], prog().copy(get(*ns, idx)));
+            idx = 0;
+            if (n_out >= 32 && !p.keep_copies && scope.sparse.empty() && ns->sparse.empty() && n_out <= ns->dense.size()) {
+                uint64_t hi = 0;
+                for (size_t k = 0; k < n_out; k++) hi = std::max(hi, outs[k]);
+                if (scope.ensure_dense(hi, n_out)) {
+                    const uint32_t* src = ns->dense.data();
+                    uint32_t* dst = scope.dense.data();
+                    for (; idx < n_out; idx++) {
+                        const uint64_t id = outs[idx];
+                        if (src[idx] == Scope::kNone || dst[id] != Scope::kNone) break;
+                        dst[id] = src[idx];
+                    }
+                    p.cb_count[CB_COPY] += idx;
+                    scope.bulk_inserted(idx);
+                }
+            }
+            for (; idx < n_out; idx++) set(scope, outs[idx], p.copy(get(*ns, idx)));
         } catch (...) {
             depth--;
             release_scope(ns);
@@ -385,7 +658,7 @@ struct zkb_evaluator {
     void ingest_gate(const ir::Gate& g, const std::vector<std::vector<uint8_t>>& consts, Scope& scope, Iters& iters,
                      Queue& instances, Queue& witnesses, const uint32_t* weight) {
         Program& p = prog();
-        if (p.n_values() >= c->max_values) throw EvalErr{"zkb: resource limit exceeded (max_values)"};
+        if (p.n_total_values() >= c->max_values) throw EvalErr{"zkb: resource limit exceeded (max_values)"};
         step();
         switch (g.type) {
             case ir::G_CONSTANT: {  // :345-348
@@ -477,6 +750,23 @@ struct zkb_evaluator {
                 if (!cx.body_is_anon) {
                     auto it = known_functions.find(cx.fn_name);
                     if (it != known_functions.end()) callee = &it->second;
+                }
+                // the For gate lists its outputs: the scope's table is sized once for the loop (same memory bound as
+                // one-by-one insertion) instead of doubling its way up while the iterations bind them
+                {
+                    uint64_t hi = 0, cnt = 0;
+                    for (const auto& el : cx.outputs) {
+                        const uint64_t top = el.is_range ? el.last : el.first;
+                        if (top >= el.first && top - el.first < (1ull << 32)) {
+                            hi = std::max(hi, top);
+                            cnt += top - el.first + 1;
+                        }
+                    }
+                    if (cnt >= 1024 && scope.sparse.empty()) scope.ensure_dense(hi, cnt);
+                }
+                if (callee && try_call_group(cx, *callee, scope, iters, weight)) {  // the whole loop as one call group
+                    iters_remove(iters, cx.name);
+                    break;
                 }
                 Iters fresh;
                 for (uint64_t i = cx.first; i <= cx.last; i++) {
@@ -973,7 +1263,9 @@ struct zkb_evaluator {
         if (!p.field_set || p.n_values() == 0) return ZKB_OK;
         if (!c->finalized) {
             c->live_values.clear();
-            values.for_each([&](uint64_t, uint32_t v) { c->live_values.push_back(v); });
+            values.for_each([&](uint64_t, uint32_t v) {
+                if (!is_callout(v)) c->live_values.push_back(v);  // group outputs (implicit values) are always kept
+            });
             int rc = ctx_finalize(c, 0);
             if (rc != ZKB_OK) return fail(rc, c->err);
         }

@@ -719,6 +719,76 @@ k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
     }
 }
 
+// Call groups (program.h): thread <-> (call, 32-witness word).  A call's inputs are read from the wire store into a register
+// file held in shared memory (register r of thread t at regs[r * blockDim + t]: conflict-free), the body of the function runs
+// over it op by op — every thread of a warp interprets the same template, so the op fetches are broadcasts — and only the
+// call's outputs go back to the wire store: the locals of a call never touch memory, and one 96-byte GroupDesc stands for
+// n_calls x |body| gates instead of one 16-byte GateOp each.
+__global__ void __launch_bounds__(256)
+k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t total_calls, const TmplOp* __restrict__ tops,
+              const uint32_t* __restrict__ tables, uint32_t* __restrict__ store, const uint32_t* __restrict__ const_bits,
+              uint32_t log2_words) {
+    extern __shared__ uint32_t s_regs[];
+    __shared__ uint32_t s_g0;
+    const uint32_t B = blockDim.x;
+    uint32_t* R = s_regs + threadIdx.x;
+    const uint64_t total = total_calls << log2_words;
+    const uint64_t n_tiles = (total + B - 1) / B;
+    const uint32_t wmask = (1u << log2_words) - 1;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * B;
+        if (threadIdx.x == 0) {  // the group holding the block's first call: the last one whose first_call is <= it
+            const uint32_t c0 = (uint32_t)(t0 >> log2_words);
+            uint32_t lo = 0, hi = n_groups;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&descs[mid].first_call) <= c0) lo = mid;
+                else hi = mid;
+            }
+            s_g0 = lo;
+        }
+        __syncthreads();
+        uint32_t gi = s_g0;
+        __syncthreads();
+        const uint64_t tid = t0 + threadIdx.x;
+        if (tid >= total) continue;
+        const uint32_t call_g = (uint32_t)(tid >> log2_words), word = (uint32_t)tid & wmask;
+        while (gi + 1 < n_groups && call_g >= __ldg(&descs[gi + 1].first_call)) gi++;
+        const GroupDesc* d = descs + gi;
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(d));      // tmpl_off, n_ops, n_out, n_in
+        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);  // n_calls, out_slot, first_call, pad
+        const uint32_t call = call_g - h1.z;
+        for (uint32_t k = 0; k < h0.w; k++) {
+            const uint32_t base = __ldg(&d->in_base[k]), st = __ldg(&d->in_stride[k]);
+            const uint32_t slot = st == kTableStride ? __ldg(tables + base + call) : base + st * call;
+            R[(h0.z + k) * B] = store[((size_t)slot << log2_words) + word];
+        }
+        const uint2* op = reinterpret_cast<const uint2*>(tops) + h0.x;
+        for (uint32_t i = 0; i < h0.y; i++) {
+            const uint2 o = __ldg(op + i);  // kind | dst << 8 | a << 16, b
+            const uint32_t kind = o.x & 0xff, dst = (o.x >> 8) & 0xff, ra = (o.x >> 16) & 0xff;
+            uint32_t r;
+            if (kind == V_CONST) {
+                r = 0u - (__ldg(const_bits + o.y) & 1);
+            } else {
+                const uint32_t a = R[ra * B];
+                switch (kind) {
+                    case V_ADD:
+                    case V_XOR: r = a ^ R[o.y * B]; break;
+                    case V_MUL:
+                    case V_AND: r = a & R[o.y * B]; break;
+                    case V_ADDC: r = a ^ (0u - (__ldg(const_bits + o.y) & 1)); break;
+                    case V_MULC: r = a & (0u - (__ldg(const_bits + o.y) & 1)); break;
+                    default: r = ~a; break;  // V_NOT
+                }
+            }
+            R[dst * B] = r;
+        }
+        const size_t out0 = (size_t)h1.y + (size_t)call * h0.z;
+        for (uint32_t k = 0; k < h0.z; k++) store[((out0 + k) << log2_words) + word] = R[k * B];
+    }
+}
+
 __global__ void k_bool_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
                                    uint32_t log2_wt, uint32_t* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -969,6 +1039,21 @@ void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, 
         unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, grid_per_sm(256));
         k_bool_level<1><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g);
     }
+}
+
+void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const TmplOp* tops, const uint32_t* tables,
+                        uint32_t* store, const uint32_t* const_bits, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s) {
+    if (n_groups == 0 || total_calls == 0) return;
+    static bool attr_set = false;
+    const size_t smem = (size_t)n_regs * 256 * sizeof(uint32_t);
+    if (!attr_set && smem > 48 * 1024) {
+        cudaFuncSetAttribute(k_bool_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * 256 * sizeof(uint32_t)));
+        attr_set = true;
+    }
+    const uint64_t total = total_calls << (g.log2_wt - 5);
+    const uint64_t tiles = (total + 255) / 256;
+    const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sm_count * 64);
+    k_bool_groups<<<grid, 256, smem, s>>>(descs, n_groups, total_calls, tops, tables, store, const_bits, g.log2_wt - 5);
 }
 
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,

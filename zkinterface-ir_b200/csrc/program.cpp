@@ -199,7 +199,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     constexpr uint32_t kAhead = 16;  // operands are random earlier values: start their loads a few iterations early
     for (uint32_t v = 0; v < n; v++) {
         if (v + kAhead < n) {
-            __builtin_prefetch(&level[opa[v + kAhead]]);
+            __builtin_prefetch(&level[opa[v + kAhead] < n ? opa[v + kAhead] : 0]);
             __builtin_prefetch(&level[opb[v + kAhead] < n ? opb[v + kAhead] : 0]);
         }
         uint8_t k = kind[v];
@@ -207,10 +207,14 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             level[v] = 0;
             continue;
         }
-        uint32_t la = level[opa[v]];
-        used[opa[v]] = 1;
+        // a group output (implicit value, program.h) is ready before the first wavefront, like an input, and always stored
+        uint32_t la = 0;
+        if (!is_callout(opa[v])) {
+            la = level[opa[v]];
+            used[opa[v]] = 1;
+        }
         bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
-        if (two) {
+        if (two && !is_callout(opb[v])) {
             uint32_t lb = level[opb[v]];
             used[opb[v]] = 1;
             if (lb > la) la = lb;
@@ -218,12 +222,37 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         level[v] = la + 1;
         if (la + 1 > max_level) max_level = la + 1;
     }
+    // what a call group reads is consumed (stored); groups only read level-0 values, so nothing else changes
+    // (the loops of a nest usually read the same progressions: each distinct one is walked once)
+    struct Progression {
+        uint32_t base, stride, n;
+        bool operator==(const Progression& o) const { return base == o.base && stride == o.stride && n == o.n; }
+    };
+    struct ProgressionHash {
+        size_t operator()(const Progression& p) const { return ((size_t)p.base * 0x9E3779B97F4A7C15ull) ^ ((size_t)p.stride << 32) ^ p.n; }
+    };
+    std::unordered_map<Progression, std::pair<uint32_t, uint32_t>, ProgressionHash> progressions;  // -> (slot stride | kTableStride, table offset)
+    for (const CallGroup& cg : prog.groups)
+        for (size_t k = 0; k < cg.in_base.size(); k++) {
+            const uint32_t b = cg.in_base[k], st = cg.in_stride[k];
+            if (is_callout(b)) continue;
+            if (!progressions.emplace(Progression{b, st, st ? cg.n_calls : 1}, std::make_pair(0u, 0u)).second) continue;
+            if (st == 0) used[b] = 1;
+            else for (uint32_t c = 0; c < cg.n_calls; c++) used[b + st * c] = 1;
+        }
     lap("levels");
     // earliest assert per value (a value that is non-zero fails at its first assert)
     std::vector<uint32_t> aseq(n, kNoSeq);
+    callout_assert_seq.clear();
+    callout_assert_value.clear();
     for (size_t s = 0; s < prog.asserts.size(); s++) {
         uint32_t v = prog.asserts[s].value;
-        if (aseq[v] == kNoSeq) aseq[v] = (uint32_t)s;  // asserts are in program order: first wins
+        if (is_callout(v)) {  // AssertZero directly on a group output: a standalone test in wavefront 1
+            callout_assert_seq.push_back((uint32_t)s);
+            callout_assert_value.push_back(v);
+        } else if (aseq[v] == kNoSeq) {
+            aseq[v] = (uint32_t)s;  // asserts are in program order: first wins
+        }
     }
     std::vector<uint8_t> observable;
     if (!keep_all) {
@@ -233,7 +262,8 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             uint8_t* obs = observable.data();
             parallel_chunks(live_values->size() >= (1u << 18) ? T : 1, live_values->size(),
                             [&](unsigned, uint64_t b, uint64_t e) {
-                                for (uint64_t i = b; i < e; i++) obs[lv[i]] = 1;
+                                for (uint64_t i = b; i < e; i++)
+                                    if (!is_callout(lv[i])) obs[lv[i]] = 1;
                             });
         }
     }
@@ -242,11 +272,11 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     input_assert_seq.clear();
     input_assert_value.clear();
     for (uint32_t v = 0; v < n; v++)
-        if (kind[v] <= V_WITNESS && aseq[v] != kNoSeq) {
+        if (aseq[v] != kNoSeq && kind[v] <= V_WITNESS) {
             input_assert_seq.push_back(aseq[v]);
             input_assert_value.push_back(v);
         }
-    if (!input_assert_seq.empty() && max_level < 1) max_level = 1;
+    if (!(input_assert_seq.empty() && callout_assert_seq.empty()) && max_level < 1) max_level = 1;
     n_levels = max_level;
 
     lap("asserts/observable");
@@ -263,7 +293,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint64_t> cnt(n_keys + 1, 0);
     for (unsigned t = 0; t < Tsort; t++)
         for (size_t k = 0; k < n_keys; k++) cnt[k + 1] += hist[t][k];
-    cnt[(size_t)0 * D_OPS + D_ASSERT + 1] += input_assert_seq.size();
+    cnt[(size_t)0 * D_OPS + D_ASSERT + 1] += input_assert_seq.size() + callout_assert_seq.size();
     for (size_t i = 0; i < n_keys; i++) cnt[i + 1] += cnt[i];
     const uint64_t n_ops = cnt[n_keys];
     level_off.assign((size_t)n_levels + 1, 0);
@@ -285,13 +315,13 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         parallel_chunks(T, n, [&](unsigned, uint64_t b, uint64_t e) {  // a maximum: order of the updates is irrelevant
             for (uint64_t v = b; v < e; v++) {
                 if (v + kAhead < e) {
-                    __builtin_prefetch(&lu[opa[v + kAhead]], 1);
+                    __builtin_prefetch(&lu[opa[v + kAhead] < n ? opa[v + kAhead] : 0], 1);
                     __builtin_prefetch(&lu[opb[v + kAhead] < n ? opb[v + kAhead] : 0], 1);
                 }
                 uint8_t k = kind[v];
                 if (k <= V_WITNESS) continue;
-                atomic_max_u32(&lu[opa[v]], level[v]);
-                if (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR) atomic_max_u32(&lu[opb[v]], level[v]);
+                if (!is_callout(opa[v])) atomic_max_u32(&lu[opa[v]], level[v]);
+                if ((k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR) && !is_callout(opb[v])) atomic_max_u32(&lu[opb[v]], level[v]);
             }
         });
         for (uint32_t v : input_assert_value)
@@ -323,6 +353,11 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             if (reuse && last_use[v] != kForever) release_after[last_use[v]].push(next_slot, kInputWriter);
             next_slot++;
         }
+    // group outputs follow the inputs (whose slots stay 0 .. n_loads - 1: the raw-value flags are indexed by them), in index
+    // order; they are never released
+    callout_slot0 = next_slot;
+    n_callouts = prog.n_callouts;
+    next_slot += prog.n_callouts;
     // slots must follow the sorted order, so ops are walked by position: value_at[position] = value
     std::vector<uint32_t> value_at(n_ops, kNoSlot);
     {
@@ -457,7 +492,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                     }
                     uint32_t v1 = value_at[i + kAhead];
                     if (v1 != kNoSlot) {
-                        __builtin_prefetch(&slot_of_value[opa[v1]]);
+                        if (opa[v1] < n) __builtin_prefetch(&slot_of_value[opa[v1]]);
                         if (opb[v1] < n) __builtin_prefetch(&slot_of_value[opb[v1]]);
                     }
                 }
@@ -466,20 +501,22 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                 uint8_t k = kind[v];
                 GateOp g;
                 g.meta = meta_of[i];
-                g.a = slot_of_value[opa[v]];
+                g.a = slot_of(opa[v]);
                 bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
-                g.b = two ? slot_of_value[opb[v]] : opb[v];
+                g.b = two ? slot_of(opb[v]) : opb[v];
                 g.out = slot_of_value[v];
-                if (k == V_NOT && kind[opa[v]] <= V_WITNESS) {  // not(input): the reference tests the RAW integer
+                const bool a_in = !is_callout(opa[v]) && kind[opa[v]] <= V_WITNESS;
+                if (k == V_NOT && a_in) {  // not(input): the reference tests the RAW integer
                     g.meta |= F_RAW;
                     dc[D_OPS]++;
                 }
                 // and / xor act on the integers the reference holds: an input operand >= p takes part unreduced
                 // (evaluator.rs:924-930).  Mod 2 only the low bit matters, residues are exact there.
-                if ((k == V_AND || k == V_XOR) && !prog.binary && (kind[opa[v]] <= V_WITNESS || kind[opb[v]] <= V_WITNESS)) {
-                    if (kind[opa[v]] <= V_WITNESS) g.meta |= F_RAW;
-                    if (kind[opb[v]] <= V_WITNESS) g.meta |= F_RAWB;
-                    dc[D_OPS]++;
+                if ((k == V_AND || k == V_XOR) && !prog.binary) {
+                    const bool b_in = !is_callout(opb[v]) && kind[opb[v]] <= V_WITNESS;
+                    if (a_in) g.meta |= F_RAW;
+                    if (b_in) g.meta |= F_RAWB;
+                    if (a_in || b_in) dc[D_OPS]++;
                 }
                 ops[i] = g;
                 op_assert_seq[i] = aseq[v];
@@ -503,6 +540,82 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             ops[p] = g;
             op_assert_seq[p] = input_assert_seq[i];
             n_dev_ops[D_ASSERT]++;
+        }
+        for (size_t i = 0; i < callout_assert_seq.size(); i++, p++) {  // a group output is a reduced value: no raw flag
+            GateOp g;
+            g.meta = D_ASSERT | F_ASSERT | F_NOSTORE;
+            g.a = slot_of(callout_assert_value[i]);
+            g.b = 0;
+            g.out = kNoSlot;
+            ops[p] = g;
+            op_assert_seq[p] = callout_assert_seq[i];
+            n_dev_ops[D_ASSERT]++;
+        }
+    }
+    // call groups -> device descriptors, launch order = depth order (stable inside a depth)
+    group_descs.clear();
+    group_ops.clear();
+    group_tables.clear();
+    depth_off.clear();
+    group_regs = 0;
+    if (!prog.groups.empty()) {
+        std::vector<uint32_t> tmpl_off(prog.templates.size());
+        for (size_t t = 0; t < prog.templates.size(); t++) {
+            group_regs = std::max(group_regs, prog.templates[t].n_regs);
+            tmpl_off[t] = (uint32_t)group_ops.size();
+            group_ops.insert(group_ops.end(), prog.templates[t].ops.begin(), prog.templates[t].ops.end());
+        }
+        uint32_t max_depth = 0;
+        for (const CallGroup& cg : prog.groups) max_depth = std::max(max_depth, cg.depth);
+        depth_off.assign((size_t)max_depth + 2, 0);
+        for (const CallGroup& cg : prog.groups) depth_off[cg.depth + 1]++;
+        for (size_t d = 0; d + 1 < depth_off.size(); d++) depth_off[d + 1] += depth_off[d];
+        std::vector<uint32_t> cursor(depth_off.begin(), depth_off.end() - 1), calls_before((size_t)max_depth + 1, 0);
+        group_descs.resize(prog.groups.size());
+        for (const CallGroup& cg : prog.groups) {
+            const Template& tp = prog.templates[cg.tmpl];
+            GroupDesc gd{};
+            gd.tmpl_off = tmpl_off[cg.tmpl];
+            gd.n_ops = (uint32_t)tp.ops.size();
+            gd.n_out = tp.n_out;
+            gd.n_in = tp.n_in;
+            gd.n_calls = cg.n_calls;
+            gd.out_slot = callout_slot0 + cg.first_callout;
+            gd.first_call = calls_before[cg.depth];
+            calls_before[cg.depth] += cg.n_calls;
+            for (uint32_t k = 0; k < tp.n_in; k++) {
+                const uint32_t b = cg.in_base[k], st = cg.in_stride[k];
+                if (is_callout(b)) {  // outputs of earlier groups: consecutive indices are consecutive slots
+                    gd.in_base[k] = slot_of(b);
+                    gd.in_stride[k] = st;
+                    continue;
+                }
+                const uint32_t s0 = slot_of_value[b];
+                auto& memo = progressions[Progression{b, st, st ? cg.n_calls : 1}];  // (slot stride + 1 | 0: not looked at yet, table)
+                if (memo.first == 0) {
+                    bool affine = true;
+                    uint32_t sst = 0;
+                    if (cg.n_calls > 1 && st != 0) {
+                        sst = slot_of_value[b + st] - s0;
+                        for (uint32_t c = 2; c < cg.n_calls && affine; c++) affine = slot_of_value[b + st * c] == s0 + sst * c;
+                    }
+                    if (affine && sst < kTableStride - 1) {
+                        memo.first = sst + 1;
+                    } else {  // one table per distinct progression, shared by the groups that read it
+                        memo.first = kTableStride;
+                        memo.second = (uint32_t)group_tables.size();
+                        for (uint32_t c = 0; c < cg.n_calls; c++) group_tables.push_back(slot_of_value[b + st * c]);
+                    }
+                }
+                if (memo.first != kTableStride) {
+                    gd.in_base[k] = s0;
+                    gd.in_stride[k] = memo.first - 1;
+                } else {
+                    gd.in_base[k] = memo.second;
+                    gd.in_stride[k] = kTableStride;
+                }
+            }
+            group_descs[cursor[cg.depth]++] = gd;
         }
     }
     lap("emit");

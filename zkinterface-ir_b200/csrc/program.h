@@ -35,7 +35,46 @@ enum ValKind : uint8_t {
     V_XOR,
     V_NOT,
     V_COPY,  // only recorded in flatten mode (Program::keep_copies); otherwise a copy is an alias
+    V_CALLOUT,  // output of a call group (below); never stored in Program::kind — such values have implicit handles
     V_KINDS
+};
+
+// ---- loop-structured recording ---------------------------------------------
+// A For loop whose body is a call of a plain named function, with iterator expressions affine in the loop variable and
+// inputs that exist before the loop, is n_calls runs of one small straight-line program over affinely moving operands.
+// Instead of n_calls x |body| SSA values and as many 16-byte device descriptors, the Program keeps the body ONCE (a
+// Template: register-to-register ops, registers = outputs, inputs, locals as in the function's own wire numbering) and one
+// CallGroup per loop execution; only the calls' OUTPUTS become SSA values, because only they can be named by later gates —
+// the locals of a call die with its scope (evaluator.rs:698-746).  Those outputs are IMPLICIT values: handle =
+// kCalloutBit | index, indices handed out consecutively (call c, output k of a group: first_callout + c * n_out + k), no
+// entry in kind / opa / opb, wavefront 0, slot = Plan::callout_slot0 + index, always stored and readable — so neither the
+// recorder nor the levelizer does any per-output work (C5: 2^24 outputs of 2^23 calls).  The device expands a group
+// inside one kernel, every call's locals living in registers (kernels.cu: k_bool_groups).
+constexpr uint32_t kCalloutBit = 0x80000000u;
+constexpr uint32_t kMaxCallouts = 0x7FFFFF00u;
+inline bool is_callout(uint32_t h) { return (h & kCalloutBit) != 0; }  // (Scope::kNone has the bit too: test it first)
+inline uint32_t callout_index(uint32_t h) { return h & ~kCalloutBit; }
+struct TmplOp {       // 8 bytes
+    uint8_t kind;     // ValKind: V_CONST (b = const-pool index), V_ADD, V_MUL, V_ADDC / V_MULC (b = const-pool index), V_AND, V_XOR, V_NOT
+    uint8_t dst;      // register written
+    uint8_t a;        // register read
+    uint8_t pad;
+    uint32_t b;       // register read (two-input ops) or const-pool index
+};
+struct Template {
+    uint32_t n_out = 0, n_in = 0, n_regs = 0;
+    std::vector<TmplOp> ops;
+    uint64_t cb[12] = {0};   // callbacks one call makes, by CbKind (copies of the inputs and outputs included)
+    uint64_t ir_gates = 0;
+    uint64_t n_two = 0, n_one = 0;  // two-input / one-input value gates (algorithmic bytes)
+};
+struct CallGroup {
+    uint32_t tmpl = 0;
+    uint32_t n_calls = 0;
+    uint32_t first_callout = 0;  // index of output 0 of call 0; call c, output k is first_callout + c * n_out + k
+    uint32_t depth = 0;        // 0: reads input values only; d: reads outputs of groups of depth < d as well
+    std::vector<uint32_t> in_base, in_stride;  // per input position: handle of call c's input = base + stride * c
+    uint32_t n_out = 0;
 };
 
 // callback counters (one per ZKBackend method that the Evaluator drives)
@@ -62,6 +101,24 @@ struct AssertRec {
     uint32_t value;     // asserted SSA value
     uint32_t pos;       // number of SSA values recorded before it (program position)
     uint64_t src_wire;  // local-scope wire id of the AssertZero gate (evaluator.rs:357-362)
+};
+
+// Device form of a call group: thread <-> (call, witness word).  An operand's slot is base + stride * call, or — when the
+// slots the plan gave the input values are not an arithmetic progression — table[base + call] (stride == kTableStride).
+constexpr uint32_t kMaxGroupInputs = 8;
+constexpr uint32_t kMaxTemplateRegs = 48;
+constexpr uint32_t kMaxTemplateOps = 128;
+constexpr uint32_t kTableStride = 0xFFFFFFFFu;
+struct GroupDesc {  // 16-byte aligned
+    uint32_t tmpl_off;   // first op of the template in the op array
+    uint32_t n_ops;
+    uint32_t n_out, n_in;
+    uint32_t n_calls;
+    uint32_t out_slot;   // slot of output 0 of call 0; outputs are consecutive slots
+    uint32_t first_call; // calls of the groups before this one in the same launch (prefix sum: thread -> group search)
+    uint32_t pad;
+    uint32_t in_base[kMaxGroupInputs];
+    uint32_t in_stride[kMaxGroupInputs];
 };
 
 struct InputLoad {  // level-0 values: filled by the input kernel on every pass
@@ -99,6 +156,22 @@ public:
     std::unordered_map<std::string, uint32_t> const_index;
     uint32_t n_consts() const { return (uint32_t)const_unreduced.size(); }
     uint32_t intern_const(const uint8_t* le, size_t n);
+
+    std::vector<Template> templates;
+    std::vector<CallGroup> groups;  // ascending first_callout
+    uint32_t n_callouts = 0;
+    uint64_t n_total_values() const { return (uint64_t)kind.size() + n_callouts; }
+    bool valid_handle(uint64_t h) const { return h < kind.size() || (h >= kCalloutBit && h - kCalloutBit < n_callouts); }
+    // the group whose outputs include callout index i
+    const CallGroup& group_of_callout(uint32_t i) const {
+        size_t lo = 0, hi = groups.size();
+        while (hi - lo > 1) {
+            const size_t mid = (lo + hi) / 2;
+            if (groups[mid].first_callout <= i) lo = mid;
+            else hi = mid;
+        }
+        return groups[lo];
+    }
 
     uint32_t n_values() const { return (uint32_t)kind.size(); }
     uint32_t push_value(uint8_t k, uint32_t a, uint32_t b) {
@@ -203,6 +276,17 @@ struct Plan {
     // raw-semantics bookkeeping (SURVEY.md §8a trap 1): asserts applied directly to an input value
     std::vector<uint32_t> input_assert_seq;    // assert seq ...
     std::vector<uint32_t> input_assert_value;  // ... on this level-0 SSA value
+    // call groups, in launch order: depth_off[d] .. depth_off[d + 1] are the groups of depth d (one launch each, between the
+    // input kernel and the first wavefront)
+    std::vector<GroupDesc> group_descs;
+    std::vector<TmplOp> group_ops;
+    std::vector<uint32_t> group_tables;
+    std::vector<uint32_t> depth_off;
+    uint32_t group_regs = 0;  // registers of the widest template
+    uint32_t callout_slot0 = 0, n_callouts = 0;  // group outputs: slot of implicit value i = callout_slot0 + i
+    uint32_t slot_of(uint32_t h) const { return is_callout(h) ? callout_slot0 + callout_index(h) : slot_of_value[h]; }
+    bool is_readable(uint32_t h) const { return is_callout(h) || readable[h]; }
+    std::vector<uint32_t> callout_assert_seq, callout_assert_value;  // AssertZero directly on a group output: tested in wavefront 1
     // accounting for bench.py (algorithmic bytes per witness)
     uint64_t n_dev_ops[D_OPS] = {0};
     uint64_t algo_bytes_per_witness = 0;
