@@ -226,3 +226,4 @@ if __name__ == "__main__":
     if "c5" in todo:
         print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 1)), flush=True)
         print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 64)), flush=True)
+        print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 128 if a.small else 4096)), flush=True)

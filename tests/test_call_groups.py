@@ -333,7 +333,7 @@ def test_gpu_failing_assertion_on_a_group_output(seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_batch", [1, 33, 64, 100, 300])
+@pytest.mark.parametrize("n_batch", [1, 33, 64, 100, 128, 300, 1000])
 def test_gpu_batches_bit_sliced(n_batch):
     """one recording, n_batch witnesses (ragged last word / tile): verdict per witness and probed values vs the oracle"""
     r = build(7, failing=True)

@@ -50,7 +50,8 @@ int ctx_upload_groups(zkb_ctx* c) {
     int rc;
     if ((rc = upload_vec(c, c->d_group_descs, c->plan.group_descs)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_group_ops, c->plan.group_ops)) != ZKB_OK) return rc;
-    return upload_vec(c, c->d_group_tables, c->plan.group_tables);
+    if ((rc = upload_vec(c, c->d_group_tables, c->plan.group_tables)) != ZKB_OK) return rc;
+    return upload_vec(c, c->d_group_hints, c->plan.group_hints);
 }
 
 int ctx_finalize(zkb_ctx* c, int keep_values) {
@@ -155,6 +156,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_group_descs);
         cudaFree(c->d_group_ops);
         cudaFree(c->d_group_tables);
+        cudaFree(c->d_group_hints);
         cudaFree(c->d_const_flags);
         cudaFree(c->d_const_raw);
         cudaFree(c->d_rawflag);
@@ -524,8 +526,8 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         const uint32_t lo = pl.depth_off[d], hi = pl.depth_off[d + 1];
         if (hi == lo) continue;
         const uint64_t calls = (uint64_t)pl.group_descs[hi - 1].first_call + pl.group_descs[hi - 1].n_calls;
-        launch_bool_groups(c->d_group_descs + lo, hi - lo, calls, c->d_group_ops, c->d_group_tables, c->d_store, c->d_consts, g,
-                           pl.group_regs, c->sm_count, c->stream);
+        launch_bool_groups(c->d_group_descs + lo, hi - lo, calls, c->d_group_ops, c->d_group_tables, c->d_group_hints + pl.hint_off[d],
+                           c->d_store, g, pl.group_regs, c->sm_count, c->stream);
         (*launches)++;
         if (level_launches) (*level_launches)++;
     }
@@ -848,7 +850,8 @@ extern "C" int zkb_debug_plan_hash(zkb_ctx* c, uint64_t* out) {
     mix(pl.level_off.data(), pl.level_off.size() * 8);
     mix(pl.level_rare.data(), pl.level_rare.size() * 8);
     mix(pl.group_descs.data(), pl.group_descs.size() * sizeof(GroupDesc));
-    mix(pl.group_ops.data(), pl.group_ops.size() * sizeof(TmplOp));
+    mix(pl.group_ops.data(), pl.group_ops.size() * sizeof(GroupOp));
+    mix(pl.group_hints.data(), pl.group_hints.size() * 4);
     mix(pl.group_tables.data(), pl.group_tables.size() * 4);
     mix(&pl.callout_slot0, 4);
     mix(&pl.n_callouts, 4);

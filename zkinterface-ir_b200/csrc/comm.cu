@@ -223,7 +223,7 @@ struct ReplicaHeader {
     uint64_t cb_count[CB_KINDS];
     uint64_t n_dev_ops[D_OPS];
     uint64_t modulus_len, pending_len, const_raw_bytes;
-    uint64_t n_group_descs, n_group_ops, n_group_tables, n_depth_off, group_regs, callout_slot0, n_callouts;  // call groups (program.h)
+    uint64_t n_group_descs, n_group_ops, n_group_tables, n_depth_off, group_regs, callout_slot0, n_callouts, n_group_hints;  // call groups (program.h)
     uint32_t n_slots, max_level_ops, n_instance, n_witness;
     uint32_t nlimb, binary, is_boolean, has_pending, keep_all, const_raw_stride, has_const_flags, pad;
     FieldParams fp;
@@ -323,6 +323,7 @@ static int broadcast_program(zkb_ctx* c, int root) {
         h.n_group_ops = pl.group_ops.size();
         h.n_group_tables = pl.group_tables.size();
         h.n_depth_off = pl.depth_off.size();
+        h.n_group_hints = pl.group_hints.size();
         h.group_regs = pl.group_regs;
         h.callout_slot0 = pl.callout_slot0;
         h.n_callouts = pl.n_callouts;
@@ -330,6 +331,8 @@ static int broadcast_program(zkb_ctx* c, int root) {
         put(blob, pl.group_ops.data(), pl.group_ops.size());
         put(blob, pl.group_tables.data(), pl.group_tables.size());
         put(blob, pl.depth_off.data(), pl.depth_off.size());
+        put(blob, pl.group_hints.data(), pl.group_hints.size());
+        put(blob, pl.hint_off.data(), pl.hint_off.size());
         h.blob_bytes = blob.size();
     }
     // 1. the fixed-size header
@@ -382,6 +385,8 @@ static int broadcast_program(zkb_ctx* c, int root) {
         get(cur, pl.group_ops, h.n_group_ops);
         get(cur, pl.group_tables, h.n_group_tables);
         get(cur, pl.depth_off, h.n_depth_off);
+        get(cur, pl.group_hints, h.n_group_hints);
+        get(cur, pl.hint_off, h.n_depth_off);
         pl.group_regs = (uint32_t)h.group_regs;
         pl.callout_slot0 = (uint32_t)h.callout_slot0;
         pl.n_callouts = (uint32_t)h.n_callouts;

@@ -161,8 +161,9 @@ struct zkb_ctx {
     uint32_t* d_consts = nullptr;
     uint64_t* d_level_off = nullptr;
     zkb::GroupDesc* d_group_descs = nullptr;  // call groups (program.h), launch order
-    zkb::TmplOp* d_group_ops = nullptr;
+    zkb::GroupOp* d_group_ops = nullptr;
     uint32_t* d_group_tables = nullptr;
+    uint32_t* d_group_hints = nullptr;
     uint8_t* d_const_flags = nullptr;   // per constant: raw value >= p
     uint8_t* d_const_raw = nullptr;     // raw bytes of the constants (const_raw_stride each), when a bitwise gate may need them
     uint32_t const_raw_stride = 0;

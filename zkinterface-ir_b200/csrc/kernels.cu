@@ -720,72 +720,57 @@ k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
 }
 
 // Call groups (program.h): thread <-> (call, 32-witness word).  A call's inputs are read from the wire store into a register
-// file held in shared memory (register r of thread t at regs[r * blockDim + t]: conflict-free), the body of the function runs
-// over it op by op — every thread of a warp interprets the same template, so the op fetches are broadcasts — and only the
-// call's outputs go back to the wire store: the locals of a call never touch memory, and one 96-byte GroupDesc stands for
-// n_calls x |body| gates instead of one 16-byte GateOp each.
-__global__ void __launch_bounds__(256)
-k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t total_calls, const TmplOp* __restrict__ tops,
-              const uint32_t* __restrict__ tables, uint32_t* __restrict__ store, const uint32_t* __restrict__ const_bits,
+// file held in shared memory (register r of thread t at (r * 256 + t) * 4: conflict-free), the body of the function runs
+// over it op by op — every thread of a warp interprets the same pre-decoded template (GroupOp: byte offsets + four masks
+// of one bitwise form, two broadcast 16-byte loads, no branch) — and only the call's outputs go back to the wire store:
+// the locals of a call never touch memory, and one 96-byte GroupDesc stands for n_calls x |body| gates instead of one
+// 16-byte GateOp each.  thread -> group: a host-made hint per 128 calls, then a forward walk over first_call.
+// WPT = 4 for tiles of >= 128 witnesses (a register is one 16-byte vector: one LDS.128 / STS.128 and one 512-byte warp
+// request per operand, the op fetch and the loop control are shared by four words), WPT = 1 below.
+template <int WPT>
+__global__ void __launch_bounds__(kGroupThreads)
+k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* __restrict__ gops,
+              const uint32_t* __restrict__ tables, const uint32_t* __restrict__ hints, uint32_t* __restrict__ store,
               uint32_t log2_words) {
-    extern __shared__ uint32_t s_regs[];
-    __shared__ uint32_t s_g0;
-    const uint32_t B = blockDim.x;
-    uint32_t* R = s_regs + threadIdx.x;
-    const uint64_t total = total_calls << log2_words;
-    const uint64_t n_tiles = (total + B - 1) / B;
-    const uint32_t wmask = (1u << log2_words) - 1;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * B;
-        if (threadIdx.x == 0) {  // the group holding the block's first call: the last one whose first_call is <= it
-            const uint32_t c0 = (uint32_t)(t0 >> log2_words);
-            uint32_t lo = 0, hi = n_groups;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(&descs[mid].first_call) <= c0) lo = mid;
-                else hi = mid;
-            }
-            s_g0 = lo;
-        }
-        __syncthreads();
-        uint32_t gi = s_g0;
-        __syncthreads();
-        const uint64_t tid = t0 + threadIdx.x;
-        if (tid >= total) continue;
-        const uint32_t call_g = (uint32_t)(tid >> log2_words), word = (uint32_t)tid & wmask;
+    using V = typename Vec<WPT>::T;
+    constexpr uint32_t kLog2Wpt = WPT == 4 ? 2 : 0;
+    constexpr uint32_t RS = kGroupThreads * 4 * WPT;  // bytes between consecutive registers of one thread
+    extern __shared__ __align__(16) uint8_t s_regs[];
+    uint8_t* R = s_regs + threadIdx.x * (4 * WPT);
+    const uint32_t log2_vecs = log2_words - kLog2Wpt;
+    const uint64_t total = total_calls << log2_vecs;
+    const uint32_t vmask = (1u << log2_vecs) - 1;
+    V* vstore = reinterpret_cast<V*>(store);
+    for (uint64_t tid = blockIdx.x * (uint64_t)kGroupThreads + threadIdx.x; tid < total; tid += (uint64_t)gridDim.x * kGroupThreads) {
+        const uint32_t call_g = (uint32_t)(tid >> log2_vecs), vw = (uint32_t)tid & vmask;
+        uint32_t gi = __ldg(hints + (call_g >> kGroupHintShift));
         while (gi + 1 < n_groups && call_g >= __ldg(&descs[gi + 1].first_call)) gi++;
         const GroupDesc* d = descs + gi;
         const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(d));      // tmpl_off, n_ops, n_out, n_in
         const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);  // n_calls, out_slot, first_call, pad
         const uint32_t call = call_g - h1.z;
+        uint8_t* Rin = R + h0.z * RS;
         for (uint32_t k = 0; k < h0.w; k++) {
             const uint32_t base = __ldg(&d->in_base[k]), st = __ldg(&d->in_stride[k]);
             const uint32_t slot = st == kTableStride ? __ldg(tables + base + call) : base + st * call;
-            R[(h0.z + k) * B] = store[((size_t)slot << log2_words) + word];
+            *reinterpret_cast<V*>(Rin + k * RS) = vstore[((size_t)slot << log2_vecs) + vw];
         }
-        const uint2* op = reinterpret_cast<const uint2*>(tops) + h0.x;
+        const uint4* op = reinterpret_cast<const uint4*>(gops + h0.x);
+#pragma unroll 2
         for (uint32_t i = 0; i < h0.y; i++) {
-            const uint2 o = __ldg(op + i);  // kind | dst << 8 | a << 16, b
-            const uint32_t kind = o.x & 0xff, dst = (o.x >> 8) & 0xff, ra = (o.x >> 16) & 0xff;
-            uint32_t r;
-            if (kind == V_CONST) {
-                r = 0u - (__ldg(const_bits + o.y) & 1);
-            } else {
-                const uint32_t a = R[ra * B];
-                switch (kind) {
-                    case V_ADD:
-                    case V_XOR: r = a ^ R[o.y * B]; break;
-                    case V_MUL:
-                    case V_AND: r = a & R[o.y * B]; break;
-                    case V_ADDC: r = a ^ (0u - (__ldg(const_bits + o.y) & 1)); break;
-                    case V_MULC: r = a & (0u - (__ldg(const_bits + o.y) & 1)); break;
-                    default: r = ~a; break;  // V_NOT
-                }
-            }
-            R[dst * B] = r;
+            const uint4 o = __ldg(op + 2 * i);      // dst_off, a_off, b_off (in units of one register row: x WPT here)
+            const uint4 m = __ldg(op + 2 * i + 1);  // m_and, m_xor, m_a, m_c
+            uint32_t a[WPT], b[WPT], r[WPT];
+            unpack(*reinterpret_cast<const V*>(R + o.y * WPT), a);
+            unpack(*reinterpret_cast<const V*>(R + o.z * WPT), b);
+#pragma unroll
+            for (int k = 0; k < WPT; k++) r[k] = (a[k] & b[k] & m.x) ^ ((a[k] ^ b[k]) & m.y) ^ (a[k] & m.z) ^ m.w;
+            V v;
+            pack(v, r);
+            *reinterpret_cast<V*>(R + o.x * WPT) = v;
         }
         const size_t out0 = (size_t)h1.y + (size_t)call * h0.z;
-        for (uint32_t k = 0; k < h0.z; k++) store[((out0 + k) << log2_words) + word] = R[k * B];
+        for (uint32_t k = 0; k < h0.z; k++) vstore[((out0 + k) << log2_vecs) + vw] = *reinterpret_cast<const V*>(R + k * RS);
     }
 }
 
@@ -1041,19 +1026,23 @@ void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, 
     }
 }
 
-void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const TmplOp* tops, const uint32_t* tables,
-                        uint32_t* store, const uint32_t* const_bits, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s) {
+void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* gops, const uint32_t* tables,
+                        const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s) {
     if (n_groups == 0 || total_calls == 0) return;
     static bool attr_set = false;
-    const size_t smem = (size_t)n_regs * 256 * sizeof(uint32_t);
-    if (!attr_set && smem > 48 * 1024) {
-        cudaFuncSetAttribute(k_bool_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * 256 * sizeof(uint32_t)));
+    if (!attr_set) {  // up to kMaxTemplateRegs x 256 threads x 16 bytes
+        cudaFuncSetAttribute(k_bool_groups<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 4));
+        cudaFuncSetAttribute(k_bool_groups<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 16));
         attr_set = true;
     }
-    const uint64_t total = total_calls << (g.log2_wt - 5);
-    const uint64_t tiles = (total + 255) / 256;
+    const uint32_t log2_words = g.log2_wt - 5;
+    const bool wide = log2_words >= 2;
+    const size_t smem = (size_t)n_regs * kGroupThreads * (wide ? 16 : 4);
+    const uint64_t total = total_calls << (wide ? log2_words - 2 : log2_words);
+    const uint64_t tiles = (total + kGroupThreads - 1) / kGroupThreads;
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sm_count * 64);
-    k_bool_groups<<<grid, 256, smem, s>>>(descs, n_groups, total_calls, tops, tables, store, const_bits, g.log2_wt - 5);
+    if (wide) k_bool_groups<4><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words);
+    else k_bool_groups<1><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words);
 }
 
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,

@@ -556,6 +556,8 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     group_descs.clear();
     group_ops.clear();
     group_tables.clear();
+    group_hints.clear();
+    hint_off.clear();
     depth_off.clear();
     group_regs = 0;
     if (!prog.groups.empty()) {
@@ -563,7 +565,25 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         for (size_t t = 0; t < prog.templates.size(); t++) {
             group_regs = std::max(group_regs, prog.templates[t].n_regs);
             tmpl_off[t] = (uint32_t)group_ops.size();
-            group_ops.insert(group_ops.end(), prog.templates[t].ops.begin(), prog.templates[t].ops.end());
+            for (const TmplOp& o : prog.templates[t].ops) {
+                GroupOp g{};
+                const uint32_t all = 0xFFFFFFFFu;
+                const bool two = o.kind == V_ADD || o.kind == V_MUL || o.kind == V_AND || o.kind == V_XOR;
+                const uint32_t cmask = (o.kind == V_CONST || o.kind == V_ADDC || o.kind == V_MULC)
+                                           ? 0u - (prog.const_limbs[(size_t)o.b * prog.nlimb] & 1u) : 0u;
+                g.dst_off = o.dst * kGroupThreads * 4;
+                g.a_off = (o.kind == V_CONST ? o.dst : o.a) * kGroupThreads * 4;  // a constant reads nothing meaningful: masks are 0
+                g.b_off = two ? o.b * kGroupThreads * 4 : g.a_off;
+                switch (o.kind) {
+                    case V_ADD: case V_XOR: g.m_xor = all; break;
+                    case V_MUL: case V_AND: g.m_and = all; break;
+                    case V_NOT: g.m_a = all; g.m_c = all; break;
+                    case V_ADDC: g.m_a = all; g.m_c = cmask; break;
+                    case V_MULC: g.m_a = cmask; break;
+                    default: g.m_c = cmask; break;  // V_CONST
+                }
+                group_ops.push_back(g);
+            }
         }
         uint32_t max_depth = 0;
         for (const CallGroup& cg : prog.groups) max_depth = std::max(max_depth, cg.depth);
@@ -617,6 +637,21 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             }
             group_descs[cursor[cg.depth]++] = gd;
         }
+        // thread -> group: a hint per 2^kGroupHintShift calls of a launch, then a short forward walk over first_call
+        group_hints.clear();
+        hint_off.assign(depth_off.size(), 0);
+        for (size_t d = 0; d + 1 < depth_off.size(); d++) {
+            hint_off[d] = (uint32_t)group_hints.size();
+            const uint32_t lo = depth_off[d], hi = depth_off[d + 1];
+            if (hi == lo) continue;
+            const uint64_t calls = (uint64_t)group_descs[hi - 1].first_call + group_descs[hi - 1].n_calls;
+            uint32_t g = 0;
+            for (uint64_t c0 = 0; c0 < calls; c0 += (1u << kGroupHintShift)) {
+                while (lo + g + 1 < hi && group_descs[lo + g + 1].first_call <= c0) g++;
+                group_hints.push_back(g);
+            }
+        }
+        hint_off[depth_off.size() - 1] = (uint32_t)group_hints.size();
     }
     lap("emit");
     const uint64_t E = prog.binary ? 1 : (uint64_t)prog.nlimb * 4;

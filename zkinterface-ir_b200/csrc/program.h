@@ -120,6 +120,17 @@ struct GroupDesc {  // 16-byte aligned
     uint32_t in_base[kMaxGroupInputs];
     uint32_t in_stride[kMaxGroupInputs];
 };
+// A template op as the device interpreter wants it (32 bytes, two 16-byte loads, no decoding and no branch): byte offsets of
+// the registers in the CTA's shared-memory register file (register r of thread t at (r * kGroupThreads + t) * 4), and the
+// op as four masks of one bitwise form,  r = (a & b & m_and) ^ ((a ^ b) & m_xor) ^ (a & m_a) ^ m_c :
+//   Xor / Add: m_xor = ~0;  And / Mul: m_and = ~0;  Not: m_a = m_c = ~0;  AddConstant c: m_a = ~0, m_c = -c;
+//   MulConstant c: m_a = -c;  Constant c: m_c = -c   (c = the constant mod 2; one-input ops read a twice)
+constexpr uint32_t kGroupThreads = 256;
+struct GroupOp {
+    uint32_t dst_off, a_off, b_off, pad;
+    uint32_t m_and, m_xor, m_a, m_c;
+};
+constexpr uint32_t kGroupHintShift = 7;  // Plan::group_hints: one entry per 128 calls of a launch
 
 struct InputLoad {  // level-0 values: filled by the input kernel on every pass
     uint32_t slot;
@@ -279,7 +290,9 @@ struct Plan {
     // call groups, in launch order: depth_off[d] .. depth_off[d + 1] are the groups of depth d (one launch each, between the
     // input kernel and the first wavefront)
     std::vector<GroupDesc> group_descs;
-    std::vector<TmplOp> group_ops;
+    std::vector<GroupOp> group_ops;
+    std::vector<uint32_t> group_hints;  // per launch, per 2^kGroupHintShift calls: the group (relative to the launch) holding the first of them
+    std::vector<uint32_t> hint_off;     // per depth: where its hints start
     std::vector<uint32_t> group_tables;
     std::vector<uint32_t> depth_off;
     uint32_t group_regs = 0;  // registers of the widest template
