@@ -33,6 +33,27 @@ def test_device_field_ops(name):
     assert unlimbs(b.debug_field_ops(1, limbs(us, n), limbs(r2, n))) == [u * R % p for u in us]
 
 
+@pytest.mark.parametrize("name", [k for k in FIELDS if FIELDS[k] > (1 << 64)])
+def test_lazy_reduction_primitives(name):
+    """the R1CS check's accumulator (field_ptx.cuh: fe_lazy_mad / fe_lazy_add_one / fe_lazy_finish): plain products summed
+    over 2N + 1 limbs, one Montgomery reduction at the end — against Python integers, including moduli with the top bit set
+    (the sum overflows 2N limbs) and the edge values"""
+    z = zkb()
+    p = FIELDS[name]
+    b = z.GpuBackend(0)
+    b.set_field(p)
+    n = b.stats()["nlimb"]
+    R = 1 << (32 * n)
+    rng = np.random.default_rng(6)
+    edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R % p, (R * R) % p]
+    xs = edge + [p - 1] * 9 + [int.from_bytes(rng.bytes(4 * n), "little") % p for _ in range(20000)]
+    ys = list(reversed(edge)) + [p - 1 - k for k in range(9)] + [int.from_bytes(rng.bytes(4 * n), "little") % p for _ in range(20000)]
+    A, B = limbs(xs, n), limbs(ys, n)
+    Rinv = pow(R, -1, p)
+    assert unlimbs(b.debug_field_ops(3, A, B)) == [(3 * x * y * Rinv + y) % p for x, y in zip(xs, ys)]
+    assert unlimbs(b.debug_field_ops(4, A, B)) == [(x + y) % p for x, y in zip(xs, ys)]
+
+
 def test_field_throughput_reports_sane_numbers():
     z = zkb()
     b = z.GpuBackend(0)

@@ -22,7 +22,8 @@ using namespace zkb;
 
 namespace {
 
-// op: 0 add, 1 mont_mul (product path of the kernels), 2 mont_mul portable
+// op: 0 add, 1 mont_mul (product path of the kernels), 2 mont_mul portable,
+//     3 lazy reduction: REDC(a b + a b + a b + b R) = 3 mont_mul(a, b) + b,  4: REDC(a R + b R) = a + b  (N = 4, 8 only)
 template <int N>
 __global__ void k_field_ops(int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint64_t n, FieldParams fp) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -35,7 +36,40 @@ __global__ void k_field_ops(int op, const uint32_t* a, const uint32_t* b, uint32
     }
     if (op == 0) fe_add<N>(z, x, y, fp.p);
     else if (op == 1) fe_mont_mul<N>(z, x, y, fp.p, fp.n0inv);
-    else fe_mont_mul_portable<N>(z, x, y, fp.p, fp.n0inv);
+    else if (op == 2) fe_mont_mul_portable<N>(z, x, y, fp.p, fp.n0inv);
+    else if constexpr (N == 4 || N == 8) {
+        uint32_t T[2 * N + 1];
+#pragma unroll
+        for (int k = 0; k < 2 * N + 1; k++) T[k] = 0;
+        if (op == 3) {
+            fe_lazy_mad<N>(T, x, y);
+            fe_lazy_mad<N>(T, x, y);
+            fe_lazy_add_one<N>(T, y);
+            fe_lazy_mad<N>(T, x, y);
+        } else if (op == 4) {
+            fe_lazy_add_one<N>(T, x);
+            fe_lazy_add_one<N>(T, y);
+        } else if (op == 5) {  // one product
+            fe_lazy_mad<N>(T, x, y);
+        } else if (op == 6) {  // REDC of the N-limb integer a alone
+#pragma unroll
+            for (int k = 0; k < N; k++) T[k] = x[k];
+        } else {               // op 7: low half of the plain product (no reduction): checks fe_mul_wide limb by limb
+            uint32_t P[2 * N];
+            fe_mul_wide<N>(P, x, y);
+#pragma unroll
+            for (int k = 0; k < N; k++) z[k] = op == 7 ? P[k] : P[N + k];
+        }
+        if (op >= 7) {
+#pragma unroll
+            for (int k = 0; k < N; k++) r[i * N + k] = z[k];
+            return;
+        }
+        fe_lazy_finish<N>(z, T, fp.p, fp.n0inv);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; k++) z[k] = 0;
+    }
 #pragma unroll
     for (int k = 0; k < N; k++) r[i * N + k] = z[k];
 }

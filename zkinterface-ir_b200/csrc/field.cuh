@@ -124,6 +124,81 @@ template <int N>
 ZKB_HD void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
     fe_cond_sub_p_portable<N>(r, a, carry, p);
 }
+// lazy reduction (see field_ptx.cuh): T is a plain integer of 2N + 1 limbs
+template <int N>
+ZKB_HD void fe_mul_wide(uint32_t* P, const uint32_t* a, const uint32_t* b) {
+    for (int k = 0; k < 2 * N; k++) P[k] = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < N; j++) {
+            const uint64_t t = (uint64_t)P[i + j] + (uint64_t)a[j] * b[i] + carry;
+            P[i + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        P[i + N] = (uint32_t)carry;
+    }
+}
+template <int N>
+ZKB_HD void fe_lazy_mad(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+    for (int i = 0; i < N; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < N; j++) {
+            const uint64_t t = (uint64_t)T[i + j] + (uint64_t)a[j] * b[i] + carry;
+            T[i + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        for (int k = i + N; k <= 2 * N && carry; k++) {
+            const uint64_t t = (uint64_t)T[k] + carry;
+            T[k] = (uint32_t)t;
+            carry = t >> 32;
+        }
+    }
+}
+template <int N>
+ZKB_HD void fe_lazy_add_one(uint32_t* T, const uint32_t* a) {
+    uint64_t carry = 0;
+    for (int j = 0; j < N; j++) {
+        const uint64_t t = (uint64_t)T[N + j] + a[j] + carry;
+        T[N + j] = (uint32_t)t;
+        carry = t >> 32;
+    }
+    T[2 * N] += (uint32_t)carry;
+}
+template <int N>
+ZKB_HD void fe_lazy_finish(uint32_t* r, const uint32_t* T, const uint32_t* p, uint32_t n0inv, bool low_half = true) {
+    uint32_t t[2 * N + 2];
+    for (int k = 0; k <= 2 * N; k++) t[k] = T[k];
+    t[2 * N + 1] = 0;
+    if (low_half)
+        for (int i = 0; i < N; i++) {
+            const uint32_t m = t[i] * n0inv;
+            uint64_t carry = 0;
+            for (int j = 0; j < N; j++) {
+                const uint64_t x = (uint64_t)t[i + j] + (uint64_t)m * p[j] + carry;
+                t[i + j] = (uint32_t)x;
+                carry = x >> 32;
+            }
+            for (int k = i + N; k <= 2 * N + 1 && carry; k++) {
+                const uint64_t x = (uint64_t)t[k] + carry;
+                t[k] = (uint32_t)x;
+                carry = x >> 32;
+            }
+        }
+    uint32_t s[N], top = t[2 * N];
+    for (int j = 0; j < N; j++) s[j] = t[N + j];
+    for (;;) {
+        uint32_t d[N], borrow = 0;
+        for (int j = 0; j < N; j++) {
+            const uint64_t x = (uint64_t)s[j] - p[j] - borrow;
+            d[j] = (uint32_t)x;
+            borrow = (uint32_t)(x >> 63);
+        }
+        if (top == 0 && borrow) break;
+        top -= borrow;
+        for (int j = 0; j < N; j++) s[j] = d[j];
+    }
+    for (int j = 0; j < N; j++) r[j] = s[j];
+}
 #else
 template <int N>
 __device__ __forceinline__ void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p);

@@ -35,6 +35,8 @@ __device__ __forceinline__ void mul_pairs4(uint32_t* acc, uint32_t x0, uint32_t 
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
 }
 
+// (the accumulator operands are early-clobber: a chain writes acc[0] before it reads its last inputs, and the compiler would
+// otherwise let an accumulator limb and an input that hold the same value - two literal zeros, say - share one register)
 // acc pairs += x_k * y with one carry chain; returns cin + the carry out of the top pair (cin: the carries this limb
 // position has already collected in this row, so that two chains into the same accumulator need no separate addition)
 __device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y,
@@ -49,7 +51,7 @@ __device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint3
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.u32 %8, %14, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(c)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(cin));
     return c;
 }
@@ -68,13 +70,45 @@ __device__ __forceinline__ uint32_t mad_chain4_fold(uint32_t& e0, uint32_t f0, u
         "madc.lo.cc.u32 %6, %15, %16, %6;\n\t"
         "madc.hi.cc.u32 %7, %15, %16, %7;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c),
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(c),
           "=r"(e0)
         : "r"(f0), "r"(f1), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
     return c;
 }
 
+// acc pairs += x_k * y with a carry-in at the BOTTOM of the chain (cbot in {0, 1}: the carry of a fold done outside); returns
+// the carry out of the top pair
+__device__ __forceinline__ uint32_t mad_chain4_cbot(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y,
+                                                    uint32_t cbot) {
+    uint32_t c, t;
+    asm("add.cc.u32 %9, %15, 0xFFFFFFFF;\n\t"
+        "madc.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(c), "=r"(t)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(cbot));
+    return c;
+}
+
 // ---- N = 4: two pairs per chain --------------------------------------------------------------
+__device__ __forceinline__ uint32_t mad_chain2_cbot(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y, uint32_t cbot) {
+    uint32_t c, t;
+    asm("add.cc.u32 %5, %9, 0xFFFFFFFF;\n\t"
+        "madc.lo.cc.u32 %0, %6, %8, %0;\n\t"
+        "madc.hi.cc.u32 %1, %6, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %7, %8, %2;\n\t"
+        "madc.hi.cc.u32 %3, %7, %8, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=r"(c), "=r"(t)
+        : "r"(x0), "r"(x1), "r"(y), "r"(cbot));
+    return c;
+}
 __device__ __forceinline__ void mul_pairs2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y) {
     asm("mul.lo.u32 %0, %4, %6;\n\t"
         "mul.hi.u32 %1, %4, %6;\n\t"
@@ -90,7 +124,7 @@ __device__ __forceinline__ uint32_t mad_chain2(uint32_t* acc, uint32_t x0, uint3
         "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
         "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
         "addc.u32 %4, %8, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=r"(c)
         : "r"(x0), "r"(x1), "r"(y), "r"(cin));
     return c;
 }
@@ -103,7 +137,7 @@ __device__ __forceinline__ uint32_t mad_chain2_fold(uint32_t& e0, uint32_t f0, u
         "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
         "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
         "addc.u32 %4, 0, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c), "=r"(e0)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=r"(c), "=r"(e0)
         : "r"(f0), "r"(f1), "r"(x0), "r"(x1), "r"(y));
     return c;
 }
@@ -170,6 +204,37 @@ __device__ __forceinline__ uint32_t add_chain4(uint32_t* s, const uint32_t* a, c
     return c;
 }
 
+// s = a + b + cin (cin in {0, 1}), returns the carry out: the upper half of a 2N-limb addition
+__device__ __forceinline__ uint32_t add_chain8_cin(uint32_t* s, const uint32_t* a, const uint32_t* b, uint32_t cin) {
+    uint32_t c, t;
+    asm("add.cc.u32 %9, %26, 0xFFFFFFFF;\n\t"
+        "addc.cc.u32 %0, %10, %18;\n\t"
+        "addc.cc.u32 %1, %11, %19;\n\t"
+        "addc.cc.u32 %2, %12, %20;\n\t"
+        "addc.cc.u32 %3, %13, %21;\n\t"
+        "addc.cc.u32 %4, %14, %22;\n\t"
+        "addc.cc.u32 %5, %15, %23;\n\t"
+        "addc.cc.u32 %6, %16, %24;\n\t"
+        "addc.cc.u32 %7, %17, %25;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(c), "=r"(t)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]), "r"(b[2]),
+          "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+    return c;
+}
+__device__ __forceinline__ uint32_t add_chain4_cin(uint32_t* s, const uint32_t* a, const uint32_t* b, uint32_t cin) {
+    uint32_t c, t;
+    asm("add.cc.u32 %5, %14, 0xFFFFFFFF;\n\t"
+        "addc.cc.u32 %0, %6, %10;\n\t"
+        "addc.cc.u32 %1, %7, %11;\n\t"
+        "addc.cc.u32 %2, %8, %12;\n\t"
+        "addc.cc.u32 %3, %9, %13;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(c), "=r"(t)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(cin));
+    return c;
+}
+
 template <int N>
 __device__ __forceinline__ void fe_cond_sub_p(uint32_t* r, const uint32_t* a, uint32_t carry, const uint32_t* p) {
     if constexpr (N == 8) cond_sub_chain8(r, a, carry, p);
@@ -204,6 +269,11 @@ struct PtxChains<8> {
     static __device__ __forceinline__ uint32_t mad_odd_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, const uint32_t* x, uint32_t y) {
         return mad_chain4_fold(e0, f0, f1, acc, x[1], x[3], x[5], x[7], y);
     }
+    static __device__ __forceinline__ uint32_t mad_odd_cbot(uint32_t* acc, const uint32_t* x, uint32_t y, uint32_t cbot) {
+        return mad_chain4_cbot(acc, x[1], x[3], x[5], x[7], y, cbot);
+    }
+    static __device__ __forceinline__ uint32_t add(uint32_t* s, const uint32_t* a, const uint32_t* b) { return add_chain8(s, a, b); }
+    static __device__ __forceinline__ uint32_t add_cin(uint32_t* s, const uint32_t* a, const uint32_t* b, uint32_t cin) { return add_chain8_cin(s, a, b, cin); }
 };
 template <>
 struct PtxChains<4> {
@@ -214,6 +284,11 @@ struct PtxChains<4> {
     static __device__ __forceinline__ uint32_t mad_odd_fold(uint32_t& e0, uint32_t f0, uint32_t f1, uint32_t* acc, const uint32_t* x, uint32_t y) {
         return mad_chain2_fold(e0, f0, f1, acc, x[1], x[3], y);
     }
+    static __device__ __forceinline__ uint32_t mad_odd_cbot(uint32_t* acc, const uint32_t* x, uint32_t y, uint32_t cbot) {
+        return mad_chain2_cbot(acc, x[1], x[3], y, cbot);
+    }
+    static __device__ __forceinline__ uint32_t add(uint32_t* s, const uint32_t* a, const uint32_t* b) { return add_chain4(s, a, b); }
+    static __device__ __forceinline__ uint32_t add_cin(uint32_t* s, const uint32_t* a, const uint32_t* b, uint32_t cin) { return add_chain4_cin(s, a, b, cin); }
 };
 
 template <int N>
@@ -255,6 +330,141 @@ __device__ __forceinline__ void fe_mont_mul_chain(uint32_t* r, const uint32_t* a
     if constexpr (N == 8) top = add_chain8(t, up, O) + cO;
     else top = add_chain4(t, up, O) + cO;
     fe_cond_sub_p<N>(r, t, top, p);
+}
+
+// ---- lazy reduction (the R1CS check: one Montgomery reduction per linear combination instead of one per term) --------
+// A linear combination sum_k coef_k * z_k of Montgomery residues is accumulated as the plain integer
+//     T = sum_k (z_k R)(coef_k R)  +  sum over coefficient-one terms of (z_k R) * R            (R = 2^(32N)),
+// 2N + 1 limbs (every term is below p R < R^2: the top limb counts the overflows), and reduced ONCE: REDC(T) = T / R mod p
+// = R sum_k coef_k z_k.  A term costs the N^2 multiplications of the plain product instead of the 2 N^2 of a Montgomery
+// product, a linear combination N^2 more for its reduction.
+
+// P (2N limbs) = a * b as plain integers: the rows of fe_mont_mul_chain without the reduction steps
+template <int N>
+__device__ __forceinline__ void fe_mul_wide(uint32_t* P, const uint32_t* a, const uint32_t* b) {
+    using Ch = PtxChains<N>;
+    uint32_t E[N], O[N];
+    Ch::mul_even(E, a, b[0]);
+    Ch::mul_odd(O, a, b[0]);
+    P[0] = E[0];
+    uint32_t cE = 0, cO = 0;
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+        uint32_t nE[N], nO[N];
+#pragma unroll
+        for (int j = 1; j < N; j++) nE[j] = O[j];
+#pragma unroll
+        for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
+        nO[N - 2] = cE;
+        nO[N - 1] = cO;
+        cO = Ch::mad_odd_fold(nE[0], O[0], E[1], nO, a, b[i]);
+        cE = Ch::mad_even(nE, a, b[i]);
+        P[i] = nE[0];  // nothing lands on this limb any more
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            E[j] = nE[j];
+            O[j] = nO[j];
+        }
+    }
+    uint32_t up[N];
+#pragma unroll
+    for (int j = 0; j < N - 1; j++) up[j] = E[j + 1];
+    up[N - 1] = cE;
+    Ch::add(P + N, up, O);  // the product is below R^2: no carry out, cO = 0
+}
+
+// r = (a + m p) / R for the N-limb integer a (m chosen limb by limb so that the division is exact): a value in [0, p],
+// congruent to a / R.  NOT reduced below p: the caller adds the upper half of its accumulator and reduces once.
+template <int N>
+__device__ __forceinline__ void fe_redc_low(uint32_t* r, const uint32_t* a, const uint32_t* p, uint32_t n0inv) {
+    using Ch = PtxChains<N>;
+    uint32_t E[N], O[N];
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {  // a as the first row of a product by 1: even limbs in E, odd limbs in O
+        E[j] = a[j];
+        E[j + 1] = 0;
+        O[j] = a[j + 1];
+        O[j + 1] = 0;
+    }
+    uint32_t m = E[0] * n0inv;
+    uint32_t cE = Ch::mad_even(E, p, m);
+    uint32_t cO = Ch::mad_odd(O, p, m);
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+        uint32_t nE[N], nO[N];
+#pragma unroll
+        for (int j = 1; j < N; j++) nE[j] = O[j];
+#pragma unroll
+        for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
+        nO[N - 2] = cE;
+        nO[N - 1] = cO;
+        uint32_t cf;
+        asm("add.cc.u32 %0, %2, %3;\n\t"
+            "addc.u32 %1, 0, 0;"
+            : "=r"(nE[0]), "=r"(cf)
+            : "r"(O[0]), "r"(E[1]));
+        m = nE[0] * n0inv;
+        cE = Ch::mad_even(nE, p, m);
+        cO = Ch::mad_odd_cbot(nO, p, m, cf);
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            E[j] = nE[j];
+            O[j] = nO[j];
+        }
+    }
+    uint32_t up[N];
+#pragma unroll
+    for (int j = 0; j < N - 1; j++) up[j] = E[j + 1];
+    up[N - 1] = cE;
+    Ch::add(r, up, O);  // <= p < R: no carry out
+}
+
+// T (2N + 1 limbs) += a * b
+template <int N>
+__device__ __forceinline__ void fe_lazy_mad(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+    using Ch = PtxChains<N>;
+    uint32_t P[2 * N];
+    fe_mul_wide<N>(P, a, b);
+    const uint32_t c = Ch::add(T, T, P);
+    T[2 * N] += Ch::add_cin(T + N, T + N, P + N, c);
+}
+// T += a * R  (a term with coefficient one)
+template <int N>
+__device__ __forceinline__ void fe_lazy_add_one(uint32_t* T, const uint32_t* a) {
+    using Ch = PtxChains<N>;
+    T[2 * N] += Ch::add(T + N, T + N, a);
+}
+// r = T / R mod p, fully reduced.  T < (k + 1) p R after k terms, so the quotient by p is small: subtract p while it fits.
+// `low_half`: false when only coefficient-one terms were added (the lower N limbs are zero: the division by R is a shift).
+template <int N>
+__device__ __forceinline__ void fe_lazy_finish(uint32_t* r, const uint32_t* T, const uint32_t* p, uint32_t n0inv, bool low_half = true) {
+    using Ch = PtxChains<N>;
+    uint32_t s[N];
+    uint32_t top = T[2 * N];
+    if (low_half) {
+        uint32_t lo[N];
+        fe_redc_low<N>(lo, T, p, n0inv);
+        top += Ch::add(s, lo, T + N);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) s[j] = T[N + j];
+    }
+    for (;;) {
+        uint32_t d[N];
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {  // d = s - p limb by limb (compiles to one borrow chain)
+            const uint64_t x = (uint64_t)s[j] - p[j] - borrow;
+            d[j] = (uint32_t)x;
+            borrow = (uint32_t)(x >> 63);
+        }
+        if (top == 0 && borrow) break;  // (top : s) < p
+        top -= borrow;
+#pragma unroll
+        for (int j = 0; j < N; j++) s[j] = d[j];
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = s[j];
 }
 
 // Two-limb fields (33..64-bit moduli) as ONE 64-bit limb: the 128-bit product is mul.lo.u64 / mul.hi.u64, the Montgomery

@@ -144,8 +144,11 @@ constexpr uint32_t M_END_A = 1, M_END_B = 2, M_END_C = 3;  // tag >> 30
 #ifndef ZKB_R1CS_GA
 #define ZKB_R1CS_GA 3
 #endif
+#ifndef ZKB_R1CS_LAZY
+#define ZKB_R1CS_LAZY 1
+#endif
 #ifndef ZKB_R1CS_MIN_CTAS
-#define ZKB_R1CS_MIN_CTAS 4
+#define ZKB_R1CS_MIN_CTAS (ZKB_R1CS_LAZY ? 3 : 4)  // the 2N + 1 limb accumulator spills under a 64-register cap (profiles/r02j_ab_r1cs_lazy.log)
 #endif
 constexpr int kR1csThreads = 256;
 
@@ -234,9 +237,14 @@ k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, 
     uint64_t c_item = d_item;  // item the consumer is in
     int drain = 0;
 
-    uint32_t acc[N];
+    // the linear combination being summed: for 4- and 8-limb fields the plain integer of field_ptx.cuh's lazy reduction (one
+    // Montgomery reduction per linear combination, N^2 multiplications per term instead of 2 N^2), else a reduced residue
+    constexpr bool LAZY = ZKB_R1CS_LAZY && (N == 4 || N == 8);
+    constexpr int NT = LAZY ? 2 * N + 1 : N;
+    uint32_t acc[NT];
 #pragma unroll
-    for (int i = 0; i < N; i++) acc[i] = 0;
+    for (int i = 0; i < NT; i++) acc[i] = 0;
+    bool products = false;  // LAZY: the accumulator holds a product (else it is a sum of residues times R: no REDC needed)
 
     for (uint32_t s = 0;; s++) {
         cp_async_wait<GA - 1>();
@@ -276,27 +284,42 @@ k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, 
 #pragma unroll
             for (int c = 0; c < NC; c++) lds_chunk<CW>(zl + c * CW, srcs + c * C_STEP);
             if (tag == TD_ONE) {
-                fe_add<N>(acc, acc, zl, fp.p);
+                if constexpr (LAZY) fe_lazy_add_one<N>(acc, zl);
+                else fe_add<N>(acc, acc, zl, fp.p);
             } else {
-                uint32_t cf[N], prod[N];
+                uint32_t cf[N];
                 using V = typename Vec<CW>::T;
                 const V* cv = reinterpret_cast<const V*>(coefs) + (size_t)tag * NC;  // a few KB, L1-resident (the gathers bypass L1)
 #pragma unroll
                 for (int c = 0; c < NC; c++) unpack(__ldg(cv + c), cf + c * CW);
-                fe_mont_mul<N>(prod, zl, cf, fp.p, fp.n0inv);
-                fe_add<N>(acc, acc, prod, fp.p);
+                if constexpr (LAZY) {
+                    fe_lazy_mad<N>(acc, zl, cf);
+                    products = true;
+                } else {
+                    uint32_t prod[N];
+                    fe_mont_mul<N>(prod, zl, cf, fp.p, fp.n0inv);
+                    fe_add<N>(acc, acc, prod, fp.p);
+                }
             }
         }
         const uint32_t mark = t.y >> 30;
         if (mark != 0) {
+            uint32_t lc[N];  // the finished linear combination, reduced
+            if constexpr (LAZY) {
+                fe_lazy_finish<N>(lc, acc, fp.p, fp.n0inv, products);
+                products = false;
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) lc[i] = acc[i];
+            }
             if (mark == M_END_A) {  // park A_r . z in shared memory: the registers serve B_r
 #pragma unroll
-                for (int c = 0; c < NC; c++) sts_chunk<CW>(a_base + c * C_STEP, acc + c * CW);
+                for (int c = 0; c < NC; c++) sts_chunk<CW>(a_base + c * C_STEP, lc + c * CW);
             } else if (mark == M_END_B) {  // (aR)(bR)/R = abR takes the parking place: only the accumulator lives across terms
                 uint32_t av[N], ab[N];
 #pragma unroll
                 for (int c = 0; c < NC; c++) lds_chunk<CW>(av + c * CW, a_base + c * C_STEP);
-                fe_mont_mul<N>(ab, av, acc, fp.p, fp.n0inv);
+                fe_mont_mul<N>(ab, av, lc, fp.p, fp.n0inv);
 #pragma unroll
                 for (int c = 0; c < NC; c++) sts_chunk<CW>(a_base + c * C_STEP, ab + c * CW);
             } else {  // abR against cR
@@ -305,14 +328,14 @@ k_r1cs_check(const uint4* __restrict__ slices, const uint2* __restrict__ terms, 
                 for (int c = 0; c < NC; c++) lds_chunk<CW>(ab + c * CW, a_base + c * C_STEP);
                 uint32_t diff = 0;
 #pragma unroll
-                for (int i = 0; i < N; i++) diff |= ab[i] ^ acc[i];
+                for (int i = 0; i < N; i++) diff |= ab[i] ^ lc[i];
                 const uint64_t srow = c_item >> g.log2_wt;
                 const bool fail = diff != 0 && srow < n_rows && lane < g.n_valid;  // the last slice may hold padding rows
                 report_fail(fail, fail ? __ldg(row_ids + srow) : 0u, first_fail, g.batch0 + lane, single);
                 c_item += stride;
             }
 #pragma unroll
-            for (int i = 0; i < N; i++) acc[i] = 0;
+            for (int i = 0; i < NT; i++) acc[i] = 0;
         }
     }
     cp_async_wait<0>();
