@@ -22,6 +22,9 @@ python tests/bench_configs.py --only c3s >> $out/${tag}_configs.jsonl 2>> $out/$
 python scripts/r1cs_once.py 22 1 > /dev/null 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:k_r1cs_check -c 2 -o $out/${tag}_prof_r1cs \
       python scripts/r1cs_once.py 22 1 > $out/${tag}_ncu_r1cs.log 2>&1
+python tests/bench_configs.py --only c5 > /dev/null 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:k_bool_groups -c 3 -o $out/${tag}_prof_groups \
+      python tests/bench_configs.py --only c5 > $out/${tag}_ncu_groups.log 2>&1
 python scripts/field_throughput.py > $out/${tag}_field_throughput.jsonl 2>/dev/null
 for f in m31 goldilocks p124; do
   python bench.py --field $f --no-cpu-baseline --no-value-check --steps 2 --warmup 2 2>/dev/null > $out/${tag}_bench_$f.json

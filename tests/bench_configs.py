@@ -112,6 +112,18 @@ def c4(log2_rows, log2_free, batch):
         # the gathered sectors at the gather ceiling + the streamed descriptors at the copy peak
         floor_ms = (z_bytes / gather + (algo - z_bytes) / PEAK) / 1e9 * 1e3
         extra = {"random_gather_GBps": gather, "gather_bound_ms": floor_ms, "frac_of_gather_bound": floor_ms / lv}
+    # the integer-pipe ceiling of the same work: N^2 = 64 wide multiply-adds per general term (plain product), 64 per linear
+    # combination that holds one (its single Montgomery reduction), 128 for (A_r.z)(B_r.z); against the measured rate of
+    # register-resident Montgomery products (128 wide multiply-adds each)
+    wide_mads = 0
+    for (rp, col, ci) in (r.A, r.B):
+        general = (ci != 0)
+        wide_mads += 64 * int(general.sum())
+        wide_mads += 64 * int((np.add.reduceat(general.astype(np.int64), rp[:-1].astype(np.int64)) > 0).sum())
+    wide_mads += 128 * r.n_rows
+    mads_per_s = b.debug_field_throughput(1, 500) * 128
+    imad_ms = wide_mads * batch / mads_per_s * 1e3
+    extra.update({"wide_mads_per_assignment": wide_mads, "integer_pipe_bound_ms": imad_ms, "frac_of_integer_pipe_bound": imad_ms / lv})
     return {**extra, "config": f"C4 R1CS 2^{log2_rows} constraints, BN254, batch {batch}", "constraints_per_s": r.n_rows * batch / (lv * 1e-3),
             "gate_equivalent_per_s": ge * batch / (lv * 1e-3), "check_kernel_ms": lv, "total_ms_incl_z_conversion": tot, "nnz": r.nnz,
             "n_vars": r.n_vars, "algo_GBps": algo / (lv * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (lv * 1e-3) / 1e9 / PEAK,

@@ -25,7 +25,7 @@ from typing import Iterable, List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkb.so")
+LIB_PATH = os.environ.get("ZKB_LIB_PATH") or os.path.join(_HERE, "libzkb.so")  # ZKB_LIB_PATH: a sanitized build (scripts/asan_host.sh)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -293,7 +293,8 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint64_t> cnt(n_keys + 1, 0);
     for (unsigned t = 0; t < Tsort; t++)
         for (size_t k = 0; k < n_keys; k++) cnt[k + 1] += hist[t][k];
-    cnt[(size_t)0 * D_OPS + D_ASSERT + 1] += input_assert_seq.size() + callout_assert_seq.size();
+    if (n_levels > 0)  // (a program of inputs only has no wavefront and, by the rule above, no standalone assertion)
+        cnt[(size_t)0 * D_OPS + D_ASSERT + 1] += input_assert_seq.size() + callout_assert_seq.size();
     for (size_t i = 0; i < n_keys; i++) cnt[i + 1] += cnt[i];
     const uint64_t n_ops = cnt[n_keys];
     level_off.assign((size_t)n_levels + 1, 0);
@@ -528,7 +529,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
             n_raw_ops += dev_cnt[t][D_OPS];
         }
     }
-    {
+    if (n_levels > 0) {
         uint64_t p = cnt[(size_t)0 * D_OPS + D_ASSERT];
         for (size_t i = 0; i < input_assert_seq.size(); i++, p++) {
             GateOp g;
