@@ -73,6 +73,32 @@ def test_true_single_witness_values():
     assert st["ir_gates"] == 5000
 
 
+@pytest.mark.parametrize("name", ["p101", "m31", "goldilocks", "p61", "p64full"])
+@pytest.mark.parametrize("flow_min", ["1", "256"])
+@pytest.mark.parametrize("window", [0, 64])
+def test_dataflow_launch_single_witness(name, flow_min, window, monkeypatch):
+    """one witness over a 1- / 2-limb field: every wavefront in ONE barrier-free launch (k_levels_flow: gates poll their
+    operand words until the all-ones marker is gone).  Every gate kind, every wire value and the first failing assertion
+    against the oracle; ZKB_FLOW_MIN=1 sends even the narrowest program through it, a windowed circuit makes it deep
+    (hundreds of wavefronts, producers and consumers in neighbouring warps); ZKB_FLOW=0 must give the same answers."""
+    monkeypatch.setenv("ZKB_FLOW_MIN", flow_min)
+    c = circuits()
+    p = FIELDS[name]
+    for seed, corrupt in ((41, {}), (42, {0: 2})):
+        circ = c.random_circuit(6000, 48, p, seed=seed, n_tracked=6, window=window)
+        w = c.make_witnesses(circ, 1, seed=seed + 1, corrupt=corrupt)
+        v, ref, st = _check(c, circ.gates, circ.const_pool, p, None, w, 1, circ.n_wires)
+        monkeypatch.setenv("ZKB_FLOW", "0")
+        v0, _, st0 = _check(c, circ.gates, circ.const_pool, p, None, w, 1, circ.n_wires)
+        monkeypatch.delenv("ZKB_FLOW")
+        assert (int(v[0]["ok"]), int(v[0]["first_fail_seq"])) == (int(v0[0]["ok"]), int(v0[0]["first_fail_seq"]))
+    gates, pool, n_wires = random_flat_program(p, 1500, 5, 9, seed=7, bool_ops=True)   # And / Xor / Not, Free + id re-use
+    rng = np.random.default_rng(3)
+    inst = c.random_field_elements(rng, (5,), p)
+    wit = c.random_field_elements(rng, (1, 9), p)
+    _check(c, gates, pool, p, inst, wit, 1, n_wires)
+
+
 @pytest.mark.parametrize("tile_log2", ["0", "2", "5"])
 def test_multi_tile_batches(tile_log2, monkeypatch):
     # force small tiles so a batch takes several passes, with a ragged last tile

@@ -65,6 +65,9 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
         c->flat_scope.for_each([&](uint64_t, uint32_t v) { live.push_back(v); });
     }
     if (const char* e = getenv("ZKB_SLOT_REUSE")) c->plan.slot_reuse = atoi(e) != 0;
+    // small programs over 1- / 2-limb fields keep one slot per value: a single witness then runs as a barrier-free dataflow
+    // launch (k_levels_flow), which needs every slot written once; the wire store of such a program is small either way
+    else if (!c->prog.binary && c->prog.nlimb <= 2 && c->prog.n_values() <= (1u << 22)) c->plan.slot_reuse = false;
     {
         NvtxRange r("zkb:levelize");
         c->plan.build(c->prog, keep_all, &live);
@@ -534,6 +537,27 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     // launch-bound programs (levels far too small to fill the chip): all wavefronts in one cooperative launch
     bool coop = !p.binary && pl.n_levels > 1 && ((uint64_t)pl.max_level_ops << c->log2_wt) <= (uint64_t)c->sm_count * 8192;
     if (const char* e = getenv("ZKB_COOP")) coop = coop && atoi(e) != 0;
+    // one witness, 1- / 2-limb field, no slot written twice: every wavefront in one dataflow launch, no barrier (k_levels_flow)
+    if (!p.binary && p.nlimb <= 2 && c->log2_wt == 0 && pl.n_levels > 1 && pl.n_reused_slots == 0 && c->coop_supported) {
+        const char* e = getenv("ZKB_FLOW");
+        const char* em = getenv("ZKB_FLOW_MIN");
+        // a program whose wavefronts fit a few warps stays on the cluster-barrier kernel: producer and consumer lanes of ONE warp
+        // exchanging values through L2 measured 10 us per wavefront (C1), the cluster barrier 0.23 us (profiles/r02l_ab_flow*.log)
+        if ((e && atoi(e) != 0) && pl.max_level_ops >= (uint32_t)(em ? atoi(em) : 256)) {
+            cudaError_t err = launch_levels_flow(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, rawctx,
+                                                 g, p.fp, c->sm_count, pl.max_level_ops, (uint32_t)pl.loads.size() + pl.n_callouts, pl.n_slots,
+                                                 c->stream);
+            if (err == cudaSuccess) {
+                *launches += 2;  // marker fill + the launch
+                if (level_launches) (*level_launches)++;
+                if (timed) cudaEventRecord(c->tile_ev[2 * tile + 1], c->stream);
+                c->resident_tile = tile;
+                return;
+            }
+            if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: dataflow launch failed: %s\n", cudaGetErrorString(err));
+            cudaGetLastError();
+        }
+    }
     uint32_t first_level = 0;  // levels [0, first_level) have been run by the all-levels launches below
     if (coop && c->coop_supported) {
         // Runs of at least three consecutive wavefronts that each fit one thread-block cluster (8 x 512 threads, two

@@ -591,6 +591,102 @@ k_levels_coop(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq,
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_levels_flow: every wavefront in ONE cooperative launch and NO barrier at all — dataflow.  For one witness over a 1- or
+// 2-limb field an element is one naturally aligned 4- / 8-byte word, and the all-ones word is no residue (a stored value is
+// < p <= 2^(32N) - 1): it marks "not computed yet".  The host fills the computed slots with it before the launch; a gate
+// polls its operand words (ld.relaxed.gpu: single-copy atomic, served by L2) until they are values, computes, and publishes
+// its result with one st.relaxed.gpu — the value IS the flag, so a producer-consumer hop costs one L2 round trip instead of
+// store -> fence -> grid barrier (1.2 us) -> descriptor -> gather (C2: 4.5 us per wavefront).
+// Progress: all CTAs are resident (cooperative launch) and every thread walks its gates wavefront by wavefront, so the
+// lowest wavefront with an unfinished gate only waits on finished ones.  Inside one loop trip the lanes of a warp hold gates
+// of the SAME wavefront (the stride loop restarts at every wavefront boundary): lanes never wait on each other, which matters
+// because the compiler reconverges the warp after the polling loop.  Needs a plan without slot re-use (a slot written twice
+// would make a late reader of the first value see the second).
+// ---------------------------------------------------------------------------------------------------------------------
+// one poll of an element's word: all ones = not computed yet
+template <int N>
+__device__ __forceinline__ uint64_t flow_peek(const uint32_t* store, uint32_t slot) {
+    if constexpr (N == 2) {
+        uint64_t v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<const uint64_t*>(store) + slot) : "memory");
+        return v;
+    } else {
+        uint32_t v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(store + slot) : "memory");
+        return v == ~0u ? ~0ull : (uint64_t)v;
+    }
+}
+template <int N>
+__device__ __forceinline__ void flow_publish_elem(uint32_t* store, uint32_t slot, const uint32_t* r) {
+    if constexpr (N == 2) {
+        const uint64_t v = (uint64_t)r[1] << 32 | r[0];
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(reinterpret_cast<uint64_t*>(store) + slot), "l"(v) : "memory");
+    } else {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(store + slot), "r"(r[0]) : "memory");
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+k_levels_flow(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
+              uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
+              RawCtx rc, TileGeom g, FieldParams fp, uint32_t sleep_ns) {
+    static_assert(N <= 2, "one word per element");
+    constexpr uint32_t kOffCache = 2048;
+    __shared__ uint64_t s_off[kOffCache + 1];
+    for (uint32_t i = threadIdx.x; i <= n_levels && i <= kOffCache; i += blockDim.x) s_off[i] = level_off[i];
+    __syncthreads();
+    auto off = [&](uint32_t i) -> uint64_t { return i <= kOffCache ? s_off[i] : level_off[i]; };
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint4* dptr = reinterpret_cast<const uint4*>(ops);
+    // the descriptor of a thread's first gate of the NEXT wavefront is fetched while it works on (waits in) the current one:
+    // descriptors do not depend on wire data, and the fetch would otherwise head every hop of the dependency chain
+    uint4 first = make_uint4(0, 0, 0, 0);
+    if (n_levels && off(0) + tid0 < off(1)) first = ldg_pinned(dptr + off(0) + tid0);
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint64_t lo = off(l), hi = off(l + 1);
+        uint4 next_first = make_uint4(0, 0, 0, 0);
+        if (l + 1 < n_levels && hi + tid0 < off(l + 2)) next_first = ldg_pinned(dptr + hi + tid0);
+        for (uint64_t gi = lo + tid0; gi < hi; gi += stride) {
+            const uint4 raw = gi == lo + tid0 ? first : __ldg(dptr + gi);
+            const uint32_t opc = raw.w & 0xff;
+            const bool two = opc == D_ADD || opc == D_MUL || opc == D_AND || opc == D_XOR;
+            uint32_t a[N], b[N], r[N];
+            // both operand polls in flight together
+            uint64_t va = flow_peek<N>(store, raw.x);
+            uint64_t vb = two ? flow_peek<N>(store, raw.y) : 0;
+            while (va == ~0ull) {
+                if (sleep_ns) __nanosleep(sleep_ns);
+                va = flow_peek<N>(store, raw.x);
+            }
+            while (vb == ~0ull) {
+                if (sleep_ns) __nanosleep(sleep_ns);
+                vb = flow_peek<N>(store, raw.y);
+            }
+            a[0] = (uint32_t)va;
+            if constexpr (N == 2) a[1] = (uint32_t)(va >> 32);
+            if (opc == D_ADDC || opc == D_MULC) {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)raw.y * N + k);
+            } else {
+                b[0] = (uint32_t)vb;
+                if constexpr (N == 2) b[1] = (uint32_t)(vb >> 32);
+            }
+            if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
+            else if (opc == D_MUL || opc == D_MULC) fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
+            else rare_gate<N>(r, a, b, raw, 0u, g, rc, fp);
+            if (!(raw.w & F_NOSTORE)) flow_publish_elem<N>(store, raw.z, r);
+            if ((raw.w & F_ASSERT) && !fe_is_zero<N>(r)) atomicMin(first_fail + g.batch0, __ldg(aseq + gi));
+        }
+        first = next_first;
+        // the warp moves on together: a lane without a gate in this wavefront must not run ahead and poll for a value that a
+        // lane of its own warp has yet to produce (divergent lanes of one warp share its issue slot)
+        __syncwarp();
+    }
+}
+
 template <int N>
 __global__ void k_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
                               uint32_t log2_wt, uint32_t* __restrict__ out, FieldParams fp) {
@@ -998,6 +1094,41 @@ cudaError_t launch_levels_coop(int nlimb, const GateOp* ops, const uint32_t* ase
     ZKB_DISPATCH_N(nlimb, (e = launch_coop_n<N>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count,
                                                 max_level_items, barrier_ctr, barrier_epoch, s)));
     return e;
+}
+
+// the dataflow launch (k_levels_flow): one witness, 1- or 2-limb field, plan without slot re-use.  `fill_from` .. `n_slots`
+// are the computed slots, marked "not computed yet" first.  cudaErrorNotSupported: not this kernel's case.
+template <int N>
+static cudaError_t launch_flow_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
+                                 const uint32_t* consts_mont, uint32_t* first_fail, RawCtx rc, TileGeom g, FieldParams fp, int sm_count,
+                                 uint64_t max_level_items, uint32_t fill_from, uint32_t n_slots, cudaStream_t s) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels_flow<N>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    uint64_t want = (max_level_items + 255) / 256;
+    uint64_t blocks = ((want + sm_count - 1) / sm_count) * sm_count;
+    if (blocks < (uint64_t)sm_count) blocks = sm_count;
+    if (blocks > (uint64_t)sm_count * per_sm) blocks = (uint64_t)sm_count * per_sm;
+    if (const char* eb = getenv("ZKB_FLOW_BLOCKS")) blocks = std::min<uint64_t>((uint64_t)std::max(1, atoi(eb)), (uint64_t)sm_count * per_sm);
+    if (n_slots > fill_from) {
+        e = cudaMemsetAsync(store + (size_t)fill_from * N, 0xFF, (size_t)(n_slots - fill_from) * N * 4, s);
+        if (e != cudaSuccess) return e;
+    }
+    uint32_t sleep_ns = 0;  // back-off between polls of a marker word (A/B knob)
+    if (const char* es = getenv("ZKB_FLOW_SLEEP")) sleep_ns = (uint32_t)atoi(es);
+    void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
+                    (void*)&first_fail, (void*)&rc, (void*)&g, (void*)&fp, (void*)&sleep_ns};
+    return cudaLaunchCooperativeKernel((void*)k_levels_flow<N>, dim3((unsigned)blocks), dim3(256), args, 0, s);
+}
+cudaError_t launch_levels_flow(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
+                               uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
+                               const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t fill_from, uint32_t n_slots,
+                               cudaStream_t s) {
+    if (g.log2_wt != 0) return cudaErrorNotSupported;
+    if (nlimb == 1) return launch_flow_n<1>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count, max_level_items, fill_from, n_slots, s);
+    if (nlimb == 2) return launch_flow_n<2>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count, max_level_items, fill_from, n_slots, s);
+    return cudaErrorNotSupported;
 }
 
 void launch_read_values(int nlimb, const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
