@@ -79,7 +79,8 @@ def c2(log2_gates, window):
     return {"barrier": bar, "barrier_floor_ms": st["n_levels"] * used * 1e-3, "frac_of_barrier_floor": st["n_levels"] * used * 1e-3 / tot,
             "widest_level_gates": widest,
             "config": f"C2 2^{log2_gates}-gate Goldilocks, 1 witness, operands {'windowed ' + str(window) if window else 'global'}",
-            "gates_per_s": circ.n_gates / (tot * 1e-3), "ms": tot, "levels": st["n_levels"], "us_per_level": tot * 1e3 / st["n_levels"],
+            "gates_per_s": circ.n_gates / (tot * 1e-3), "ms": tot, "levels_ms": lv, "levels": st["n_levels"], "us_per_level": tot * 1e3 / st["n_levels"],
+            "us_per_level_levels_only": lv * 1e3 / st["n_levels"], "kernel_launches": b.timing()["kernel_launches"],
             "algo_GBps_incl_descriptors": algo / (tot * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (tot * 1e-3) / 1e9 / PEAK,
             "prep_s": prep, "note": "L2-resident, launch/latency bound (one launch per wavefront)"}
 

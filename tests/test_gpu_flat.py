@@ -82,6 +82,7 @@ def test_dataflow_launch_single_witness(name, flow_min, window, monkeypatch):
     against the oracle; ZKB_FLOW_MIN=1 sends even the narrowest program through it, a windowed circuit makes it deep
     (hundreds of wavefronts, producers and consumers in neighbouring warps); ZKB_FLOW=0 must give the same answers."""
     monkeypatch.setenv("ZKB_FLOW_MIN", flow_min)
+    monkeypatch.setenv("ZKB_FLOW", "1")
     c = circuits()
     p = FIELDS[name]
     for seed, corrupt in ((41, {}), (42, {0: 2})):
@@ -90,7 +91,7 @@ def test_dataflow_launch_single_witness(name, flow_min, window, monkeypatch):
         v, ref, st = _check(c, circ.gates, circ.const_pool, p, None, w, 1, circ.n_wires)
         monkeypatch.setenv("ZKB_FLOW", "0")
         v0, _, st0 = _check(c, circ.gates, circ.const_pool, p, None, w, 1, circ.n_wires)
-        monkeypatch.delenv("ZKB_FLOW")
+        monkeypatch.setenv("ZKB_FLOW", "1")
         assert (int(v[0]["ok"]), int(v[0]["first_fail_seq"])) == (int(v0[0]["ok"]), int(v0[0]["first_fail_seq"]))
     gates, pool, n_wires = random_flat_program(p, 1500, 5, 9, seed=7, bool_ops=True)   # And / Xor / Not, Free + id re-use
     rng = np.random.default_rng(3)

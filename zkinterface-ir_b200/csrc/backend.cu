@@ -46,6 +46,17 @@ static int upload_vec(zkb_ctx* c, T*& dptr, const std::vector<T>& v) {
     return ZKB_OK;
 }
 
+int ctx_result_buffer(zkb_ctx* c, size_t n_words) {
+    if (n_words <= c->h_res_cap) return ZKB_OK;
+    if (c->h_res) cudaFreeHost(c->h_res);
+    c->h_res = nullptr;
+    c->h_res_cap = 0;
+    size_t cap = std::max<size_t>(n_words, 1024);
+    CUDA_TRY(c, cudaHostAlloc((void**)&c->h_res, cap * 4, cudaHostAllocDefault));
+    c->h_res_cap = cap;
+    return ZKB_OK;
+}
+
 int ctx_upload_groups(zkb_ctx* c) {
     int rc;
     if ((rc = upload_vec(c, c->d_group_descs, c->plan.group_descs)) != ZKB_OK) return rc;
@@ -142,6 +153,7 @@ extern "C" zkb_ctx* zkb_create(int device) {
     cudaMalloc((void**)&c->d_unreduced, sizeof(uint32_t));
     cudaMalloc((void**)&c->d_barrier, sizeof(uint32_t));  // arrival counter of the grid barrier (kernels.cu: grid_barrier)
     cudaMemset(c->d_barrier, 0, sizeof(uint32_t));
+    ctx_result_buffer(c, 8192);  // pinned verdict buffer up front: cudaHostAlloc costs a millisecond, not for the first run to pay
     c->has_gpu = true;
     return c;
 }
@@ -160,6 +172,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_group_ops);
         cudaFree(c->d_group_tables);
         cudaFree(c->d_group_hints);
+        if (c->h_res) cudaFreeHost(c->h_res);
         cudaFree(c->d_const_flags);
         cudaFree(c->d_const_raw);
         cudaFree(c->d_rawflag);
@@ -543,7 +556,7 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         const char* em = getenv("ZKB_FLOW_MIN");
         // a program whose wavefronts fit a few warps stays on the cluster-barrier kernel: producer and consumer lanes of ONE warp
         // exchanging values through L2 measured 10 us per wavefront (C1), the cluster barrier 0.23 us (profiles/r02l_ab_flow*.log)
-        if ((e && atoi(e) != 0) && pl.max_level_ops >= (uint32_t)(em ? atoi(em) : 256)) {
+        if ((!e || atoi(e) != 0) && pl.max_level_ops >= (uint32_t)(em ? atoi(em) : 256)) {
             cudaError_t err = launch_levels_flow(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, rawctx,
                                                  g, p.fp, c->sm_count, pl.max_level_ops, (uint32_t)pl.loads.size() + pl.n_callouts, pl.n_slots,
                                                  c->stream);
@@ -674,10 +687,9 @@ int ctx_run(zkb_ctx* c, zkb_verdict* out, uint32_t first, uint32_t n_total, bool
         if ((rc = comm_allreduce_min_u32(c, c->d_first_fail, n_total)) != ZKB_OK) return rc;
     }
     NvtxRange r_d2h("zkb:verdict_d2h");
-    c->h_first_fail.resize(n_total);
-    uint32_t unreduced = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_first_fail.data(), c->d_first_fail, (size_t)n_total * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&unreduced, c->d_unreduced, 4, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = ctx_result_buffer(c, (size_t)n_total + 1)) != ZKB_OK) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_res, c->d_first_fail, (size_t)n_total * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_res + n_total, c->d_unreduced, 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
@@ -695,10 +707,10 @@ int ctx_run(zkb_ctx* c, zkb_verdict* out, uint32_t first, uint32_t n_total, bool
     c->timing.load_ms = ms - lv;    // input conversion, verdict fill / all-reduce / copy, gaps
     c->timing.level_launches = level_launches;
     c->timing.kernel_launches = launches;
-    c->n_unreduced_inputs = unreduced;
+    c->n_unreduced_inputs = c->h_res[n_total];
     if (out)
         for (uint32_t j = 0; j < n_total; j++) {
-            uint32_t f = c->h_first_fail[j];
+            uint32_t f = c->h_res[j];
             memset(&out[j], 0, sizeof(zkb_verdict));
             out[j].ok = (f == 0xFFFFFFFFu) && !c->has_pending;
             out[j].first_fail_seq = f == 0xFFFFFFFFu ? UINT64_MAX : f;

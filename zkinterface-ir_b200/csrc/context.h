@@ -187,7 +187,8 @@ struct zkb_ctx {
     uint32_t barrier_epoch = 0;      // its value once every launch issued so far has finished
     int64_t resident_tile = -1;
     bool inputs_uploaded = false;
-    std::vector<uint32_t> h_first_fail;
+    uint32_t* h_res = nullptr;       // pinned: the verdict vector + the unreduced-input count of a run land here (a copy to
+    size_t h_res_cap = 0;            // pageable memory is staged and synchronous: tens of microseconds per small copy)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> tile_ev;
     zkb_timing timing{};
@@ -211,6 +212,7 @@ struct zkb_ctx {
 namespace zkb {
 // shared helpers implemented in backend.cu
 int ctx_upload_groups(zkb_ctx* c);  // plan.group_* -> device
+int ctx_result_buffer(zkb_ctx* c, size_t n_words);  // c->h_res holds at least n_words
 int ctx_finalize(zkb_ctx* c, int keep_values);  // 0 live wires, 1 all values, 2 verdicts only
 bool ctx_record_ok(zkb_ctx* c);  // false when a recording error is latched
 void ctx_latch(zkb_ctx* c, const std::string& msg);

@@ -650,10 +650,12 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
         cudaEventRecord(c->tile_ev[2 * t + 1], c->stream);
         launches += 2;
     }
-    c->h_first_fail.resize(r->n_batch);
-    uint32_t unreduced = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_first_fail.data(), r->d_first_fail, (size_t)r->n_batch * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(&unreduced, c->d_unreduced, 4, cudaMemcpyDeviceToHost, c->stream));
+    {
+        int rcb = ctx_result_buffer(c, (size_t)r->n_batch + 1);
+        if (rcb != ZKB_OK) return rcb;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_res, r->d_first_fail, (size_t)r->n_batch * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_res + r->n_batch, c->d_unreduced, 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaEventRecord(c->ev[3], c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
@@ -672,10 +674,9 @@ extern "C" int zkb_r1cs_run(zkb_ctx* c, zkb_verdict* out) {
     c->timing.kernel_launches = launches;
     // values >= p are legal inputs for the reference (kept raw, reduced by the first Mul/Add they meet):
     // every z value passes through Mul(var, const) or the LC additions, so residues are exact here.
-    (void)unreduced;
     if (out)
         for (uint32_t j = 0; j < r->n_batch; j++) {
-            uint32_t f = c->h_first_fail[j];
+            uint32_t f = c->h_res[j];
             memset(&out[j], 0, sizeof(zkb_verdict));
             out[j].ok = f == 0xFFFFFFFFu;
             out[j].first_fail_seq = f == 0xFFFFFFFFu ? UINT64_MAX : f;
