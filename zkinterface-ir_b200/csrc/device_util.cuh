@@ -1,6 +1,7 @@
 // Device helpers shared by kernels.cu and r1cs.cu: wire-store element access (limb-chunk-major,
 // witness-minor layout, see kernels.cuh) and AssertZero failure reporting.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -168,6 +169,16 @@ __device__ __forceinline__ void report_fail(bool fail, uint32_t seq, uint32_t* f
     } else if (fail) {
         atomicMin(first_fail + widx, seq);
     }
+}
+
+// Function attributes (cudaFuncSetAttribute) are per device: true the first time a launch site sees the current device.
+// One host thread per device may be launching at the same time (zkb_evaluate_sharded), hence the atomic mask.
+inline bool first_on_device(std::atomic<uint64_t>& seen) {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d >= 64) return true;
+    const uint64_t bit = 1ull << d;
+    return (seen.fetch_or(bit) & bit) == 0;
 }
 
 }  // namespace zkb

@@ -962,9 +962,11 @@ void launch_level(int nlimb, const GateOp* ops, const uint32_t* aseq, uint64_t n
                 k_level_pipe<1, 4><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, consts_mont, first_fail, g, fp);
             } else if (nlimb == 8 && g.log2_wt >= 8 && level_tma_enabled()) {
                 static int tma_per_sm = 0;
+                static std::atomic<uint64_t> tma_attr_seen{0};
                 constexpr size_t smem = kTmaSmemBytes;
-                if (!tma_per_sm) {
+                if (first_on_device(tma_attr_seen))
                     cudaFuncSetAttribute(k_level_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (!tma_per_sm) {
                     const char* e = getenv("ZKB_TMA_GRID_PER_SM");
                     tma_per_sm = e ? std::max(1, atoi(e)) : 128;
                 }
@@ -1160,11 +1162,10 @@ void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, 
 void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* gops, const uint32_t* tables,
                         const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s) {
     if (n_groups == 0 || total_calls == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {  // up to kMaxTemplateRegs x 256 threads x 16 bytes
+    static std::atomic<uint64_t> attr_seen{0};
+    if (first_on_device(attr_seen)) {  // up to kMaxTemplateRegs x 256 threads x 16 bytes
         cudaFuncSetAttribute(k_bool_groups<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 4));
         cudaFuncSetAttribute(k_bool_groups<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 16));
-        attr_set = true;
     }
     const uint32_t log2_words = g.log2_wt - 5;
     const bool wide = log2_words >= 2;

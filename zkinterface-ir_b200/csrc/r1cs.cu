@@ -348,8 +348,10 @@ template <int N>
 static void launch_r1cs_check(zkb_ctx* c, R1csDev* r, const R1csLayout& L, TileGeom g, const FieldParams& fp) {
     const size_t smem = R1csSmem<N>::bytes;
     static int per_sm = 0;
-    if (!per_sm) {
+    static std::atomic<uint64_t> attr_seen{0};
+    if (first_on_device(attr_seen))  // per device: a second GPU of the process needs its own opt-in to 56 KB of shared memory
         cudaFuncSetAttribute(k_r1cs_check<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!per_sm) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_r1cs_check<N>, kR1csThreads, smem);
         if (per_sm < 1) per_sm = 1;
         if (const char* e = getenv("ZKB_R1CS_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
