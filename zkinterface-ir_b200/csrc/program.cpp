@@ -6,6 +6,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <memory>
+#include <atomic>
 #include <iterator>
 #include <chrono>
 #include <thread>
@@ -197,31 +199,66 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
     std::vector<uint8_t> used(n, 0);  // consumed by another value
     uint32_t max_level = 0;
     constexpr uint32_t kAhead = 16;  // operands are random earlier values: start their loads a few iterations early
-    for (uint32_t v = 0; v < n; v++) {
-        if (v + kAhead < n) {
-            __builtin_prefetch(&level[opa[v + kAhead] < n ? opa[v + kAhead] : 0]);
-            __builtin_prefetch(&level[opb[v + kAhead] < n ? opb[v + kAhead] : 0]);
+    // level(v) = 1 + max(level(operands)) over values in program order.  The chain is sequential in principle, but the
+    // operands of a random circuit lie far back: chunks of 2^10 values (2^15: 0.93 s, 2^12: 0.38 s, 2^10: 0.19 s, 2^8: 0.26 s for C3 on 8 threads) are handed to the threads in order, a thread publishes
+    // how far into its chunk it has got, and a reader only waits when its operand sits in a chunk that is still being worked on
+    // (it never waits on a later chunk, and every claimed chunk is worked to its end: no deadlock).  A circuit whose operands
+    // are all recent (a window of a few thousand wires) degenerates to one thread at a time — no slower than the plain loop.
+    constexpr uint32_t kChunkLog2 = 10, kChunk = 1u << kChunkLog2;
+    const uint32_t n_chunks = (uint32_t)(((uint64_t)n + kChunk - 1) >> kChunkLog2);
+    std::unique_ptr<std::atomic<uint32_t>[]> progress(new std::atomic<uint32_t>[n_chunks ? n_chunks : 1]);
+    for (uint32_t i = 0; i < n_chunks; i++) progress[i].store(0, std::memory_order_relaxed);
+    std::atomic<uint32_t> next_chunk{0};
+    const unsigned Tl = T;  // (T is 1 below 2^18 values)
+    std::vector<uint32_t> thread_max(Tl, 0);
+    uint32_t* lvl = level.data();
+    uint8_t* usd = used.data();
+    auto level_worker = [&](unsigned t) {
+        uint32_t local_max = 0;
+        for (;;) {
+            const uint32_t c = next_chunk.fetch_add(1, std::memory_order_relaxed);
+            if (c >= n_chunks) break;
+            const uint32_t b = c << kChunkLog2, e = (uint32_t)std::min<uint64_t>(n, (uint64_t)b + kChunk);
+            auto level_of = [&](uint32_t u) -> uint32_t {
+                const uint32_t cu = u >> kChunkLog2;
+                if (cu != c) {
+                    const uint32_t need = u - (cu << kChunkLog2) + 1;
+                    while (progress[cu].load(std::memory_order_acquire) < need) __builtin_ia32_pause();
+                }
+                __atomic_store_n(&usd[u], (uint8_t)1, __ATOMIC_RELAXED);
+                return lvl[u];
+            };
+            for (uint32_t v = b; v < e; v++) {
+                if (v + kAhead < e) {
+                    __builtin_prefetch(&lvl[opa[v + kAhead] < n ? opa[v + kAhead] : 0]);
+                    __builtin_prefetch(&lvl[opb[v + kAhead] < n ? opb[v + kAhead] : 0]);
+                }
+                const uint8_t k = kind[v];
+                uint32_t lv = 0;
+                if (k > V_WITNESS) {
+                    // a group output (implicit value, program.h) is ready before the first wavefront, like an input, and always stored
+                    uint32_t la = is_callout(opa[v]) ? 0 : level_of(opa[v]);
+                    const bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
+                    if (two && !is_callout(opb[v])) la = std::max(la, level_of(opb[v]));
+                    lv = la + 1;
+                    if (lv > local_max) local_max = lv;
+                }
+                lvl[v] = lv;
+                if (Tl > 1 && ((v - b) & 255) == 255) progress[c].store(v - b + 1, std::memory_order_release);
+            }
+            progress[c].store(e - b, std::memory_order_release);
         }
-        uint8_t k = kind[v];
-        if (k <= V_WITNESS) {
-            level[v] = 0;
-            continue;
-        }
-        // a group output (implicit value, program.h) is ready before the first wavefront, like an input, and always stored
-        uint32_t la = 0;
-        if (!is_callout(opa[v])) {
-            la = level[opa[v]];
-            used[opa[v]] = 1;
-        }
-        bool two = (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR);
-        if (two && !is_callout(opb[v])) {
-            uint32_t lb = level[opb[v]];
-            used[opb[v]] = 1;
-            if (lb > la) la = lb;
-        }
-        level[v] = la + 1;
-        if (la + 1 > max_level) max_level = la + 1;
+        thread_max[t] = local_max;
+    };
+    if (Tl > 1) {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < Tl; t++) pool.emplace_back(level_worker, t);
+        level_worker(0);
+        for (auto& th : pool) th.join();
+    } else {
+        level_worker(0);
     }
+    for (unsigned t = 0; t < Tl; t++) max_level = std::max(max_level, thread_max[t]);
     // what a call group reads is consumed (stored); groups only read level-0 values, so nothing else changes
     // (the loops of a nest usually read the same progressions: each distinct one is walked once)
     struct Progression {
