@@ -852,13 +852,26 @@ k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t t
             *reinterpret_cast<V*>(Rin + k * RS) = vstore[((size_t)slot << log2_vecs) + vw];
         }
         const uint4* op = reinterpret_cast<const uint4*>(gops + h0.x);
+        uint32_t r[WPT];  // the previous op's result stays in registers: an operand that names it is not re-read (GroupOp::fwd)
+#pragma unroll
+        for (int k = 0; k < WPT; k++) r[k] = 0;
 #pragma unroll 2
         for (uint32_t i = 0; i < h0.y; i++) {
-            const uint4 o = __ldg(op + 2 * i);      // dst_off, a_off, b_off (in units of one register row: x WPT here)
+            const uint4 o = __ldg(op + 2 * i);      // dst_off, a_off, b_off (in units of one register row: x WPT here), fwd
             const uint4 m = __ldg(op + 2 * i + 1);  // m_and, m_xor, m_a, m_c
-            uint32_t a[WPT], b[WPT], r[WPT];
-            unpack(*reinterpret_cast<const V*>(R + o.y * WPT), a);
-            unpack(*reinterpret_cast<const V*>(R + o.z * WPT), b);
+            uint32_t a[WPT], b[WPT];
+            if (o.w & 1) {
+#pragma unroll
+                for (int k = 0; k < WPT; k++) a[k] = r[k];
+            } else {
+                unpack(*reinterpret_cast<const V*>(R + o.y * WPT), a);
+            }
+            if (o.w & 2) {
+#pragma unroll
+                for (int k = 0; k < WPT; k++) b[k] = r[k];
+            } else {
+                unpack(*reinterpret_cast<const V*>(R + o.z * WPT), b);
+            }
 #pragma unroll
             for (int k = 0; k < WPT; k++) r[k] = (a[k] & b[k] & m.x) ^ ((a[k] ^ b[k]) & m.y) ^ (a[k] & m.z) ^ m.w;
             V v;

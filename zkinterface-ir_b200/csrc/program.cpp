@@ -603,6 +603,7 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
         for (size_t t = 0; t < prog.templates.size(); t++) {
             group_regs = std::max(group_regs, prog.templates[t].n_regs);
             tmpl_off[t] = (uint32_t)group_ops.size();
+            uint32_t prev_dst = 0xFFFFFFFFu;
             for (const TmplOp& o : prog.templates[t].ops) {
                 GroupOp g{};
                 const uint32_t all = 0xFFFFFFFFu;
@@ -620,6 +621,11 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                     case V_MULC: g.m_a = cmask; break;
                     default: g.m_c = cmask; break;  // V_CONST
                 }
+                if (o.kind != V_CONST && prev_dst != 0xFFFFFFFFu) {
+                    if (o.a == prev_dst) g.fwd |= 1;
+                    if ((two ? o.b : o.a) == prev_dst) g.fwd |= 2;
+                }
+                prev_dst = o.dst;
                 group_ops.push_back(g);
             }
         }

@@ -126,8 +126,10 @@ struct GroupDesc {  // 16-byte aligned
 //   Xor / Add: m_xor = ~0;  And / Mul: m_and = ~0;  Not: m_a = m_c = ~0;  AddConstant c: m_a = ~0, m_c = -c;
 //   MulConstant c: m_a = -c;  Constant c: m_c = -c   (c = the constant mod 2; one-input ops read a twice)
 constexpr uint32_t kGroupThreads = 256;
+// fwd: bit 0 / bit 1 = operand a / b is the result of the previous op, which the interpreter still holds in registers (5 of the
+// 16 operand reads of C5's body): no shared-memory load for it
 struct GroupOp {
-    uint32_t dst_off, a_off, b_off, pad;
+    uint32_t dst_off, a_off, b_off, fwd;
     uint32_t m_and, m_xor, m_a, m_c;
 };
 constexpr uint32_t kGroupHintShift = 7;  // Plan::group_hints: one entry per 128 calls of a launch
