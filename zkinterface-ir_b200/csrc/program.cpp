@@ -223,7 +223,12 @@ void Plan::build(const Program& prog, bool keep_all, const std::vector<uint32_t>
                 const uint32_t cu = u >> kChunkLog2;
                 if (cu != c) {
                     const uint32_t need = u - (cu << kChunkLog2) + 1;
-                    while (progress[cu].load(std::memory_order_acquire) < need) __builtin_ia32_pause();
+                    // (more threads than free cores: the chunk's owner may be descheduled, so a waiter that has spun a while
+                    // gives its time slice away instead of burning it — 2.1 s instead of 0.012 s measured with 32 threads on 16 cores)
+                    for (uint32_t spins = 0; progress[cu].load(std::memory_order_acquire) < need; spins++) {
+                        if (spins < 256) __builtin_ia32_pause();
+                        else std::this_thread::yield();
+                    }
                 }
                 __atomic_store_n(&usd[u], (uint8_t)1, __ATOMIC_RELAXED);
                 return lvl[u];
