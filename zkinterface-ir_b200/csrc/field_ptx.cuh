@@ -17,6 +17,14 @@
 
 #if defined(__CUDA_ARCH__) && !defined(ZKB_NO_PTX_FIELD)
 #define ZKB_FIELD_PTX 1
+// accumulator operands of the chains: early-clobber (see the note above mad_chain4); -DZKB_NO_EARLY_CLOBBER for the A/B only —
+// the lazy-reduction code is wrong without it
+#ifdef ZKB_NO_EARLY_CLOBBER
+#define ZKB_ACC_C "+r"
+#else
+#define ZKB_ACC_C "+&r"
+#endif
+#define ZKB_ACC(x) ZKB_ACC_C(x)
 
 namespace zkb {
 
@@ -51,7 +59,7 @@ __device__ __forceinline__ uint32_t mad_chain4(uint32_t* acc, uint32_t x0, uint3
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.u32 %8, %14, 0;"
-        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(c)
+        : ZKB_ACC(acc[0]), ZKB_ACC(acc[1]), ZKB_ACC(acc[2]), ZKB_ACC(acc[3]), ZKB_ACC(acc[4]), ZKB_ACC(acc[5]), ZKB_ACC(acc[6]), ZKB_ACC(acc[7]), "=r"(c)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(cin));
     return c;
 }
@@ -70,7 +78,7 @@ __device__ __forceinline__ uint32_t mad_chain4_fold(uint32_t& e0, uint32_t f0, u
         "madc.lo.cc.u32 %6, %15, %16, %6;\n\t"
         "madc.hi.cc.u32 %7, %15, %16, %7;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(c),
+        : ZKB_ACC(acc[0]), ZKB_ACC(acc[1]), ZKB_ACC(acc[2]), ZKB_ACC(acc[3]), ZKB_ACC(acc[4]), ZKB_ACC(acc[5]), ZKB_ACC(acc[6]), ZKB_ACC(acc[7]), "=r"(c),
           "=r"(e0)
         : "r"(f0), "r"(f1), "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
     return c;
@@ -91,7 +99,7 @@ __device__ __forceinline__ uint32_t mad_chain4_cbot(uint32_t* acc, uint32_t x0, 
         "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
         "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]), "=r"(c), "=r"(t)
+        : ZKB_ACC(acc[0]), ZKB_ACC(acc[1]), ZKB_ACC(acc[2]), ZKB_ACC(acc[3]), ZKB_ACC(acc[4]), ZKB_ACC(acc[5]), ZKB_ACC(acc[6]), ZKB_ACC(acc[7]), "=r"(c), "=r"(t)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(cbot));
     return c;
 }
@@ -105,7 +113,7 @@ __device__ __forceinline__ uint32_t mad_chain2_cbot(uint32_t* acc, uint32_t x0, 
         "madc.lo.cc.u32 %2, %7, %8, %2;\n\t"
         "madc.hi.cc.u32 %3, %7, %8, %3;\n\t"
         "addc.u32 %4, 0, 0;"
-        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=r"(c), "=r"(t)
+        : ZKB_ACC(acc[0]), ZKB_ACC(acc[1]), ZKB_ACC(acc[2]), ZKB_ACC(acc[3]), "=r"(c), "=r"(t)
         : "r"(x0), "r"(x1), "r"(y), "r"(cbot));
     return c;
 }
@@ -124,7 +132,7 @@ __device__ __forceinline__ uint32_t mad_chain2(uint32_t* acc, uint32_t x0, uint3
         "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
         "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
         "addc.u32 %4, %8, 0;"
-        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=r"(c)
+        : ZKB_ACC(acc[0]), ZKB_ACC(acc[1]), ZKB_ACC(acc[2]), ZKB_ACC(acc[3]), "=r"(c)
         : "r"(x0), "r"(x1), "r"(y), "r"(cin));
     return c;
 }
@@ -137,7 +145,7 @@ __device__ __forceinline__ uint32_t mad_chain2_fold(uint32_t& e0, uint32_t f0, u
         "madc.lo.cc.u32 %2, %9, %10, %2;\n\t"
         "madc.hi.cc.u32 %3, %9, %10, %3;\n\t"
         "addc.u32 %4, 0, 0;"
-        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=r"(c), "=r"(e0)
+        : ZKB_ACC(acc[0]), ZKB_ACC(acc[1]), ZKB_ACC(acc[2]), ZKB_ACC(acc[3]), "=r"(c), "=r"(e0)
         : "r"(f0), "r"(f1), "r"(x0), "r"(x1), "r"(y));
     return c;
 }
