@@ -125,6 +125,51 @@ def test_sharded_every_gate_kind_with_instances_and_raw_inputs():
         sh.close()
 
 
+@pytest.mark.parametrize("devices", [[0, 0, 0], "all"])
+def test_call_groups_travel_with_the_program(devices):
+    """a relation recorded as loop-structured call groups (C5's shape): the group descriptors, pre-decoded ops, hints and the
+    implicit-value slots reach the replicas with the broadcast; verdicts = one context's, outputs readable on every rank"""
+    from oracle import ir, sieve_fbs as F, workloads as wl
+    z = zkb()
+    if devices == "all":
+        if _n_devices() < 2:
+            pytest.skip("needs two devices (NCCL transport)")
+        devices = list(range(_n_devices()))
+    lo, li, n_wit = 4, 5, 256
+    rel, _ = wl.boolean_for_relation(lo, li, n_wit)
+    buf = F.write_messages([ir.Witness(rel.header, [b"\0"] * n_wit), rel])
+    n_batch = 70
+    rng = np.random.default_rng(9)
+    W = rng.integers(0, 2, size=(n_batch, n_wit, 1)).astype(np.uint8)
+
+    one = z.GpuBackend(0)
+    e1 = z.Evaluator(one)
+    e1.ingest_source(z.Source.from_buffers([buf]))
+    one.finalize(keep_all_values=True)
+    v_one = one.evaluate(None, W, n_batch)
+
+    sh = z.ShardedBackend(devices)
+    e = z.Evaluator(sh.root)
+    e.ingest_source(z.Source.from_buffers([buf]))
+    assert sh.root.stats()["n_call_groups"] == 1 << lo
+    sh.root.finalize(keep_all_values=True)
+    v = sh.evaluate(None, W, n_batch)
+    assert (v["ok"] == v_one["ok"]).all() and (v["first_fail_seq"] == v_one["first_fail_seq"]).all()
+    n_out = (1 << lo) * (2 << li)
+    handles = [e.value_handle(n_wit + k) for k in range(0, n_out, 5)]
+    for r in range(len(devices)):
+        b_lo, b_hi = sh.shard_of(r, n_batch)
+        for j in (b_lo, b_hi - 1):
+            b, local = sh.owner(j, n_batch)
+            outs = wl.boolean_for_expected_outputs(W[j, :, 0], lo, li).reshape(-1)
+            assert b.read_values(local, handles, 4) == [int(outs[k]) for k in range(0, n_out, 5)], (r, j)
+    st0, st1 = sh.root.stats(), sh.backends[-1].stats()
+    for k in ("n_values", "n_call_groups", "n_group_calls", "n_group_launches", "n_slots", "n_device_ops"):
+        assert st0[k] == st1[k], k
+    sh.close()
+    one.close()
+
+
 def test_boolean_program_sharded():
     z, c = zkb(), circuits()
     gates, pool, n_wires = random_flat_program(2, 2000, 6, 10, seed=5, bool_ops=True)
