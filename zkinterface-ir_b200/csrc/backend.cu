@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 #include "context.h"
 
@@ -297,6 +299,189 @@ extern "C" int zkb_witness(zkb_ctx* c, zkb_wire* out) {
 // ------------------------------------------------------------------------------------------
 // 3. bulk flat gates — the simple arms of Evaluator::ingest_gate (evaluator.rs:344-439)
 // ------------------------------------------------------------------------------------------
+// Bulk form of the gate loop below for long regular runs (what a builder-produced relation is: C3 = 2^24 gates in one call),
+// the same three passes as the Evaluator's bulk ingest of flat FlatBuffers messages (evaluator.cpp: ingest_flat_window), over
+// chunks of the gate array on the plan threads:
+//   count    values / assertions / stream positions per chunk -> prefix sums give every chunk its handle range
+//   define   kind + operand WIRES written at the final position, the output wire bound with a compare-and-swap
+//   resolve  operand wires -> handles of values bound EARLIER in program order
+// Anything irregular — Copy, Free, a wire defined twice or used before its definition, an index out of range, flatten /
+// expand-definable mode, ids the dense scope table may not hold — undoes everything and returns false: the gate loop then
+// runs from the start and reports the error where the reference does.  true: recorded, state as the gate loop leaves it.
+static bool push_gates_bulk(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gates, const std::vector<uint32_t>& cidx) {
+    Program& p = c->prog;
+    Scope& sc = c->flat_scope;
+    const unsigned T = plan_threads();
+    if (n_gates < (1u << 16) || T < 2 || p.keep_copies || p.expand_on || !sc.sparse.empty() || getenv("ZKB_NO_BULK_PUSH")) return false;
+    constexpr uint64_t kChunk = 1u << 16;
+    const uint64_t n_chunks = (n_gates + kChunk - 1) / kChunk;
+    struct Count {
+        uint64_t values = 0, asserts = 0, inst = 0, wit = 0, by_op[16] = {0};
+        uint32_t max_out = 0;
+        bool ok = true;
+    };
+    std::vector<Count> cnt(n_chunks);
+    auto parallel = [&](uint64_t n, auto fn) {
+        std::atomic<uint64_t> next{0};
+        auto work = [&]() {
+            for (uint64_t i; (i = next.fetch_add(1)) < n;) fn(i);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T && t < n; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    };
+    const uint64_t n_consts = cidx.size();
+    parallel(n_chunks, [&](uint64_t ch) {
+        Count& k = cnt[ch];
+        const uint64_t lo = ch * kChunk, hi = std::min(n_gates, lo + kChunk);
+        for (uint64_t i = lo; i < hi; i++) {
+            const zkb_gate& g = gates[i];
+            switch (g.op) {
+                case ZKB_G_ASSERT_ZERO: k.asserts++; break;
+                case ZKB_G_CONSTANT: case ZKB_G_ADD_CONSTANT: case ZKB_G_MUL_CONSTANT:
+                    if (g.b >= n_consts) k.ok = false;
+                    // fall through
+                case ZKB_G_ADD: case ZKB_G_MUL: case ZKB_G_AND: case ZKB_G_XOR: case ZKB_G_NOT:
+                    k.values++;
+                    k.max_out = std::max(k.max_out, g.out);
+                    break;
+                case ZKB_G_INSTANCE: k.values++; k.inst++; k.max_out = std::max(k.max_out, g.out); break;
+                case ZKB_G_WITNESS: k.values++; k.wit++; k.max_out = std::max(k.max_out, g.out); break;
+                default: k.ok = false; break;  // Copy, Free, unknown opcodes
+            }
+            k.by_op[g.op & 15]++;
+        }
+    });
+    uint64_t tv = 0, ta = 0, ti = 0, tw = 0;
+    uint32_t max_out = 0;
+    for (const Count& k : cnt) {
+        if (!k.ok) return false;
+        tv += k.values; ta += k.asserts; ti += k.inst; tw += k.wit;
+        max_out = std::max(max_out, k.max_out);
+    }
+    const uint64_t v0 = p.n_values(), a0 = p.asserts.size();
+    if (tv == 0 || p.n_total_values() + tv >= c->max_values || v0 + tv >= kCalloutBit || a0 + ta >= 0xFFFFFFF0ull) return false;
+    if ((uint64_t)p.n_instance + ti >= 0xFFFFFFFFull || (uint64_t)p.n_witness + tw >= 0xFFFFFFFFull) return false;
+    if (!sc.ensure_dense(max_out, tv)) return false;
+    p.kind.resize(v0 + tv);
+    p.opa.resize(v0 + tv);
+    p.opb.resize(v0 + tv);
+    p.asserts.resize(a0 + ta);
+    struct Base { uint64_t v, a, inst, wit; };
+    std::vector<Base> base(n_chunks);
+    {
+        uint64_t v = v0, a = a0, ii = p.n_instance, ww = p.n_witness;
+        for (uint64_t ch = 0; ch < n_chunks; ch++) {
+            base[ch] = Base{v, a, ii, ww};
+            v += cnt[ch].values; a += cnt[ch].asserts; ii += cnt[ch].inst; ww += cnt[ch].wit;
+        }
+    }
+    std::atomic<bool> bad{false};
+    uint32_t* dense = sc.dense.data();
+    const size_t dn = sc.dense.size();
+    parallel(n_chunks, [&](uint64_t ch) {
+        uint64_t v = base[ch].v, a = base[ch].a, ii = base[ch].inst, ww = base[ch].wit;
+        const uint64_t lo = ch * kChunk, hi = std::min(n_gates, lo + kChunk);
+        for (uint64_t i = lo; i < hi; i++) {
+            const zkb_gate& g = gates[i];
+            if (g.op == ZKB_G_ASSERT_ZERO) {
+                p.asserts[a++] = AssertRec{g.a, (uint32_t)v, g.a};  // value: the wire for now (resolved below)
+                continue;
+            }
+            uint8_t kind;
+            uint32_t oa = 0, ob = 0;
+            switch (g.op) {
+                case ZKB_G_CONSTANT: kind = V_CONST; ob = cidx[g.b]; break;
+                case ZKB_G_ADD: kind = V_ADD; oa = g.a; ob = g.b; break;
+                case ZKB_G_MUL: kind = V_MUL; oa = g.a; ob = g.b; break;
+                case ZKB_G_AND: kind = V_AND; oa = g.a; ob = g.b; break;
+                case ZKB_G_XOR: kind = V_XOR; oa = g.a; ob = g.b; break;
+                case ZKB_G_NOT: kind = V_NOT; oa = g.a; break;
+                case ZKB_G_ADD_CONSTANT: kind = V_ADDC; oa = g.a; ob = cidx[g.b]; break;
+                case ZKB_G_MUL_CONSTANT: kind = V_MULC; oa = g.a; ob = cidx[g.b]; break;
+                case ZKB_G_INSTANCE: kind = V_INSTANCE; ob = (uint32_t)ii++; break;
+                default: kind = V_WITNESS; ob = (uint32_t)ww++; break;
+            }
+            p.kind[v] = kind;
+            p.opa[v] = oa;
+            p.opb[v] = ob;
+            uint32_t expect = Scope::kNone;
+            if (!__atomic_compare_exchange_n(&dense[g.out], &expect, (uint32_t)v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                bad = true;  // "Wire_{id} already has a value in this scope."
+                return;
+            }
+            v++;
+        }
+    });
+    if (!bad) {
+        const uint64_t vchunks = (tv + kChunk - 1) / kChunk, achunks = (ta + kChunk - 1) / kChunk;
+        parallel(vchunks + achunks, [&](uint64_t ch) {
+            if (ch < vchunks) {
+                const uint64_t lo = v0 + ch * kChunk, hi = std::min(v0 + tv, lo + kChunk);
+                for (uint64_t v = lo; v < hi; v++) {
+                    const uint8_t k = p.kind[v];
+                    if (k < V_ADD) continue;
+                    const uint32_t wa = p.opa[v];
+                    const uint32_t ra = wa < dn ? dense[wa] : Scope::kNone;
+                    if (ra >= v) { bad = true; return; }  // undefined, bound later, or an implicit value: the gate loop decides
+                    p.opa[v] = ra;
+                    if (k == V_ADD || k == V_MUL || k == V_AND || k == V_XOR) {
+                        const uint32_t wb = p.opb[v];
+                        const uint32_t rb = wb < dn ? dense[wb] : Scope::kNone;
+                        if (rb >= v) { bad = true; return; }
+                        p.opb[v] = rb;
+                    }
+                }
+            } else {
+                const uint64_t lo = a0 + (ch - vchunks) * kChunk, hi = std::min(a0 + ta, lo + kChunk);
+                for (uint64_t a = lo; a < hi; a++) {
+                    AssertRec& r = p.asserts[a];
+                    const uint32_t rv = r.value < dn ? dense[r.value] : Scope::kNone;
+                    if (rv >= r.pos) { bad = true; return; }
+                    r.value = rv;
+                }
+            }
+        });
+    }
+    if (bad) {  // undo: unbind what this call bound, drop its values
+        parallel(n_chunks, [&](uint64_t ch) {
+            const uint64_t lo = ch * kChunk, hi = std::min(n_gates, lo + kChunk);
+            for (uint64_t i = lo; i < hi; i++) {
+                const zkb_gate& g = gates[i];
+                if (g.op == ZKB_G_ASSERT_ZERO || g.out >= dn) continue;
+                const uint32_t d = __atomic_load_n(&dense[g.out], __ATOMIC_RELAXED);
+                if (d != Scope::kNone && d >= v0 && d < v0 + tv) __atomic_store_n(&dense[g.out], Scope::kNone, __ATOMIC_RELAXED);
+            }
+        });
+        p.kind.resize(v0);
+        p.opa.resize(v0);
+        p.opb.resize(v0);
+        p.asserts.resize(a0);
+        return false;
+    }
+    uint64_t by_op[16] = {0};
+    for (const Count& k : cnt)
+        for (int o = 0; o < 16; o++) by_op[o] += k.by_op[o];
+    p.cb_count[CB_CONSTANT] += by_op[ZKB_G_CONSTANT];
+    p.cb_count[CB_ADD] += by_op[ZKB_G_ADD];
+    p.cb_count[CB_MUL] += by_op[ZKB_G_MUL];
+    p.cb_count[CB_ADDC] += by_op[ZKB_G_ADD_CONSTANT];
+    p.cb_count[CB_MULC] += by_op[ZKB_G_MUL_CONSTANT];
+    p.cb_count[CB_AND] += by_op[ZKB_G_AND];
+    p.cb_count[CB_XOR] += by_op[ZKB_G_XOR];
+    p.cb_count[CB_NOT] += by_op[ZKB_G_NOT];
+    p.cb_count[CB_INSTANCE] += by_op[ZKB_G_INSTANCE];
+    p.cb_count[CB_WITNESS] += by_op[ZKB_G_WITNESS];
+    p.cb_count[CB_COPY] += by_op[ZKB_G_ASSERT_ZERO];  // an unweighted assertion tests a copy (evaluator.rs:355)
+    p.cb_count[CB_ASSERT_ZERO] += by_op[ZKB_G_ASSERT_ZERO];
+    p.ir_gates += n_gates - by_op[ZKB_G_CONSTANT] - by_op[ZKB_G_INSTANCE] - by_op[ZKB_G_WITNESS];
+    p.n_instance += (uint32_t)ti;
+    p.n_witness += (uint32_t)tw;
+    sc.bulk_inserted(tv);
+    return true;
+}
+
 extern "C" int zkb_push_gates(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gates, const uint8_t* pool, size_t cstride,
                               uint64_t n_consts) {
     REC_PROLOGUE(c);
@@ -318,6 +503,7 @@ extern "C" int zkb_push_gates(zkb_ctx* c, const zkb_gate* gates, uint64_t n_gate
     // constants of this call are interned once
     std::vector<uint32_t> cidx(n_consts);
     for (uint64_t i = 0; i < n_consts; i++) cidx[i] = p.intern_const(pool + i * cstride, cstride);
+    if (push_gates_bulk(c, gates, n_gates, cidx)) return ZKB_OK;
     p.kind.reserve(p.kind.size() + n_gates);
     p.opa.reserve(p.opa.size() + n_gates);
     p.opb.reserve(p.opb.size() + n_gates);

@@ -146,7 +146,7 @@ static inline uint32_t dev_op_of(uint8_t k) {
 // The passes of Plan::build that walk values in sorted (i.e. random) order wait on DRAM latency, not on arithmetic:
 // a few threads multiply the misses in flight.  Every parallel pass produces exactly what its sequential form does
 // (positions, slots and release order are derived from prefix sums, not from arrival order).
-static unsigned plan_threads() {
+unsigned plan_threads() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("ZKB_PLAN_THREADS");

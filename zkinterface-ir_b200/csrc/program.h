@@ -273,6 +273,9 @@ public:
     std::vector<uint8_t> minus_one_le() const;
 };
 
+// threads of the host passes that are split over chunks (ZKB_PLAN_THREADS, default min(8, cores))
+unsigned plan_threads();
+
 struct Plan {
     uint32_t n_slots = 0;
     uint32_t n_levels = 0;
