@@ -22,7 +22,7 @@ export ZKB_LIB_PATH=$PWD/$OUT/libzkb.so
 export LD_PRELOAD="$(gcc -print-file-name=libtsan.so)"
 export TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0 suppressions=$PWD/scripts/tsan.supp"
 export ZKB_PLAN_THREADS=6 ZKB_PARSE_THREADS=6
-python -m pytest tests/test_flat_ingest_host.py tests/test_host_evaluator.py tests/test_call_groups.py tests/test_robustness_host.py \
+python -m pytest tests/test_flat_ingest_host.py tests/test_host_evaluator.py tests/test_call_groups.py tests/test_robustness_host.py tests/test_bulk_push_host.py \
   -x -q -m "not gpu" -p no:cacheprovider 2>&1 | tee /tmp/tsan_pytest.log | grep -E "WARNING: ThreadSanitizer|SUMMARY: ThreadSanitizer|passed|failed" | sort | uniq -c | sort -rn | head -20
 python - <<'PY' 2>&1 | grep -E "WARNING: ThreadSanitizer|SUMMARY: ThreadSanitizer|plan ok" | sort | uniq -c | sort -rn | head -20
 import sys, importlib
