@@ -2,8 +2,9 @@
 //
 // Reference seam: `trait ZKBackend` + `PlaintextBackend` (rust/src/consumers/evaluator.rs:17-76,
 // 848-947) and the simple arms of `Evaluator::ingest_gate` (:344-439).  The backend is deferred:
-// callbacks record SSA values (program.h); zkb_finalize levelizes; zkb_run streams tiles of
-// witnesses through one kernel launch per wavefront.
+// callbacks record SSA values (program.h; long regular runs of zkb_push_gates in bulk on several threads); zkb_finalize
+// levelizes; zkb_run streams tiles of witnesses through one kernel launch per wavefront — or, for launch-bound programs,
+// through one launch for all wavefronts (cluster / grid barrier, or the barrier-free dataflow launch).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>

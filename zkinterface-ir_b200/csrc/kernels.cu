@@ -7,7 +7,12 @@
 //   k_load_inputs  `constant` / `instance` / `witness` (:896-898, 940-946): raw little-endian
 //                  values -> Montgomery residues in the wire store
 //   k_read_values  what `Evaluator::get` (:750-752) returns: canonical residues of chosen wires
-//   k_bool_*       the same for p = 2, bit-sliced (32 witnesses per word)
+//   k_level_pipe / k_level_tma   the hot forms of k_level: software-pipelined per-thread vector loads / operand rows
+//                  through the bulk-copy engine into an mbarrier ring (8-limb fields, tiles of >= 256 lanes)
+//   k_levels_coop  every wavefront in one launch, grid or cluster barrier between them (launch-bound programs)
+//   k_levels_flow  every wavefront in one launch with NO barrier: dataflow on marker words (one witness, 1- / 2-limb fields)
+//   k_bool_*       the same for p = 2, bit-sliced (32 witnesses per word); k_bool_groups expands the loop-structured
+//                  call groups of program.h (For over a plain function, evaluator.rs:495-559 + :441-471 + :698-746)
 //
 // No tensor cores on purpose: nothing on this path is a dense contraction.  The work is HBM-bound
 // streaming of wire limbs plus 32-bit integer multiply-add chains (IMAD), see DESIGN.md.
