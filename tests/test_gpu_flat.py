@@ -73,16 +73,17 @@ def test_true_single_witness_values():
     assert st["ir_gates"] == 5000
 
 
-@pytest.mark.parametrize("name", ["p101", "m31", "goldilocks", "p61", "p64full"])
+@pytest.mark.parametrize("name", ["p101", "m31", "goldilocks", "p61", "p64full", "kat124", "bn254", "bls381", "p256full"])
 @pytest.mark.parametrize("flow_min", ["1", "256"])
 @pytest.mark.parametrize("window", [0, 64])
 def test_dataflow_launch_single_witness(name, flow_min, window, monkeypatch):
-    """one witness over a 1- / 2-limb field: every wavefront in ONE barrier-free launch (k_levels_flow: gates poll their
-    operand words until the all-ones marker is gone).  Every gate kind, every wire value and the first failing assertion
+    """one witness: every wavefront in ONE barrier-free launch (k_levels_flow for 1- / 2-limb fields: gates poll their
+    operand words until the all-ones marker is gone; k_levels_flow_wide for 4- / 8-limb fields: a flag word per slot).  Every gate kind, every wire value and the first failing assertion
     against the oracle; ZKB_FLOW_MIN=1 sends even the narrowest program through it, a windowed circuit makes it deep
     (hundreds of wavefronts, producers and consumers in neighbouring warps); ZKB_FLOW=0 must give the same answers."""
     monkeypatch.setenv("ZKB_FLOW_MIN", flow_min)
     monkeypatch.setenv("ZKB_FLOW", "1")
+    monkeypatch.setenv("ZKB_FLOW_WIDE", "1")      # the flag-word variant is opt-in (slower than the barrier kernels): still exact
     c = circuits()
     p = FIELDS[name]
     for seed, corrupt in ((41, {}), (42, {0: 2})):

@@ -81,7 +81,8 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     if (const char* e = getenv("ZKB_SLOT_REUSE")) c->plan.slot_reuse = atoi(e) != 0;
     // small programs over 1- / 2-limb fields keep one slot per value: a single witness then runs as a barrier-free dataflow
     // launch (k_levels_flow), which needs every slot written once; the wire store of such a program is small either way
-    else if (!c->prog.binary && c->prog.nlimb <= 2 && c->prog.n_values() <= (1u << 22)) c->plan.slot_reuse = false;
+    // (ZKB_FLOW_WIDE=1: the same for wider fields, for the flag-word variant that measured slower than the barriers)
+    else if (!c->prog.binary && (c->prog.nlimb <= 2 || getenv("ZKB_FLOW_WIDE")) && c->prog.n_values() <= (1u << 22)) c->plan.slot_reuse = false;
     {
         NvtxRange r("zkb:levelize");
         c->plan.build(c->prog, keep_all, &live);
@@ -186,6 +187,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_scratch_fail);
         cudaFree(c->d_unreduced);
         cudaFree(c->d_barrier);
+        cudaFree(c->d_flow_flags);
         cudaFree(c->d_tab_slot);
         cudaFree(c->d_tab_opb);
         cudaFree(c->d_tab_readable);
@@ -737,7 +739,44 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     // launch-bound programs (levels far too small to fill the chip): all wavefronts in one cooperative launch
     bool coop = !p.binary && pl.n_levels > 1 && ((uint64_t)pl.max_level_ops << c->log2_wt) <= (uint64_t)c->sm_count * 8192;
     if (const char* e = getenv("ZKB_COOP")) coop = coop && atoi(e) != 0;
-    // one witness, 1- / 2-limb field, no slot written twice: every wavefront in one dataflow launch, no barrier (k_levels_flow)
+    // one witness, no slot written twice: every wavefront in one dataflow launch, no barrier.  Wide elements (flag words) are
+    // opt-in (ZKB_FLOW_WIDE=1): two fences per hop made it 1.3-2.1 x SLOWER than the barrier kernels on every shape tried
+    // (profiles/r02n_ab_flow_wide.log) — kept as the measured negative of DESIGN.md section 10
+    if (!p.binary && p.nlimb >= 4 && c->log2_wt == 0 && pl.n_levels > 1 && pl.n_reused_slots == 0 && c->coop_supported &&
+        getenv("ZKB_FLOW_WIDE")) {
+        const char* e = getenv("ZKB_FLOW");
+        const char* em = getenv("ZKB_FLOW_MIN");
+        if ((!e || atoi(e) != 0) && pl.max_level_ops >= (uint32_t)(em ? atoi(em) : 256)) {
+            cudaError_t err = cudaSuccess;
+            if (c->flow_flags_cap < pl.n_slots) {
+                if (c->d_flow_flags) cudaFree(c->d_flow_flags);
+                c->d_flow_flags = nullptr;
+                c->flow_flags_cap = 0;
+                err = cudaMalloc((void**)&c->d_flow_flags, (size_t)pl.n_slots * 4);
+                if (err == cudaSuccess) err = cudaMemsetAsync(c->d_flow_flags, 0, (size_t)pl.n_slots * 4, c->stream);
+                if (err == cudaSuccess) c->flow_flags_cap = pl.n_slots;
+                c->flow_epoch = 0;
+            }
+            if (err == cudaSuccess && ++c->flow_epoch == 0) {  // the run counter wrapped: start over with clean flags
+                err = cudaMemsetAsync(c->d_flow_flags, 0, c->flow_flags_cap * 4, c->stream);
+                c->flow_epoch = 1;
+            }
+            if (err == cudaSuccess)
+                err = launch_levels_flow_wide(p.nlimb, c->d_ops, c->d_aseq, c->d_level_off, pl.n_levels, c->d_store, c->d_consts, d_fail, rawctx, g,
+                                              p.fp, c->sm_count, pl.max_level_ops, (uint32_t)pl.loads.size() + pl.n_callouts, c->d_flow_flags,
+                                              c->flow_epoch, c->stream);
+            if (err == cudaSuccess) {
+                (*launches)++;
+                if (level_launches) (*level_launches)++;
+                if (timed) cudaEventRecord(c->tile_ev[2 * tile + 1], c->stream);
+                c->resident_tile = tile;
+                return;
+            }
+            if (getenv("ZKB_DEBUG")) fprintf(stderr, "zkb: dataflow launch failed: %s\n", cudaGetErrorString(err));
+            cudaGetLastError();
+        }
+    }
+    // 1- / 2-limb fields: the value is its own flag (k_levels_flow)
     if (!p.binary && p.nlimb <= 2 && c->log2_wt == 0 && pl.n_levels > 1 && pl.n_reused_slots == 0 && c->coop_supported) {
         const char* e = getenv("ZKB_FLOW");
         const char* em = getenv("ZKB_FLOW_MIN");

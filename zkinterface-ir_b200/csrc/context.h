@@ -183,6 +183,9 @@ struct zkb_ctx {
     uint32_t* d_scratch_fail = nullptr;
     size_t first_fail_cap = 0;
     uint32_t* d_unreduced = nullptr;
+    uint32_t* d_flow_flags = nullptr;  // dataflow launch over wide elements: per slot, the number of the run that wrote it
+    size_t flow_flags_cap = 0;
+    uint32_t flow_epoch = 0;
     uint32_t* d_barrier = nullptr;   // monotonic arrival counter of the grid barrier
     uint32_t barrier_epoch = 0;      // its value once every launch issued so far has finished
     int64_t resident_tile = -1;

@@ -692,6 +692,70 @@ k_levels_flow(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq,
     }
 }
 
+// The same dataflow launch for elements wider than one atomic word (4- and 8-limb fields): a flag word per slot carries the
+// number of the run that produced the value (never reset: a new run is a new number).  Producer: value stores, fence, flag
+// store; consumer: relaxed polls of both operands' flags, one fence, then the limb loads (L2-coherent).  A hop costs a flag
+// round trip plus a value round trip instead of one, still without any barrier.  Slots below n_ready hold level-0 values
+// (inputs, group outputs) written by earlier kernels of the stream.
+template <int N>
+__global__ void __launch_bounds__(256)
+k_levels_flow_wide(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off,
+                   uint32_t n_levels, uint32_t* store, const uint32_t* __restrict__ consts_mont, uint32_t* __restrict__ first_fail,
+                   RawCtx rc, TileGeom g, FieldParams fp, uint32_t* flags, uint32_t epoch, uint32_t n_ready) {
+    constexpr uint32_t kOffCache = 2048;
+    __shared__ uint64_t s_off[kOffCache + 1];
+    for (uint32_t i = threadIdx.x; i <= n_levels && i <= kOffCache; i += blockDim.x) s_off[i] = level_off[i];
+    __syncthreads();
+    auto off = [&](uint32_t i) -> uint64_t { return i <= kOffCache ? s_off[i] : level_off[i]; };
+    auto peek = [&](uint32_t slot) -> bool {
+        if (slot < n_ready) return true;
+        uint32_t v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + slot) : "memory");
+        return v == epoch;
+    };
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint4* dptr = reinterpret_cast<const uint4*>(ops);
+    uint4 first = make_uint4(0, 0, 0, 0);
+    if (n_levels && off(0) + tid0 < off(1)) first = ldg_pinned(dptr + off(0) + tid0);
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint64_t lo = off(l), hi = off(l + 1);
+        uint4 next_first = make_uint4(0, 0, 0, 0);
+        if (l + 1 < n_levels && hi + tid0 < off(l + 2)) next_first = ldg_pinned(dptr + hi + tid0);
+        for (uint64_t gi = lo + tid0; gi < hi; gi += stride) {
+            const uint4 raw = gi == lo + tid0 ? first : __ldg(dptr + gi);
+            const uint32_t opc = raw.w & 0xff;
+            const bool two = opc == D_ADD || opc == D_MUL || opc == D_AND || opc == D_XOR;
+            bool ra = peek(raw.x), rb = two ? peek(raw.y) : true;
+            while (!ra) ra = peek(raw.x);
+            while (!rb) rb = peek(raw.y);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            uint32_t a[N], b[N], r[N];
+            load_elem_coherent<N>(a, store, raw.x, 0u, 0u);
+            if (opc == D_ADDC || opc == D_MULC) {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = __ldg(consts_mont + (size_t)raw.y * N + k);
+            } else if (two) {
+                load_elem_coherent<N>(b, store, raw.y, 0u, 0u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < N; k++) b[k] = 0;
+            }
+            if (opc == D_ADD || opc == D_ADDC) fe_add<N>(r, a, b, fp.p);
+            else if (opc == D_MUL || opc == D_MULC) fe_mont_mul<N>(r, a, b, fp.p, fp.n0inv);
+            else rare_gate<N>(r, a, b, raw, 0u, g, rc, fp);
+            if (!(raw.w & F_NOSTORE)) {
+                store_elem<N>(store, raw.z, 0u, 0u, r);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + raw.z), "r"(epoch) : "memory");
+            }
+            if ((raw.w & F_ASSERT) && !fe_is_zero<N>(r)) atomicMin(first_fail + g.batch0, __ldg(aseq + gi));
+        }
+        first = next_first;
+        __syncwarp();
+    }
+}
+
 template <int N>
 __global__ void k_read_values(const uint32_t* __restrict__ slots, uint32_t n, const uint32_t* __restrict__ store, uint32_t lane,
                               uint32_t log2_wt, uint32_t* __restrict__ out, FieldParams fp) {
@@ -1141,6 +1205,33 @@ static cudaError_t launch_flow_n(const GateOp* ops, const uint32_t* aseq, const 
                     (void*)&first_fail, (void*)&rc, (void*)&g, (void*)&fp, (void*)&sleep_ns};
     return cudaLaunchCooperativeKernel((void*)k_levels_flow<N>, dim3((unsigned)blocks), dim3(256), args, 0, s);
 }
+template <int N>
+static cudaError_t launch_flow_wide_n(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
+                                      const uint32_t* consts_mont, uint32_t* first_fail, RawCtx rc, TileGeom g, FieldParams fp, int sm_count,
+                                      uint64_t max_level_items, uint32_t n_ready, uint32_t* flags, uint32_t epoch, cudaStream_t s) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_levels_flow_wide<N>, 256, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    uint64_t want = (max_level_items + 255) / 256;
+    uint64_t blocks = ((want + sm_count - 1) / sm_count) * sm_count;
+    if (blocks < (uint64_t)sm_count) blocks = sm_count;
+    if (blocks > (uint64_t)sm_count * per_sm) blocks = (uint64_t)sm_count * per_sm;
+    if (const char* eb = getenv("ZKB_FLOW_BLOCKS")) blocks = std::min<uint64_t>((uint64_t)std::max(1, atoi(eb)), (uint64_t)sm_count * per_sm);
+    void* args[] = {(void*)&ops, (void*)&aseq, (void*)&level_off, (void*)&n_levels, (void*)&store, (void*)&consts_mont,
+                    (void*)&first_fail, (void*)&rc, (void*)&g, (void*)&fp, (void*)&flags, (void*)&epoch, (void*)&n_ready};
+    return cudaLaunchCooperativeKernel((void*)k_levels_flow_wide<N>, dim3((unsigned)blocks), dim3(256), args, 0, s);
+}
+cudaError_t launch_levels_flow_wide(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
+                                    uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
+                                    const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t n_ready, uint32_t* flags,
+                                    uint32_t epoch, cudaStream_t s) {
+    if (g.log2_wt != 0) return cudaErrorNotSupported;
+    if (nlimb == 4) return launch_flow_wide_n<4>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count, max_level_items, n_ready, flags, epoch, s);
+    if (nlimb == 8) return launch_flow_wide_n<8>(ops, aseq, level_off, n_levels, store, consts_mont, first_fail, rc, g, fp, sm_count, max_level_items, n_ready, flags, epoch, s);
+    return cudaErrorNotSupported;
+}
+
 cudaError_t launch_levels_flow(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
                                uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
                                const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t fill_from, uint32_t n_slots,

@@ -59,6 +59,11 @@ cudaError_t launch_levels_flow(int nlimb, const GateOp* ops, const uint32_t* ase
                                uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
                                const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t fill_from, uint32_t n_slots,
                                cudaStream_t s);
+// the same for 4- / 8-limb fields: a flag word per slot holds the number (epoch) of the run that produced the value
+cudaError_t launch_levels_flow_wide(int nlimb, const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels,
+                                    uint32_t* store, const uint32_t* consts_mont, uint32_t* first_fail, const RawCtx& rc, TileGeom g,
+                                    const FieldParams& fp, int sm_count, uint64_t max_level_items, uint32_t n_ready, uint32_t* flags,
+                                    uint32_t epoch, cudaStream_t s);
 // microseconds per barrier of a kernel that does nothing else (kind 0: cooperative_groups grid.sync, 1: the counter barrier of
 // k_levels_coop, 2: the hardware barrier of one 8-CTA cluster)
 cudaError_t measure_barrier_cost(int kind, unsigned blocks, unsigned n_barriers, uint32_t* barrier_ctr, uint32_t* barrier_epoch,
