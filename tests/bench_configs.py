@@ -131,6 +131,64 @@ def c4(log2_rows, log2_free, batch):
             "assignment_gen_s": gen}
 
 
+def c4_rows_sharded(log2_rows, log2_free):
+    """SURVEY 8(e), one assignment: the constraints sharded in contiguous row blocks over every visible GPU (z replicated), one host
+    thread per device, first violated row = MIN over the blocks.  Reports the slowest device's check kernel and the wall time of
+    the concurrent runs beside the one-device figure of the same run."""
+    import threading
+    import torch
+    shard = importlib.import_module("zkir_b200.sharding")
+    n_dev = torch.cuda.device_count()
+    p = c.BN254_FR
+    r = c.random_r1cs(1 << log2_rows, 1 << log2_free, p, 0x5EED0004)
+    zz = c.r1cs_assignment(r, 1)
+    zb = c.assignment_bytes(zz, p)
+    bad_row = (1 << log2_rows) // 3
+    zbad = zb.copy()
+    zbad[r.n_free + 1 + bad_row, 0] ^= 1
+    want_bad = min(bad_row, c.r1cs_first_row_reading(r, r.n_free + 1 + bad_row))
+    out = {}
+    for world in sorted({1, n_dev}):
+        backs, row0 = [], []
+        for rank in range(world):
+            A, B, Cm, lo = shard.shard_r1cs_rows(r.A, r.B, r.C, rank, world)
+            b = z.GpuBackend(rank)
+            b.set_field(p)
+            b.r1cs_load(A, B, Cm, r.coef_table, r.n_vars)
+            backs.append(b)
+            row0.append(lo)
+        # parity: the satisfying assignment and the corrupted one, MIN over the blocks
+        for zv, exp in ((zb, -1), (zbad, want_bad)):
+            parts = [shard.global_first_row(b.r1cs_check(zv[None]), lo) for b, lo in zip(backs, row0)]
+            ff = np.minimum.reduce(parts)
+            assert (-1 if ff[0] == shard.NO_FAIL else int(ff[0])) == exp
+        for b in backs:
+            b.r1cs_upload(zb[None])
+        def one(b):
+            b.r1cs_run()
+        for _ in range(2):
+            for b in backs:
+                one(b)
+        walls, kern = [], []
+        for _ in range(5):
+            th = [threading.Thread(target=one, args=(b,)) for b in backs]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            walls.append((time.perf_counter() - t0) * 1e3)
+            kern.append(max(b.timing()["levels_ms"] for b in backs))
+        out[world] = {"slowest_check_kernel_ms": float(np.median(kern)), "wall_ms_concurrent_runs": float(np.median(walls))}
+        for b in backs:
+            b.close()
+    res = {"config": f"C4 R1CS 2^{log2_rows} constraints, BN254, 1 assignment, rows sharded over {n_dev} GPU(s)", "devices": n_dev,
+           "one_device": out[1], "all_devices": out[n_dev]}
+    if n_dev > 1:
+        res["kernel_speedup"] = out[1]["slowest_check_kernel_ms"] / out[n_dev]["slowest_check_kernel_ms"]
+    return res
+
+
 def c5(lo, li, batch):
     from oracle import ir, sieve_fbs as F, workloads as wl
     n_wit = 4096
@@ -236,6 +294,8 @@ if __name__ == "__main__":
         print(json.dumps(c3_sieve(14 if a.small else 22)), flush=True)
     if "c3s24" in todo:      # the headline relation as a statement: 168 messages of 100 000 gates
         print(json.dumps(c3_sieve(14 if a.small else 24)), flush=True)
+    if "c4rows" in todo:     # explicit only: wants a multi-GPU box (gpurun --gpus N)
+        print(json.dumps(c4_rows_sharded(14 if a.small else 22, 12 if a.small else 20)), flush=True)
     if "c5" in todo:
         print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 1)), flush=True)
         print(json.dumps(c5(6 if a.small else 13, 6 if a.small else 10, 64)), flush=True)
