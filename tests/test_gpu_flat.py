@@ -101,6 +101,21 @@ def test_dataflow_launch_single_witness(name, flow_min, window, monkeypatch):
     _check(c, gates, pool, p, inst, wit, 1, n_wires)
 
 
+@pytest.mark.parametrize("name", ["goldilocks", "bn254"])
+def test_all_levels_launches_beyond_the_cached_wavefront_table(name, monkeypatch):
+    """2493 wavefronts: more than the 2048 wavefront offsets the all-levels kernels keep in shared memory (the rest is read from
+    global memory) — the dataflow launch (forced on, flag-word variant included) and the barrier kernels against the oracle"""
+    c = circuits()
+    p = FIELDS[name]
+    circ = c.random_circuit(20000, 48, p, seed=41, n_tracked=6, window=3)
+    w = c.make_witnesses(circ, 1, seed=5, corrupt={0: 3})
+    for env in ({"ZKB_FLOW": "1", "ZKB_FLOW_MIN": "1", "ZKB_FLOW_WIDE": "1"}, {"ZKB_FLOW": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        v_, ref, st = _check(c, circ.gates, circ.const_pool, p, None, w, 1, circ.n_wires)
+        assert st["n_levels"] > 2048
+
+
 @pytest.mark.parametrize("tile_log2", ["0", "2", "5"])
 def test_multi_tile_batches(tile_log2, monkeypatch):
     # force small tiles so a batch takes several passes, with a ragged last tile
