@@ -732,7 +732,7 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         if (hi == lo) continue;
         const uint64_t calls = (uint64_t)pl.group_descs[hi - 1].first_call + pl.group_descs[hi - 1].n_calls;
         launch_bool_groups(c->d_group_descs + lo, hi - lo, calls, c->d_group_ops, c->d_group_tables, c->d_group_hints + pl.hint_off[d],
-                           c->d_store, g, pl.group_regs, c->sm_count, c->stream);
+                           c->d_store, g, pl.group_regs, c->sm_count, c->stream, pl.group_ops.data(), (uint32_t)pl.group_ops.size());
         (*launches)++;
         if (level_launches) (*level_launches)++;
     }

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <cooperative_groups.h>
 
@@ -892,11 +893,17 @@ k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
 // 16-byte GateOp each.  thread -> group: a host-made hint per 128 calls, then a forward walk over first_call.
 // WPT = 4 for tiles of >= 128 witnesses (a register is one 16-byte vector: one LDS.128 / STS.128 and one 512-byte warp
 // request per operand, the op fetch and the loop control are shared by four words), WPT = 1 below.
-template <int WPT>
+// PARAM_OPS: the templates' ops travel as a kernel parameter (constant bank) when they fit: an op fetch is then an indexed
+// constant load through the constant cache instead of two 16-byte loads through L1 — the kernel's busiest unit (l1tex 92 %).
+constexpr uint32_t kGroupParamOps = 256;
+struct GroupOpsParam {
+    uint4 q[2 * kGroupParamOps];
+};
+template <int WPT, bool PARAM_OPS>
 __global__ void __launch_bounds__(kGroupThreads)
 k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* __restrict__ gops,
               const uint32_t* __restrict__ tables, const uint32_t* __restrict__ hints, uint32_t* __restrict__ store,
-              uint32_t log2_words) {
+              uint32_t log2_words, const __grid_constant__ GroupOpsParam pops) {
     using V = typename Vec<WPT>::T;
     constexpr uint32_t kLog2Wpt = WPT == 4 ? 2 : 0;
     constexpr uint32_t RS = kGroupThreads * 4 * WPT;  // bytes between consecutive registers of one thread
@@ -926,8 +933,9 @@ k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t t
         for (int k = 0; k < WPT; k++) r[k] = 0;
 #pragma unroll 2
         for (uint32_t i = 0; i < h0.y; i++) {
-            const uint4 o = __ldg(op + 2 * i);      // dst_off, a_off, b_off (in units of one register row: x WPT here), fwd
-            const uint4 m = __ldg(op + 2 * i + 1);  // m_and, m_xor, m_a, m_c
+            // dst_off, a_off, b_off (in units of one register row: x WPT here), fwd  |  m_and, m_xor, m_a, m_c
+            const uint4 o = PARAM_OPS ? pops.q[2 * (h0.x + i)] : __ldg(op + 2 * i);
+            const uint4 m = PARAM_OPS ? pops.q[2 * (h0.x + i) + 1] : __ldg(op + 2 * i + 1);
             uint32_t a[WPT], b[WPT];
             if (o.w & 1) {
 #pragma unroll
@@ -1269,12 +1277,15 @@ void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, 
 }
 
 void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* gops, const uint32_t* tables,
-                        const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s) {
+                        const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s,
+                        const GroupOp* host_ops, uint32_t n_host_ops) {
     if (n_groups == 0 || total_calls == 0) return;
     static std::atomic<uint64_t> attr_seen{0};
     if (first_on_device(attr_seen)) {  // up to kMaxTemplateRegs x 256 threads x 16 bytes
-        cudaFuncSetAttribute(k_bool_groups<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 4));
-        cudaFuncSetAttribute(k_bool_groups<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 16));
+        cudaFuncSetAttribute(k_bool_groups<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 4));
+        cudaFuncSetAttribute(k_bool_groups<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 16));
+        cudaFuncSetAttribute(k_bool_groups<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 4));
+        cudaFuncSetAttribute(k_bool_groups<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxTemplateRegs * kGroupThreads * 16));
     }
     const uint32_t log2_words = g.log2_wt - 5;
     const bool wide = log2_words >= 2;
@@ -1282,8 +1293,17 @@ void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t tota
     const uint64_t total = total_calls << (wide ? log2_words - 2 : log2_words);
     const uint64_t tiles = (total + kGroupThreads - 1) / kGroupThreads;
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)sm_count * 64);
-    if (wide) k_bool_groups<4><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words);
-    else k_bool_groups<1><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words);
+    static GroupOpsParam none{};
+    const bool in_params = host_ops != nullptr && n_host_ops <= kGroupParamOps && getenv("ZKB_GROUP_OPS_GLOBAL") == nullptr;
+    if (in_params) {
+        GroupOpsParam pp;
+        memcpy(pp.q, host_ops, (size_t)n_host_ops * sizeof(GroupOp));
+        if (wide) k_bool_groups<4, true><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words, pp);
+        else k_bool_groups<1, true><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words, pp);
+    } else {
+        if (wide) k_bool_groups<4, false><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words, none);
+        else k_bool_groups<1, false><<<grid, kGroupThreads, smem, s>>>(descs, n_groups, total_calls, gops, tables, hints, store, log2_words, none);
+    }
 }
 
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,

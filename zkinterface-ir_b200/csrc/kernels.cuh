@@ -79,7 +79,8 @@ void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, 
                        uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, int sm_count, cudaStream_t s);
 // call groups of one depth (program.h): n_regs = the widest template's register count
 void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* gops, const uint32_t* tables,
-                        const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s);
+                        const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s,
+                        const GroupOp* host_ops, uint32_t n_host_ops);  // host copy of all templates' ops: sent as a kernel parameter when small
 void launch_bool_read_values(const uint32_t* slots, uint32_t n, const uint32_t* store, uint32_t lane, uint32_t log2_wt,
                              uint32_t* out, cudaStream_t s);
 
