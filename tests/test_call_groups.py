@@ -164,7 +164,7 @@ class Rel:
 def build(seed, raw=False, failing=False):
     r = Rel(seed, raw_witness=raw)
     kinds = ["plain", "plain", "plain", "not_on_input", "assert", "copy", "raw_const"]
-    fs = [r.function(f"f{k}", r.ri(1, 3), r.ri(1, 4), kinds[k % len(kinds)] if k else "plain") for k in range(r.ri(2, 5))]
+    fs = [r.function(f"f{k}", r.ri(1, 3), r.ri(1, 8) if k % 2 else r.ri(1, 4), kinds[k % len(kinds)] if k else "plain") for k in range(r.ri(2, 5))]
     r.witnesses()
     r.loop(fs[0], allow_div=False)
     for k in range(r.ri(2, 6)):

@@ -922,11 +922,22 @@ k_bool_groups(const GroupDesc* __restrict__ descs, uint32_t n_groups, uint64_t t
         const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);  // n_calls, out_slot, first_call, pad
         const uint32_t call = call_g - h1.z;
         uint8_t* Rin = R + h0.z * RS;
-        for (uint32_t k = 0; k < h0.w; k++) {
-            const uint32_t base = __ldg(&d->in_base[k]), st = __ldg(&d->in_stride[k]);
-            const uint32_t slot = st == kTableStride ? __ldg(tables + base + call) : base + st * call;
-            *reinterpret_cast<V*>(Rin + k * RS) = vstore[((size_t)slot << log2_vecs) + vw];
-        }
+        // the operand progressions four at a time (one 16-byte load for four bases, one for four strides)
+        static_assert(kMaxGroupInputs == 8, "two halves of four");
+        auto gather4 = [&](uint32_t k0) {
+            const uint4 bq = __ldg(reinterpret_cast<const uint4*>(d->in_base + k0));
+            const uint4 sq = __ldg(reinterpret_cast<const uint4*>(d->in_stride + k0));
+            const uint32_t bs[4] = {bq.x, bq.y, bq.z, bq.w}, ss[4] = {sq.x, sq.y, sq.z, sq.w};
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                if (k0 + k < h0.w) {
+                    const uint32_t slot = ss[k] == kTableStride ? __ldg(tables + bs[k] + call) : bs[k] + ss[k] * call;
+                    *reinterpret_cast<V*>(Rin + (k0 + k) * RS) = vstore[((size_t)slot << log2_vecs) + vw];
+                }
+            }
+        };
+        gather4(0);
+        if (h0.w > 4) gather4(4);
         const uint4* op = reinterpret_cast<const uint4*>(gops + h0.x);
         uint32_t r[WPT];  // the previous op's result stays in registers: an operand that names it is not re-read (GroupOp::fwd)
 #pragma unroll
