@@ -193,6 +193,8 @@ typedef struct {
     uint64_t n_group_launches;     /* after finalize: kernel launches that expand them (one per dependency depth) */
     uint64_t n_group_table_slots;  /* after finalize: operand slots listed explicitly (inputs whose slots are not an
                                     * arithmetic progression over the calls) */
+    int64_t group_jit_state;       /* the groups' run-time specialised kernel: -2 none, -1 unavailable (the interpreter kernel
+                                    * runs), 0 compiling in the background, 2 compiled, 3 loaded and in use */
 } zkb_stats;
 int zkb_get_stats(zkb_ctx* ctx, zkb_stats* out);
 
@@ -322,6 +324,11 @@ int zkb_r1cs_run(zkb_ctx* ctx, zkb_verdict* out);
  * field_throughput: register-resident dependent chains of `iters` operations per thread -> operations/s. */
 int zkb_debug_field_ops(zkb_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, uint32_t* r, uint64_t n);
 int zkb_debug_field_throughput(zkb_ctx* ctx, int op, uint32_t iters, double* ops_per_second);
+/* Call groups are expanded by an interpreter kernel at first; meanwhile their templates are compiled (NVRTC, background thread)
+ * into a kernel that keeps a call's registers in registers, used from the next evaluation after it is ready.  This call
+ * blocks until the compilation has ended (state as in zkb_stats.group_jit_state); _source returns the generated CUDA. */
+int zkb_debug_group_jit_wait(zkb_ctx* ctx, int* state, double* compile_seconds);
+const char* zkb_debug_group_jit_source(zkb_ctx* ctx);
 /* random 32-byte gathers (8 in flight per thread, L2-only loads) from a table of table_bytes: bytes gathered per second —
  * the ceiling of the one-assignment R1CS check, whose traffic is z[col] look-ups in a vector larger than L2 */
 int zkb_debug_gather_throughput(zkb_ctx* ctx, uint64_t table_bytes, uint32_t iters, double* bytes_per_second);

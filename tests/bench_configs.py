@@ -215,6 +215,9 @@ def c5(lo, li, batch):
         probe = [n_wit + k for k in (0, 1, 12345 % (block << lo), block * 3 + 7)]
         got = b.read_values(j, [ev.value_handle(w_) for w_ in probe], 4)
         assert got == [int(outs.reshape(-1)[w_ - n_wit]) for w_ in probe]
+    # the groups' templates are being compiled into a specialised kernel in the background (group_jit.cpp): steady state =
+    # after that has ended; ZKB_GROUP_JIT=0 times the interpreter kernel instead
+    jit_state, jit_s = b.wait_group_jit()
     b.upload_inputs(None, W, batch)
     tot, lv = timed_runs(b.run, b.timing)
     st = b.stats()
@@ -228,6 +231,8 @@ def c5(lo, li, batch):
             "finalize_and_first_eval_s": first_s, "host_prep_s": flat_s + first_s, "values": st["n_values"],
             "call_groups": st["n_call_groups"], "group_calls": st["n_group_calls"], "device_ops": st["n_device_ops"],
             "kernel_launches": b.timing()["kernel_launches"],
+            "group_kernel": "specialised at run time (NVRTC)" if st["group_jit_state"] == 3 else "interpreter (k_bool_groups)",
+            "group_kernel_compile_s_background": jit_s,
             "descriptor_form_bytes_per_gate": 16 + 3 / 8, "grouped_bytes_per_gate": grouped_bytes / n_leaf,
             "device_GBps": grouped_bytes / (tot * 1e-3) / 1e9,
             "descriptor_form_GBps_equivalent": (16 + 3 / 8) * n_leaf / (tot * 1e-3) / 1e9}

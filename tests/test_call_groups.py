@@ -268,6 +268,22 @@ def table_relation(seed=5, n=40):
     return r, n_w
 
 
+def test_specialised_group_kernel_is_generated_and_compiles(monkeypatch):
+    """group_jit.cpp without a device: the templates of random relations as straight-line CUDA, compiled by NVRTC for
+    sm_100a in the calling thread (ZKB_GROUP_JIT=2); every template of the plan is a case of the generated switch"""
+    monkeypatch.setenv("ZKB_GROUP_JIT", "2")
+    for seed in (0, 3, 8):
+        r = build(seed)
+        b, e = record(-1, r.messages(r.witness()))
+        b.finalize(True)
+        state, seconds = b.wait_group_jit()
+        if state == -1:
+            pytest.skip("NVRTC is not available here")
+        assert state == 2, state
+        src = b.group_jit_source()
+        assert src.count("case ") >= 1 and "zkb_groups_w4" in src and "__shared__" not in src
+
+
 def test_c5_shape_is_one_group_per_inner_loop():
     rel, n_leaf = wl.boolean_for_relation(4, 5, 256)
     msgs = [ir.Witness(rel.header, [b"\0"] * 256), rel]
@@ -281,7 +297,17 @@ def test_c5_shape_is_one_group_per_inner_loop():
 
 
 # ----------------------------------------------------------------------------------------------------------------- GPU
-def check_against_oracle(r, w, exact_groups=None):
+def use_jit(b, jit):
+    """jit: wait for the groups' specialised kernel (group_jit.cpp) so that the evaluation that follows runs it;
+    returns False when this box cannot compile it (no NVRTC: the interpreter kernel stays in charge)"""
+    if not jit:
+        return False
+    state, _ = b.wait_group_jit()
+    assert state in (2, 3, -1), state
+    return state != -1
+
+
+def check_against_oracle(r, w, exact_groups=None, jit=False):
     msgs = r.messages(w)
     expected = ev.evaluate(msgs)
     b, e = record(0, msgs)
@@ -290,7 +316,9 @@ def check_against_oracle(r, w, exact_groups=None):
     else:
         assert b.stats()["n_call_groups"] == exact_groups
     b.finalize(True)
+    jitted = use_jit(b, jit)
     assert e.get_violations() == expected
+    assert b.stats()["group_jit_state"] == (3 if jitted else b.stats()["group_jit_state"])
     o = ev.Evaluator.from_messages(msgs, ev.PlaintextBackend())
     if expected == []:
         for wid, val in o.values.items():
@@ -298,27 +326,37 @@ def check_against_oracle(r, w, exact_groups=None):
     return b, e, o
 
 
+@pytest.fixture(params=["interpreter", "specialised"])
+def jit(request, monkeypatch):
+    """both expansions of a call group: the interpreter kernel (k_bool_groups; ZKB_GROUP_JIT=0 keeps the background
+    compilation from taking over mid-test) and the run-time specialised kernel (waited for before the evaluation)"""
+    if request.param == "interpreter":
+        monkeypatch.setenv("ZKB_GROUP_JIT", "0")
+        return False
+    return True
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", SEEDS)
-def test_gpu_values_and_verdicts(seed):
+def test_gpu_values_and_verdicts(seed, jit):
     r = build(seed)
-    check_against_oracle(r, r.witness())
+    check_against_oracle(r, r.witness(), jit=jit)
 
 
 @pytest.mark.gpu
-def test_gpu_slot_tables():
+def test_gpu_slot_tables(jit):
     r, _ = table_relation()
     for trial in range(4):
-        check_against_oracle(r, r.witness(), exact_groups=2)
+        check_against_oracle(r, r.witness(), exact_groups=2, jit=jit)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", [100, 101, 102, 103, 104, 105])
-def test_gpu_raw_witness_values(seed):
+def test_gpu_raw_witness_values(seed, jit):
     """witness bytes 0..4: And / Xor / Add / Mul inside a call see the raw integers' low bits (evaluator.rs:908-930), the
     Not / AssertZero outside see what the calls computed"""
     r = build(seed, raw=True)
-    check_against_oracle(r, r.witness())
+    check_against_oracle(r, r.witness(), jit=jit)
 
 
 @pytest.mark.gpu
@@ -334,12 +372,13 @@ def test_gpu_failing_assertion_on_a_group_output(seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_batch", [1, 33, 64, 100, 128, 300, 1000])
-def test_gpu_batches_bit_sliced(n_batch):
+def test_gpu_batches_bit_sliced(n_batch, jit):
     """one recording, n_batch witnesses (ragged last word / tile): verdict per witness and probed values vs the oracle"""
     r = build(7, failing=True)
     w0 = r.witness()
     b, e = record(0, r.messages(w0))
     b.finalize(True)
+    use_jit(b, jit)
     rng = np.random.default_rng(n_batch)
     W = rng.integers(0, 2, size=(n_batch, r.n_wit, 1)).astype(np.uint8)
     v = b.evaluate(None, W, n_batch)
@@ -355,7 +394,7 @@ def test_gpu_batches_bit_sliced(n_batch):
 
 
 @pytest.mark.gpu
-def test_gpu_c5_grouped_equals_serial():
+def test_gpu_c5_grouped_equals_serial(jit):
     """the C5 relation both ways on the device: same verdicts and outputs for 64 witnesses"""
     lo, li, n_wit = 5, 6, 512
     rel, _ = wl.boolean_for_relation(lo, li, n_wit)
@@ -367,7 +406,10 @@ def test_gpu_c5_grouped_equals_serial():
         b, e = record(0, msgs, no_groups=no_groups)
         assert (b.stats()["n_call_groups"] == 0) == no_groups
         b.finalize(True)
+        jitted = use_jit(b, jit and not no_groups)
         v = b.evaluate(None, W, 64)
+        if jitted:
+            assert b.stats()["group_jit_state"] == 3
         n_out = (1 << lo) * (2 << li)
         vals = [b.read_values(j, [e.value_handle(n_wit + k) for k in range(n_out)], 4) for j in (0, 31, 32, 63)]
         res.append(([bool(x["ok"]) for x in v], vals))

@@ -50,7 +50,7 @@ class ZkbStats(C.Structure):
                 ("n_device_ops", C.c_uint64), ("algo_bytes_per_witness", C.c_uint64), ("nlimb", C.c_uint32),
                 ("binary", C.c_uint32), ("tile_witnesses", C.c_uint32), ("n_tiles", C.c_uint32),
                 ("n_call_groups", C.c_uint64), ("n_group_calls", C.c_uint64),
-                ("n_group_launches", C.c_uint64), ("n_group_table_slots", C.c_uint64)]
+                ("n_group_launches", C.c_uint64), ("n_group_table_slots", C.c_uint64), ("group_jit_state", C.c_int64)]
 
 
 class ZkbTiming(C.Structure):
@@ -78,7 +78,7 @@ EXPORTED = [
     "zkb_validator_ingest_buffer", "zkb_validator_ingest_paths", "zkb_validator_get_violations", "zkb_validator_violation",
     "zkb_validator_how_many_violations", "zkb_validator_live_wires", "zkb_validator_set_limits", "zkb_validator_last_error", "zkb_metrics_create", "zkb_metrics_destroy", "zkb_metrics_ingest_message",
     "zkb_metrics_ingest_buffer", "zkb_metrics_ingest_paths", "zkb_metrics_json", "zkb_metrics_last_error", "zkb_r1cs_load", "zkb_r1cs_check",
-    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_gather_throughput", "zkb_debug_barrier_cost", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_plan_hash", "zkb_debug_write_flat_relation",
+    "zkb_r1cs_upload", "zkb_r1cs_run", "zkb_debug_field_ops", "zkb_debug_field_throughput", "zkb_debug_group_jit_wait", "zkb_debug_group_jit_source", "zkb_debug_gather_throughput", "zkb_debug_barrier_cost", "zkb_debug_r1cs_layout", "zkb_debug_rewrite_message", "zkb_debug_plan_hash", "zkb_debug_write_flat_relation",
     "zkb_comm_unique_id", "zkb_comm_init_rank", "zkb_comm_init", "zkb_comm_info", "zkb_comm_broadcast_program", "zkb_comm_evaluate",
     "zkb_comm_run", "zkb_evaluate_sharded", "zkb_run_sharded",
 ]
@@ -165,6 +165,8 @@ _sig("zkb_r1cs_upload", _i, _vp, _u8p, _u64, _u32, _u32)
 _sig("zkb_r1cs_run", _i, _vp, _vp)
 _sig("zkb_debug_field_ops", _i, _vp, _i, _vp, _vp, _vp, _u64)
 _sig("zkb_debug_field_throughput", _i, _vp, _i, _u32, C.POINTER(C.c_double))
+_sig("zkb_debug_group_jit_wait", _i, _vp, C.POINTER(C.c_int), C.POINTER(C.c_double))
+_sig("zkb_debug_group_jit_source", C.c_char_p, _vp)
 _sig("zkb_debug_gather_throughput", _i, _vp, _u64, _u32, C.POINTER(C.c_double))
 _sig("zkb_debug_barrier_cost", _i, _vp, _i, _u32, _u32, C.POINTER(C.c_double))
 _sig("zkb_debug_r1cs_layout", _i, _vp, _i, _u64p, _vp, _vp, _vp)
@@ -475,6 +477,16 @@ class GpuBackend:
         r = np.zeros_like(a)
         self._chk(_lib.zkb_debug_field_ops(self._c, op, _buf(a), _buf(b), _buf(r), a.shape[0]))
         return r
+
+    def wait_group_jit(self):
+        """block until the background compilation of the call groups' specialised kernel has ended -> (state, seconds):
+        2 compiled (used from the next evaluation on), 3 loaded, -1 unavailable (the interpreter kernel stays), -2 no groups"""
+        st, sec = C.c_int(), C.c_double()
+        self._chk(_lib.zkb_debug_group_jit_wait(self._c, C.byref(st), C.byref(sec)))
+        return st.value, sec.value
+
+    def group_jit_source(self) -> str:
+        return (_lib.zkb_debug_group_jit_source(self._c) or b"").decode()
 
     def debug_field_throughput(self, op: int, iters: int = 2000) -> float:
         out = C.c_double()

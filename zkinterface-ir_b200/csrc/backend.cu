@@ -65,7 +65,9 @@ int ctx_upload_groups(zkb_ctx* c) {
     if ((rc = upload_vec(c, c->d_group_descs, c->plan.group_descs)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_group_ops, c->plan.group_ops)) != ZKB_OK) return rc;
     if ((rc = upload_vec(c, c->d_group_tables, c->plan.group_tables)) != ZKB_OK) return rc;
-    return upload_vec(c, c->d_group_hints, c->plan.group_hints);
+    if ((rc = upload_vec(c, c->d_group_hints, c->plan.group_hints)) != ZKB_OK) return rc;
+    group_jit_start(c);  // the templates as straight-line code, compiled in the background (group_jit.cpp)
+    return ZKB_OK;
 }
 
 int ctx_finalize(zkb_ctx* c, int keep_values) {
@@ -91,7 +93,10 @@ int ctx_finalize(zkb_ctx* c, int keep_values) {
     c->finalized = true;
     c->resident_tile = -1;
     c->inputs_uploaded = false;
-    if (!c->has_gpu) return ZKB_OK;  // host-only context: plan can be inspected, not run
+    if (!c->has_gpu) {  // host-only context: plan can be inspected, not run (ZKB_GROUP_JIT=2: and its group kernel generated + compiled)
+        group_jit_start(c);
+        return ZKB_OK;
+    }
     NvtxRange r_up("zkb:program_upload");
     int rc;
     if ((rc = upload_vec(c, c->d_ops, c->plan.ops)) != ZKB_OK) return rc;
@@ -194,6 +199,7 @@ extern "C" void zkb_destroy(zkb_ctx* c) {
         cudaFree(c->d_tab_kind);
         r1cs_free(c);
         comm_free(c);
+        group_jit_free(c);
         for (int i = 0; i < 4; i++)
             if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         for (auto e : c->tile_ev) cudaEventDestroy(e);
@@ -731,8 +737,9 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
         const uint32_t lo = pl.depth_off[d], hi = pl.depth_off[d + 1];
         if (hi == lo) continue;
         const uint64_t calls = (uint64_t)pl.group_descs[hi - 1].first_call + pl.group_descs[hi - 1].n_calls;
-        launch_bool_groups(c->d_group_descs + lo, hi - lo, calls, c->d_group_ops, c->d_group_tables, c->d_group_hints + pl.hint_off[d],
-                           c->d_store, g, pl.group_regs, c->sm_count, c->stream, pl.group_ops.data(), (uint32_t)pl.group_ops.size());
+        if (!group_jit_launch(c, c->d_group_descs + lo, hi - lo, calls, c->d_group_hints + pl.hint_off[d], g.log2_wt - 5, (void*)c->stream))
+            launch_bool_groups(c->d_group_descs + lo, hi - lo, calls, c->d_group_ops, c->d_group_tables, c->d_group_hints + pl.hint_off[d],
+                               c->d_store, g, pl.group_regs, c->sm_count, c->stream, pl.group_ops.data(), (uint32_t)pl.group_ops.size());
         (*launches)++;
         if (level_launches) (*level_launches)++;
     }
@@ -1150,6 +1157,7 @@ extern "C" int zkb_get_stats(zkb_ctx* c, zkb_stats* s) {
         for (size_t d = 0; d + 1 < c->plan.depth_off.size(); d++) s->n_group_launches += c->plan.depth_off[d + 1] > c->plan.depth_off[d];
         s->n_group_table_slots = c->plan.group_tables.size();
     }
+    s->group_jit_state = (int64_t)group_jit_state(c);
     if (c->inputs_uploaded) {
         s->tile_witnesses = 1u << c->log2_wt;
         s->n_tiles = (c->n_batch + s->tile_witnesses - 1) / s->tile_witnesses;
@@ -1208,3 +1216,13 @@ extern "C" int zkb_level_info(zkb_ctx* c, uint64_t level, uint64_t out[5]) {
     }
     return ZKB_OK;
 }
+
+// the run-time specialisation of the call-group kernel (group_jit.cpp): block until its compilation has ended
+extern "C" int zkb_debug_group_jit_wait(zkb_ctx* c, int* state, double* compile_seconds) {
+    const int st = group_jit_wait(c);
+    if (state) *state = st;
+    if (compile_seconds) *compile_seconds = group_jit_compile_seconds(c);
+    if (st == -1) c->err = std::string("group kernel specialisation failed: ") + group_jit_log(c);
+    return ZKB_OK;
+}
+extern "C" const char* zkb_debug_group_jit_source(zkb_ctx* c) { return group_jit_source(c); }

@@ -121,6 +121,7 @@ public:
 
 struct R1csDev;    // r1cs.cu
 struct CommState;  // comm.cu
+struct GroupJit;   // group_jit.cpp
 
 // NVTX range over a phase of the path (host flatten / levelize / H2D / levels / D2H): shows up on the Nsight Systems and
 // ncu timelines; costs a predicted-not-taken branch when no tool is attached.
@@ -197,6 +198,7 @@ struct zkb_ctx {
     zkb_timing timing{};
 
     zkb::R1csDev* r1cs = nullptr;
+    zkb::GroupJit* gjit = nullptr;   // run-time specialisation of the call-group kernel (group_jit.cpp), if any
 
     // multi-GPU (include/zkb.h section 7): this context's rank in a communicator, and whether its program is a replica
     // received from the root rank (device plan + the host tables evaluation and read-back need; nothing was recorded here)
@@ -215,6 +217,16 @@ struct zkb_ctx {
 namespace zkb {
 // shared helpers implemented in backend.cu
 int ctx_upload_groups(zkb_ctx* c);  // plan.group_* -> device
+// group_jit.cpp
+void group_jit_start(zkb_ctx* c);
+void group_jit_free(zkb_ctx* c);
+int group_jit_wait(zkb_ctx* c);
+int group_jit_state(zkb_ctx* c);
+const char* group_jit_log(zkb_ctx* c);
+const char* group_jit_source(zkb_ctx* c);
+double group_jit_compile_seconds(zkb_ctx* c);
+bool group_jit_launch(zkb_ctx* c, const zkb::GroupDesc* d_descs, uint32_t n_groups, uint64_t total_calls, const uint32_t* d_hints,
+                      uint32_t log2_words, void* stream);
 int ctx_result_buffer(zkb_ctx* c, size_t n_words);  // c->h_res holds at least n_words
 int ctx_finalize(zkb_ctx* c, int keep_values);  // 0 live wires, 1 all values, 2 verdicts only
 bool ctx_record_ok(zkb_ctx* c);  // false when a recording error is latched
