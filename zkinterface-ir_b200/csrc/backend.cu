@@ -849,6 +849,18 @@ static void run_tile(zkb_ctx* c, uint32_t tile, uint32_t* d_fail, uint64_t* laun
     for (uint32_t l = first_level; l < pl.n_levels; l++) {
         uint64_t lo = pl.level_off[l], mid = pl.level_rare[l], hi = pl.level_off[l + 1];
         if (p.binary) {
+            // a run of wavefronts of at most 1024 items each (gate x vector of words): one CTA, one launch for the run
+            const uint32_t log2_vecs = c->log2_wt - 5 - (c->log2_wt >= 7 ? 2 : 0);
+            auto small = [&](uint32_t k) { return ((pl.level_off[k + 1] - pl.level_off[k]) << log2_vecs) <= 1024; };
+            uint32_t e = l;
+            while (e < pl.n_levels && small(e)) e++;
+            if (e - l >= 2 && !getenv("ZKB_NO_BOOL_CTA_RUNS")) {
+                launch_bool_levels_cta(c->d_ops, c->d_aseq, c->d_level_off + l, e - l, c->d_store, c->d_consts, d_fail, rawflag, g, c->stream);
+                (*launches)++;
+                if (level_launches) (*level_launches)++;
+                l = e - 1;
+                continue;
+            }
             if (hi > lo) {
                 launch_bool_level(c->d_ops + lo, c->d_aseq + lo, hi - lo, c->d_store, c->d_consts, d_fail, rawflag, g, c->sm_count, c->stream);
                 (*launches)++;

@@ -826,10 +826,10 @@ __device__ __forceinline__ uint32_t bool_gate_word(uint32_t opc, uint32_t a, uin
 // thread <-> (gate, WPT consecutive 32-witness words).  WPT = 4 (one 16-byte vector per operand, 512 bytes per warp
 // request) whenever a tile holds at least 128 witnesses; WPT = 1 for narrower tiles.
 template <int WPT>
-__global__ void __launch_bounds__(256)
-k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
-             const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag,
-             TileGeom g) {
+__device__ __forceinline__ void bool_level_items(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops,
+                                                 uint32_t* __restrict__ store, const uint32_t* __restrict__ const_bits,
+                                                 uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag, const TileGeom& g,
+                                                 uint64_t tid0, uint64_t stride) {
     using V = typename Vec<WPT>::T;
     constexpr uint32_t kLog2Wpt = WPT == 4 ? 2 : 0;
     const uint32_t log2_words = g.log2_wt - 5;
@@ -837,8 +837,7 @@ k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
     const uint64_t total = n_ops << log2_vecs;
     const uint32_t vmask = (1u << log2_vecs) - 1;
     V* vstore = reinterpret_cast<V*>(store);
-    for (uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; tid < total;
-         tid += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t tid = tid0; tid < total; tid += stride) {
         const uint32_t vw = (uint32_t)tid & vmask;
         const uint64_t gi = tid >> log2_vecs;
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ops) + gi);
@@ -882,6 +881,28 @@ k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, 
                 }
             }
         }
+    }
+}
+template <int WPT>
+__global__ void __launch_bounds__(256)
+k_bool_level(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, uint64_t n_ops, uint32_t* __restrict__ store,
+             const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail, const uint8_t* __restrict__ rawflag,
+             TileGeom g) {
+    bool_level_items<WPT>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g, blockIdx.x * (uint64_t)blockDim.x + threadIdx.x,
+                          (uint64_t)gridDim.x * blockDim.x);
+}
+// A run of consecutive wavefronts that each fit ONE CTA (the Xor chain behind C5's loops: one gate per wavefront): one launch,
+// __syncthreads() between the wavefronts (one CTA: its global writes are visible to its own threads after the barrier)
+// instead of one launch each.
+template <int WPT>
+__global__ void __launch_bounds__(256)
+k_bool_levels_cta(const GateOp* __restrict__ ops, const uint32_t* __restrict__ aseq, const uint64_t* __restrict__ level_off, uint32_t n_levels,
+                  uint32_t* store, const uint32_t* __restrict__ const_bits, uint32_t* __restrict__ first_fail,
+                  const uint8_t* __restrict__ rawflag, TileGeom g) {
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint64_t lo = level_off[l], hi = level_off[l + 1];
+        bool_level_items<WPT>(ops + lo, aseq + lo, hi - lo, store, const_bits, first_fail, rawflag, g, threadIdx.x, blockDim.x);
+        __syncthreads();
     }
 }
 
@@ -1285,6 +1306,13 @@ void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, 
         unsigned grid = grid_for(n_ops << (g.log2_wt - 5), sm_count, grid_per_sm(256));
         k_bool_level<1><<<grid, 256, 0, s>>>(ops, aseq, n_ops, store, const_bits, first_fail, rawflag, g);
     }
+}
+
+void launch_bool_levels_cta(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
+                            const uint32_t* const_bits, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, cudaStream_t s) {
+    if (n_levels == 0) return;
+    if (g.log2_wt >= 7) k_bool_levels_cta<4><<<1, 256, 0, s>>>(ops, aseq, level_off, n_levels, store, const_bits, first_fail, rawflag, g);
+    else k_bool_levels_cta<1><<<1, 256, 0, s>>>(ops, aseq, level_off, n_levels, store, const_bits, first_fail, rawflag, g);
 }
 
 void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* gops, const uint32_t* tables,

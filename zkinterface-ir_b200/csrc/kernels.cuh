@@ -77,6 +77,9 @@ void launch_bool_load_inputs(const InputLoad* loads, uint32_t n_loads, uint32_t*
                              cudaStream_t s);
 void launch_bool_level(const GateOp* ops, const uint32_t* aseq, uint64_t n_ops, uint32_t* store, const uint32_t* const_bits,
                        uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, int sm_count, cudaStream_t s);
+// a run of wavefronts that each fit one CTA, in one launch (level_off: offsets into ops, relative to `ops`' own origin)
+void launch_bool_levels_cta(const GateOp* ops, const uint32_t* aseq, const uint64_t* level_off, uint32_t n_levels, uint32_t* store,
+                            const uint32_t* const_bits, uint32_t* first_fail, const uint8_t* rawflag, TileGeom g, cudaStream_t s);
 // call groups of one depth (program.h): n_regs = the widest template's register count
 void launch_bool_groups(const GroupDesc* descs, uint32_t n_groups, uint64_t total_calls, const GroupOp* gops, const uint32_t* tables,
                         const uint32_t* hints, uint32_t* store, TileGeom g, uint32_t n_regs, int sm_count, cudaStream_t s,
